@@ -1,0 +1,34 @@
+"""`_gridencoder` — same entry points as the reference pybind module (gridencoder/src/bindings.cpp:5-9),
+backed by the C-ABI.  Positional signatures match gridencoder/src/gridencoder.h:12-15, so the reference's
+own gridencoder/grid.py runs unmodified against this module (see pienerf_b200.dropin)."""
+import torch
+
+from . import _lib
+from ._lib import check, dptr, lib, stream_ptr
+
+
+def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, dy_dx, gridtype, align_corners, interp):
+    # reference checks: CUDA + contiguous + dtype (gridencoder.cu:449-465)
+    _lib._chk(inputs, "inputs", (torch.float32, torch.float16, torch.float64))
+    _lib._chk(embeddings, "embeddings", (torch.float32, torch.float16, torch.float64))
+    _lib._chk(offsets, "offsets", torch.int32)
+    _lib._chk(outputs, "outputs", (torch.float32, torch.float16, torch.float64))
+    if inputs.dtype != torch.float32:
+        raise RuntimeError("inputs must be float32 (the reference reads inputs.data_ptr<float>())")
+    if embeddings.dtype == torch.float64:
+        raise NotImplementedError("double embeddings are not part of the B200 hot path")
+    if outputs.dtype != embeddings.dtype:
+        raise RuntimeError("outputs must have the dtype of embeddings")
+    if int(C) not in (1, 2, 4, 8):
+        raise RuntimeError("GridEncoding: C must be 1, 2, 4, or 8.")
+    check(lib.pn_grid_encode_forward(dptr(inputs), dptr(embeddings), dptr(offsets), dptr(outputs), int(B), int(D), int(C),
+                                     int(L), float(S), int(H), dptr(dy_dx), int(gridtype), int(bool(align_corners)),
+                                     int(interp), int(embeddings.dtype == torch.float16), stream_ptr()))
+
+
+def grid_encode_backward(*args):
+    check(lib.pn_grid_encode_backward())
+
+
+def grad_total_variation(*args):
+    check(lib.pn_grad_total_variation())

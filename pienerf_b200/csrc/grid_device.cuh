@@ -1,0 +1,99 @@
+// Device-side multiresolution hash-grid lookup shared by the stand-alone encoder kernel and the
+// fused field / render kernels.  Arithmetic follows gridencoder/src/gridencoder.cu:50-197 of the
+// reference operation-for-operation (same rounding points) so results are bit-comparable; the
+// scheduling around it is ours.
+#pragma once
+#include "common.cuh"
+
+namespace pn {
+
+__device__ __forceinline__ uint32_t grid_primes(uint32_t d) {
+    // spatial-hash primes of the reference (gridencoder.cu:54)
+    switch (d) {
+        case 0: return 1u;
+        case 1: return 2654435761u;
+        case 2: return 805459861u;
+        case 3: return 3674653429u;
+        case 4: return 2097192037u;
+        case 5: return 1434869437u;
+        default: return 2165219737u;
+    }
+}
+
+struct LevelGeom {
+    float scale;          // exp2f(level*S)*H - 1
+    uint32_t resolution;  // ceil(scale)+1
+    uint32_t size;        // entries in this level (offsets[l+1]-offsets[l])
+    uint32_t stride1;     // resolution (+1 unless align_corners)
+    bool dense3;          // D=3: all three axes index linearly (no hashing, no early stop)
+};
+
+__device__ __forceinline__ LevelGeom level_geom(uint32_t level, float S, uint32_t H, const int *__restrict__ offsets,
+                                                bool align_corners) {
+    LevelGeom g;
+    g.scale = exp2f(level * S) * H - 1.0f;
+    g.resolution = (uint32_t)ceilf(g.scale) + 1;
+    g.size = (uint32_t)(offsets[level + 1] - offsets[level]);
+    g.stride1 = align_corners ? g.resolution : g.resolution + 1;
+    g.dense3 = (uint64_t)g.stride1 * g.stride1 * g.stride1 <= (uint64_t)g.size;
+    return g;
+}
+
+// entry index (not yet multiplied by C) of one grid vertex; gridencoder.cu:66-84
+template <uint32_t D>
+__device__ __forceinline__ uint32_t vertex_index(const uint32_t (&v)[D], const LevelGeom &g, uint32_t gridtype) {
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        if (stride <= g.size) {
+            index += v[d] * stride;
+            stride *= g.stride1;
+        }
+    }
+    if (gridtype == 0 && stride > g.size) {
+        uint32_t h = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) h ^= v[d] * grid_primes(d);
+        index = h;
+    }
+    return index % g.size;
+}
+
+// Trilinear lookup of one level for D=3, C=2, fp32 table, linear interpolation: the hot instantiation.
+// x01 in [0,1] (caller handles the out-of-range -> zeros rule).  `tab` points at the level's first entry.
+__device__ __forceinline__ float2 lookup3_c2(const float2 *__restrict__ tab, const LevelGeom &g, float x, float y,
+                                             float z, uint32_t gridtype = 0) {
+    float px = x * g.scale + 0.5f, py = y * g.scale + 0.5f, pz = z * g.scale + 0.5f;
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    px -= fx; py -= fy; pz -= fz;
+    const uint32_t gx = (uint32_t)fx, gy = (uint32_t)fy, gz = (uint32_t)fz;
+    float2 v[8];
+    if (g.dense3) {
+        const uint32_t s1 = g.stride1, s2 = g.stride1 * g.stride1;
+        const uint32_t base = gx + gy * s1 + gz * s2;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            uint32_t idx = base + (c & 1) + ((c >> 1) & 1) * s1 + ((c >> 2) & 1) * s2;
+            v[c] = __ldg(tab + idx);  // idx < stride1^3 <= size
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint32_t vv[3] = {gx + (c & 1), gy + ((c >> 1) & 1), gz + ((c >> 2) & 1)};
+            v[c] = __ldg(tab + vertex_index<3>(vv, g, gridtype));
+        }
+    }
+    float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        float w = 1.0f;
+        w *= (c & 1) ? px : 1.0f - px;
+        w *= (c & 2) ? py : 1.0f - py;
+        w *= (c & 4) ? pz : 1.0f - pz;
+        r.x += w * v[c].x;
+        r.y += w * v[c].y;
+    }
+    return r;
+}
+
+}  // namespace pn

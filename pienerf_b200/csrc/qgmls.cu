@@ -1,0 +1,752 @@
+// Q-GMLS elastodynamics kernels (fp64) — the `_qgmls` operator set.
+//
+// The reference runs these as Warp kernels launched from Python (simulator/cuda_utils.py, cpu_utils.py) plus
+// dense torch mat-vecs on (Mat (x) I3) (simulator/solver.py:574-602).  Here:
+//   * shape functions / assembly (init): one thread per point resp. per (IP, row) — init-time, not tuned;
+//   * local step: one WARP per IP gathers its 80 DOF vectors, reduces F with shuffles, lane 0 does the 3x3
+//     SVD + projections and writes the 3x3 stress  dx^3 (mu R + lam V);
+//   * rhs: deterministic gather over the kernel->(IP,corner) CSR (the adjacency the reference builds at
+//     solver.py:279-313 but never uses) — one warp per DOF row, no fp64 atomics, bit-reproducible;
+//   * global step: compact [n,n] x [n,3] mat-vec (the reference streams the 9x larger (x)I3 matrix),
+//     one warp per row, 128-bit loads, shuffle reduction;
+//   * optional PCG on the assembled system instead of the pre-inverted matrix (warp-shuffle dot products);
+//   * ip_info: emits the renderer's packed fp32 IP state (pos, F, dF layouts) directly.
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------- func_utils.py equivalents
+__device__ __forceinline__ int sym_slot(int x, int y) {  // func_utils.py:73-81
+    if (x > y) { const int t = x; x = y; y = t; }
+    return x == 0 ? 4 + y : 5 + x + y;
+}
+__device__ __forceinline__ void basis0(const double *p, double *a) {  // func_utils.py:84-92
+    a[0] = 1; a[1] = p[0]; a[2] = p[1]; a[3] = p[2];
+    a[4] = p[0] * p[0]; a[5] = p[0] * p[1]; a[6] = p[0] * p[2];
+    a[7] = p[1] * p[1]; a[8] = p[1] * p[2]; a[9] = p[2] * p[2];
+}
+__device__ __forceinline__ void basis1(const double *p, int j, double *a) {  // func_utils.py:95-103
+    for (int i = 0; i < 10; i++) a[i] = 0;
+    a[j + 1] = 1.0;
+    for (int i = 0; i < 3; i++) a[sym_slot(i, j)] = p[i];
+    a[sym_slot(j, j)] += p[j];
+}
+__device__ __forceinline__ void basis2(int j, int k, double *a) {  // func_utils.py:106-112
+    for (int i = 0; i < 10; i++) a[i] = 0;
+    a[sym_slot(j, k)] = (j == k) ? 2.0 : 1.0;
+}
+__device__ __forceinline__ void mv10(const double *A, const double *v, double *o) {
+    for (int i = 0; i < 10; i++) {
+        double s = 0;
+        for (int j = 0; j < 10; j++) s += A[i * 10 + j] * v[j];
+        o[i] = s;
+    }
+}
+__device__ __forceinline__ double dot10(const double *a, const double *b) {
+    double s = 0;
+    for (int i = 0; i < 10; i++) s += a[i] * b[i];
+    return s;
+}
+// in-place Gauss-Jordan inverse of a 10x10 (partial pivoting); returns false when singular
+__device__ bool invert10(double *A, double *Ai) {
+    for (int i = 0; i < 100; i++) Ai[i] = (i / 10 == i % 10) ? 1.0 : 0.0;
+    for (int c = 0; c < 10; c++) {
+        int piv = c;
+        double best = fabs(A[c * 10 + c]);
+        for (int r = c + 1; r < 10; r++) { const double v = fabs(A[r * 10 + c]); if (v > best) { best = v; piv = r; } }
+        if (best == 0.0) return false;
+        if (piv != c)
+            for (int j = 0; j < 10; j++) {
+                double t = A[c * 10 + j]; A[c * 10 + j] = A[piv * 10 + j]; A[piv * 10 + j] = t;
+                t = Ai[c * 10 + j]; Ai[c * 10 + j] = Ai[piv * 10 + j]; Ai[piv * 10 + j] = t;
+            }
+        const double ip = 1.0 / A[c * 10 + c];
+        for (int j = 0; j < 10; j++) { A[c * 10 + j] *= ip; Ai[c * 10 + j] *= ip; }
+        for (int r = 0; r < 10; r++) {
+            if (r == c) continue;
+            const double f = A[r * 10 + c];
+            if (f == 0.0) continue;
+            for (int j = 0; j < 10; j++) { A[r * 10 + j] -= f * A[c * 10 + j]; Ai[r * 10 + j] -= f * Ai[c * 10 + j]; }
+        }
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------- shape functions (init)
+// cpu_utils.py:3-152 for one point per thread.  Uses the algebraically equivalent compact form
+//   dGp_x = Gi (P_x - dG_x Gp),  ddGp_xy = Gi (P_xy - dG_x dGp_y - dG_y dGp_x - ddG_xy Gp)
+// of the reference's expanded product-rule chain (cpu_utils.py:75-87).
+__global__ void __launch_bounds__(64) shape_kernel(double r, const double *__restrict__ pos, const int *__restrict__ topo,
+                                                   const double *__restrict__ kpos, int n, double *__restrict__ Nx,
+                                                   double *__restrict__ dNx, double *__restrict__ ddNx,
+                                                   int *__restrict__ status) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const double p[3] = {pos[3 * v], pos[3 * v + 1], pos[3 * v + 2]};
+    double G[100], dG[3][100], ddG[6][100];  // ddG symmetric in (x,y): slots via sym index 0..5
+    for (int i = 0; i < 100; i++) {
+        G[i] = 0;
+        for (int x = 0; x < 3; x++) dG[x][i] = 0;
+        for (int x = 0; x < 6; x++) ddG[x][i] = 0;
+    }
+    auto s6 = [](int x, int y) { if (x > y) { int t = x; x = y; y = t; } return x == 0 ? y : x + y + 1; };  // 00,01,02,11,12,22
+    double wgt[8], dwg[8][3], ddwg[8][6];
+    const double r2 = r * r;
+    for (int i = 0; i < 8; i++) {
+        const double *q = kpos + 3 * topo[8 * v + i];
+        const double e[3] = {p[0] - q[0], p[1] - q[1], p[2] - q[2]};
+        const double d = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) / r;
+        if (d >= 1) { wgt[i] = 0; continue; }          // func_utils.py:43-70
+        const double s = 1.0 - d * d;
+        wgt[i] = s * s * s;
+        for (int x = 0; x < 3; x++) dwg[i][x] = -6.0 * (s * s) * e[x] / r2;
+        for (int x = 0; x < 3; x++)
+            for (int y = x; y < 3; y++)
+                ddwg[i][s6(x, y)] = -6.0 * (s * s) * (x == y ? 1.0 : 0.0) / r2 + 24.0 * s * (e[x] / r2) * (e[y] / r2);
+        if (wgt[i] <= 0.0) continue;
+        double prim[100], a[10];
+        basis0(q, a);
+        for (int x = 0; x < 10; x++) for (int y = 0; y < 10; y++) prim[x * 10 + y] = a[x] * a[y];
+        for (int j = 0; j < 3; j++) {
+            basis1(q, j, a);
+            for (int x = 0; x < 10; x++) for (int y = 0; y < 10; y++) prim[x * 10 + y] += a[x] * a[y];
+            for (int k = 0; k < 3; k++) {
+                basis2(j, k, a);
+                for (int x = 0; x < 10; x++) for (int y = 0; y < 10; y++) prim[x * 10 + y] += a[x] * a[y];
+            }
+        }
+        for (int t = 0; t < 100; t++) {
+            G[t] += wgt[i] * prim[t];
+            for (int x = 0; x < 3; x++) dG[x][t] += dwg[i][x] * prim[t];
+            for (int x = 0; x < 6; x++) ddG[x][t] += ddwg[i][x] * prim[t];
+        }
+    }
+    double Gi[100];
+    {
+        double Gw[100];
+        for (int i = 0; i < 100; i++) Gw[i] = G[i];
+        if (!invert10(Gw, Gi)) { atomicExch(status, 1); return; }
+    }
+    double Pv[10], Gp[10], dGp[3][10], ddGp[6][10], t0[10], t1[10];
+    basis0(p, Pv);
+    mv10(Gi, Pv, Gp);
+    for (int x = 0; x < 3; x++) {
+        basis1(p, x, t0);
+        mv10(dG[x], Gp, t1);
+        for (int i = 0; i < 10; i++) t0[i] -= t1[i];
+        mv10(Gi, t0, dGp[x]);
+    }
+    for (int x = 0; x < 3; x++)
+        for (int y = x; y < 3; y++) {
+            basis2(x, y, t0);
+            mv10(dG[x], dGp[y], t1);
+            for (int i = 0; i < 10; i++) t0[i] -= t1[i];
+            mv10(dG[y], dGp[x], t1);
+            for (int i = 0; i < 10; i++) t0[i] -= t1[i];
+            mv10(ddG[s6(x, y)], Gp, t1);
+            for (int i = 0; i < 10; i++) t0[i] -= t1[i];
+            mv10(Gi, t0, ddGp[s6(x, y)]);
+        }
+    // calc_weight (cpu_utils.py:108-152): slots 0, 1..3 and the 9 (x,y) second-order terms (off-diagonals twice)
+    for (int i = 0; i < 8; i++) {
+        double *N = Nx + ((size_t)v * 8 + i) * 10;
+        double *dN = dNx ? dNx + ((size_t)v * 8 + i) * 30 : nullptr;
+        double *ddN = ddNx ? ddNx + ((size_t)v * 8 + i) * 90 : nullptr;
+        for (int t = 0; t < 10; t++) N[t] = 0;
+        if (dN) for (int t = 0; t < 30; t++) dN[t] = 0;
+        if (ddN) for (int t = 0; t < 90; t++) ddN[t] = 0;
+        if (wgt[i] <= 0.0) continue;
+        const double *q = kpos + 3 * topo[8 * v + i];
+        for (int src = 0; src < 13; src++) {
+            double a[10];
+            int slot;
+            if (src == 0) { basis0(q, a); slot = 0; }
+            else if (src < 4) { basis1(q, src - 1, a); slot = src; }
+            else { const int x = (src - 4) / 3, y = (src - 4) % 3; basis2(x, y, a); slot = sym_slot(x, y); }
+            const double g = dot10(Gp, a);
+            N[slot] += g * wgt[i];
+            if (!dN) continue;
+            double gj[3];
+            for (int j = 0; j < 3; j++) { gj[j] = dot10(dGp[j], a); dN[j * 10 + slot] += g * dwg[i][j] + gj[j] * wgt[i]; }
+            if (!ddN) continue;
+            for (int j = 0; j < 3; j++)
+                for (int k = 0; k < 3; k++)
+                    ddN[(j * 3 + k) * 10 + slot] += g * ddwg[i][s6(j, k)] + gj[k] * dwg[i][j] + gj[j] * dwg[i][k] +
+                                                    dot10(ddGp[s6(j, k)], a) * wgt[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- collect_param / assembly (init)
+__global__ void collect_param_kernel(const int *__restrict__ pts_ip, const double *__restrict__ mu,
+                                     const double *__restrict__ lam, const double *__restrict__ mass, int n_pts,
+                                     double *ip_mu, double *ip_lam, double *ip_rho) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_pts) return;
+    const int ip = pts_ip[v];
+    atomicAdd(ip_mu + ip, mu[v] * mass[v]);
+    atomicAdd(ip_lam + ip, lam[v] * mass[v]);
+    atomicAdd(ip_rho + ip, mass[v]);
+}
+__global__ void finish_param_kernel(int n_ip, double dx3, double *ip_mu, double *ip_lam, double *ip_rho) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_ip) return;
+    const double m = ip_rho[v];
+    ip_mu[v] /= m; ip_lam[v] /= m; ip_rho[v] = m / dx3;      // solver.py:450
+}
+
+// one thread per (IP, local row (i,x)); loops over the 80 local columns (cuda_utils.py:22-55)
+__global__ void __launch_bounds__(128) build_ip_global_kernel(double dx, double dt, const int *__restrict__ topo,
+                                                              const double *__restrict__ mu, const double *__restrict__ lam,
+                                                              const double *__restrict__ rho, const double *__restrict__ Nx,
+                                                              const double *__restrict__ dNx, const double *__restrict__ ddNx,
+                                                              int n_ip, int n, double *mat) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_ip * 80) return;
+    const int v = id / 80, i = (id % 80) / 10, x = id % 10;
+    const double ml = (mu ? mu[v] : 0.0) + (lam ? lam[v] : 0.0), rh = rho[v];
+    const double dx3 = dx * dx * dx, dx5 = dx3 * dx * dx, dt2 = dt * dt;
+    const double c0 = rh * dx3 / dt2, c1 = dx3 * (rh * (dx * dx) / 12.0 / dt2 + ml), c2 = dx5 * ml / 12.0;
+    const double *N = Nx + (size_t)v * 80, *dN = dNx + (size_t)v * 240, *ddN = ddNx + (size_t)v * 720;
+    const int r = topo[8 * v + i] * 10 + x;
+    double ni = N[i * 10 + x], dni[3], ddni[9];
+    for (int p = 0; p < 3; p++) dni[p] = dN[(i * 3 + p) * 10 + x];
+    for (int p = 0; p < 9; p++) ddni[p] = ddN[(i * 9 + p) * 10 + x];
+    for (int j = 0; j < 8; j++)
+        for (int y = 0; y < 10; y++) {
+            double acc = c0 * ni * N[j * 10 + y];
+            for (int p = 0; p < 3; p++) acc += c1 * dni[p] * dN[(j * 3 + p) * 10 + y];
+            for (int p = 0; p < 9; p++) acc += c2 * ddni[p] * ddN[(j * 9 + p) * 10 + y];
+            atomicAdd(mat + (size_t)r * n + topo[8 * v + j] * 10 + y, acc);
+        }
+}
+
+__global__ void build_pin_global_kernel(double stiff, const int *__restrict__ vidx, int n_pin, const int *__restrict__ topo,
+                                        const double *__restrict__ Nx, int n, double *mat) {  // cuda_utils.py:58-81
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_pin * 64) return;
+    const int v = vidx[id / 64], i = (id % 64) / 8, j = id % 8;
+    const int ki = topo[8 * v + i], kj = topo[8 * v + j];
+    const double *Ni = Nx + ((size_t)v * 8 + i) * 10, *Nj = Nx + ((size_t)v * 8 + j) * 10;
+    for (int x = 0; x < 10; x++)
+        for (int y = 0; y < 10; y++) atomicAdd(mat + (size_t)(ki * 10 + x) * n + kj * 10 + y, stiff * Ni[x] * Nj[y]);
+}
+
+__global__ void collect_gravity_kernel(double dx, const int *__restrict__ topo, const double *__restrict__ Nx, double g0,
+                                       double g1, double g2, const double *__restrict__ rho, int n_ip, double *rhs) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;  // cuda_utils.py:262-279, one thread per (IP, corner, slot)
+    if (id >= n_ip * 80) return;
+    const int v = id / 80, i = (id % 80) / 10, x = id % 10;
+    const double m = rho[v] * dx * dx * dx * Nx[(size_t)v * 80 + i * 10 + x];
+    double *o = rhs + 3 * (size_t)(topo[8 * v + i] * 10 + x);
+    atomicAdd(o, m * g0); atomicAdd(o + 1, m * g1); atomicAdd(o + 2, m * g2);
+}
+
+// ---------------------------------------------------------------- local step
+// 3x3 SVD by cyclic Jacobi on F^T F; U,V proper rotations, the sign rides on sigma_2 (the wp.svd3 convention).
+__device__ void svd3x3(const double *F, double *U, double *sg, double *V) {
+    double S[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) S[i * 3 + j] = F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j];
+    double Q[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int sweep = 0; sweep < 12; sweep++) {
+        const double off = fabs(S[1]) + fabs(S[2]) + fabs(S[5]);
+        if (off <= 1e-30 * (fabs(S[0]) + fabs(S[4]) + fabs(S[8]))) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                const double apq = S[p * 3 + q];
+                if (apq == 0.0) continue;
+                const double th = (S[q * 3 + q] - S[p * 3 + p]) / (2.0 * apq);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; k++) { const double a = S[k * 3 + p], b = S[k * 3 + q]; S[k * 3 + p] = c * a - s * b; S[k * 3 + q] = s * a + c * b; }
+                for (int k = 0; k < 3; k++) { const double a = S[p * 3 + k], b = S[q * 3 + k]; S[p * 3 + k] = c * a - s * b; S[q * 3 + k] = s * a + c * b; }
+                for (int k = 0; k < 3; k++) { const double a = Q[k * 3 + p], b = Q[k * 3 + q]; Q[k * 3 + p] = c * a - s * b; Q[k * 3 + q] = s * a + c * b; }
+            }
+    }
+    double lam[3] = {S[0], S[4], S[8]};
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (lam[o1] > lam[o0]) { const int t = o0; o0 = o1; o1 = t; }
+    if (lam[o2] > lam[o0]) { const int t = o0; o0 = o2; o2 = t; }
+    if (lam[o2] > lam[o1]) { const int t = o1; o1 = o2; o2 = t; }
+    const int ord[3] = {o0, o1, o2};
+    for (int k = 0; k < 3; k++) for (int c = 0; c < 3; c++) V[k * 3 + c] = Q[k * 3 + ord[c]];
+    const double det = V[0] * (V[4] * V[8] - V[5] * V[7]) - V[1] * (V[3] * V[8] - V[5] * V[6]) + V[2] * (V[3] * V[7] - V[4] * V[6]);
+    if (det < 0) for (int k = 0; k < 3; k++) V[k * 3 + 2] = -V[k * 3 + 2];
+    double B[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) B[r * 3 + c] = F[r * 3] * V[c] + F[r * 3 + 1] * V[3 + c] + F[r * 3 + 2] * V[6 + c];
+    double u0[3], u1[3], u2[3];
+    double n0 = sqrt(B[0] * B[0] + B[3] * B[3] + B[6] * B[6]);
+    if (n0 > 0) { u0[0] = B[0] / n0; u0[1] = B[3] / n0; u0[2] = B[6] / n0; } else { u0[0] = 1; u0[1] = 0; u0[2] = 0; }
+    const double d01 = u0[0] * B[1] + u0[1] * B[4] + u0[2] * B[7];
+    u1[0] = B[1] - d01 * u0[0]; u1[1] = B[4] - d01 * u0[1]; u1[2] = B[7] - d01 * u0[2];
+    double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    if (n1 > 1e-300) { u1[0] /= n1; u1[1] /= n1; u1[2] /= n1; }
+    else {
+        const int m = fabs(u0[0]) < fabs(u0[1]) ? (fabs(u0[0]) < fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) < fabs(u0[2]) ? 1 : 2);
+        double a[3] = {0, 0, 0};
+        a[m] = 1;
+        const double d = u0[m];
+        u1[0] = a[0] - d * u0[0]; u1[1] = a[1] - d * u0[1]; u1[2] = a[2] - d * u0[2];
+        n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+        u1[0] /= n1; u1[1] /= n1; u1[2] /= n1;
+    }
+    u2[0] = u0[1] * u1[2] - u0[2] * u1[1]; u2[1] = u0[2] * u1[0] - u0[0] * u1[2]; u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+    sg[0] = lam[o0] > 0 ? sqrt(lam[o0]) : 0.0;
+    sg[1] = lam[o1] > 0 ? sqrt(lam[o1]) : 0.0;
+    sg[2] = u2[0] * B[2] + u2[1] * B[5] + u2[2] * B[8];
+    for (int r = 0; r < 3; r++) { U[r * 3] = u0[r]; U[r * 3 + 1] = u1[r]; U[r * 3 + 2] = u2[r]; }
+}
+
+__device__ __forceinline__ void volume_project(const double *sig, double *out) {  // func_utils.py:21-40
+    double D0 = 0, D1 = 0, D2 = 0;
+    for (int it = 0; it < 3; it++) {
+        const double a = sig[0] + D0, b = sig[1] + D1, c = sig[2] + D2;
+        const double C = a * b * c - 1.0;
+        const double e0 = b * c, e1 = a * c, e2 = a * b;
+        const double coef = ((e0 * D0 + e1 * D1 + e2 * D2) - C) / (e0 * e0 + e1 * e1 + e2 * e2);
+        D0 = coef * e0; D1 = coef * e1; D2 = coef * e2;
+    }
+    out[0] = sig[0] + D0; out[1] = sig[1] + D1; out[2] = sig[2] + D2;
+}
+
+// calc_elastic (cuda_utils.py:83-121): one warp per IP.  stress[v] = dx^3 (mu R + lam V)  (row-major 3x3)
+__global__ void __launch_bounds__(128) ip_stress_kernel(double dx3, const int *__restrict__ topo, const double *__restrict__ mu,
+                                                        const double *__restrict__ lam, const double *__restrict__ dNx,
+                                                        const double *__restrict__ dof, int n_ip,
+                                                        double *__restrict__ stress) {
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (v >= n_ip) return;
+    const double *dN = dNx + (size_t)v * 240;
+    double F[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int e = lane; e < 80; e += 32) {  // e = i*10 + x
+        const int i = e / 10, x = e % 10;
+        const double *d = dof + 3 * (size_t)(topo[8 * v + i] * 10 + x);
+        const double g0 = dN[(i * 3 + 0) * 10 + x], g1 = dN[(i * 3 + 1) * 10 + x], g2 = dN[(i * 3 + 2) * 10 + x];
+        const double d0 = d[0], d1 = d[1], d2 = d[2];
+        F[0] += d0 * g0; F[1] += d0 * g1; F[2] += d0 * g2;
+        F[3] += d1 * g0; F[4] += d1 * g1; F[5] += d1 * g2;
+        F[6] += d2 * g0; F[7] += d2 * g1; F[8] += d2 * g2;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+        for (int o = 16; o > 0; o >>= 1) F[k] += __shfl_xor_sync(kFull, F[k], o);
+    if (lane == 0) {
+        double U[9], sg[3], V[9], sp[3];
+        svd3x3(F, U, sg, V);
+        volume_project(sg, sp);
+        const double m = mu[v], l = lam[v];
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) {
+                double a = 0, b = 0;
+                for (int k = 0; k < 3; k++) { a += U[r * 3 + k] * V[c * 3 + k]; b += U[r * 3 + k] * sp[k] * V[c * 3 + k]; }
+                stress[(size_t)v * 9 + r * 3 + c] = dx3 * (m * a + l * b);
+            }
+    }
+}
+
+// collect_rhs_IP as a gather (cuda_utils.py:124-151 semantics, :153-188 structure): one warp per DOF row.
+// rhs[row] = sum over (ip,corner) adjacent to kernel k of stress[ip] . dN[ip,corner,:,x]
+// out = base_add[row] + sum - base_sub[row] when the optional bases are given (fuses `momentum + rhs - rhs_rest`).
+__global__ void __launch_bounds__(128) rhs_gather_kernel(const int *__restrict__ adj_bgn, const int *__restrict__ adj,
+                                                         const double *__restrict__ stress, const double *__restrict__ dNx,
+                                                         int n_rows, const double *__restrict__ base_add,
+                                                         const double *__restrict__ base_sub, double *__restrict__ out) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const int k = row / 10, x = row % 10;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int e = adj_bgn[k] + lane; e < adj_bgn[k + 1]; e += 32) {
+        const int code = adj[e], v = code >> 3, i = code & 7;
+        const double *S = stress + (size_t)v * 9;
+        const double *dN = dNx + (size_t)v * 240 + (i * 3) * 10 + x;
+        const double g0 = dN[0], g1 = dN[10], g2 = dN[20];
+        a0 += S[0] * g0 + S[1] * g1 + S[2] * g2;
+        a1 += S[3] * g0 + S[4] * g1 + S[5] * g2;
+        a2 += S[6] * g0 + S[7] * g1 + S[8] * g2;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(kFull, a0, o); a1 += __shfl_xor_sync(kFull, a1, o); a2 += __shfl_xor_sync(kFull, a2, o);
+    }
+    if (lane == 0) {
+        if (base_add) {  // (momentum + rhs) - rhs_rest in the reference's order (solver.py:599)
+            out[3 * row] = (base_add[3 * row] + a0) - base_sub[3 * row];
+            out[3 * row + 1] = (base_add[3 * row + 1] + a1) - base_sub[3 * row + 1];
+            out[3 * row + 2] = (base_add[3 * row + 2] + a2) - base_sub[3 * row + 2];
+        } else {
+            out[3 * row] = a0; out[3 * row + 1] = a1; out[3 * row + 2] = a2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- global step
+// y = alpha_add[row] + Mat x  (optional add vectors).  One warp per row, 128-bit row loads.
+__global__ void __launch_bounds__(256) matvec3_kernel(const double *__restrict__ mat, const double *__restrict__ x, int n,
+                                                      const double *__restrict__ add0, const double *__restrict__ add1,
+                                                      const double *__restrict__ add2, double *__restrict__ y) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double *m = mat + (size_t)row * n;
+    double a0 = 0, a1 = 0, a2 = 0;
+    if ((n & 1) == 0) {
+        const double2 *m2 = reinterpret_cast<const double2 *>(m);
+        for (int j = lane; j < n / 2; j += 32) {
+            const double2 w = __ldg(m2 + j);
+            const double *xa = x + 6 * (size_t)j;
+            a0 += w.x * xa[0] + w.y * xa[3]; a1 += w.x * xa[1] + w.y * xa[4]; a2 += w.x * xa[2] + w.y * xa[5];
+        }
+    } else {
+        for (int j = lane; j < n; j += 32) {
+            const double w = __ldg(m + j);
+            a0 += w * x[3 * j]; a1 += w * x[3 * j + 1]; a2 += w * x[3 * j + 2];
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(kFull, a0, o); a1 += __shfl_xor_sync(kFull, a1, o); a2 += __shfl_xor_sync(kFull, a2, o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double v = c == 0 ? a0 : (c == 1 ? a1 : a2);
+            if (add0) v += add0[3 * row + c];
+            if (add1) v += add1[3 * row + c];
+            if (add2) v += add2[3 * row + c];
+            y[3 * row + c] = v;
+        }
+    }
+}
+
+__global__ void axpy_tilde_kernel(const double *__restrict__ dof, const double *__restrict__ vel, double dt, int n3,
+                                  double *__restrict__ tilde, double *__restrict__ last) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n3) return;
+    tilde[i] = dof[i] + dt * vel[i];   // solver.py:575
+    last[i] = dof[i];                  // solver.py:597
+}
+__global__ void finish_step_kernel(const double *__restrict__ dof, const double *__restrict__ last, double dt, int n3,
+                                   double *__restrict__ vel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) vel[i] = (dof[i] - last[i]) / dt * 0.998;  // solver.py:602
+}
+
+// ---------------------------------------------------------------- PCG on (A + 1e-3 I) x = b, 3 right-hand sides
+// Jacobi-preconditioned CG over the active rows; one cooperative single-block driver per iteration would serialise,
+// so each CG iteration is: matvec (n warps) + two fused dot/update kernels with warp-shuffle + atomic reductions.
+__global__ void __launch_bounds__(256) pcg_matvec_kernel(const double *__restrict__ A, const unsigned char *__restrict__ act,
+                                                         const double *__restrict__ p, int n, double *__restrict__ Ap,
+                                                         double *__restrict__ pAp) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double a0 = 0, a1 = 0, a2 = 0;
+    const bool on = act[row / 10] != 0;
+    if (on) {
+        const double *m = A + (size_t)row * n;
+        for (int j = lane; j < n; j += 32) {
+            if (!act[j / 10]) continue;
+            const double w = __ldg(m + j) + (j == row ? 1e-3 : 0.0);
+            a0 += w * p[3 * j]; a1 += w * p[3 * j + 1]; a2 += w * p[3 * j + 2];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(kFull, a0, o); a1 += __shfl_xor_sync(kFull, a1, o); a2 += __shfl_xor_sync(kFull, a2, o);
+        }
+    }
+    if (lane == 0) {
+        Ap[3 * row] = a0; Ap[3 * row + 1] = a1; Ap[3 * row + 2] = a2;
+        if (on) {
+            atomicAdd(pAp, p[3 * row] * a0); atomicAdd(pAp + 1, p[3 * row + 1] * a1); atomicAdd(pAp + 2, p[3 * row + 2] * a2);
+        }
+    }
+}
+// x += alpha p ; r -= alpha Ap ; z = r / diag ; rz_new = sum r z
+__global__ void __launch_bounds__(256) pcg_update_kernel(const double *__restrict__ A, const unsigned char *__restrict__ act, int n,
+                                                         const double *__restrict__ rz, const double *__restrict__ pAp,
+                                                         const double *__restrict__ p, const double *__restrict__ Ap,
+                                                         double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
+                                                         double *__restrict__ rz_new) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[3] = {0, 0, 0};
+    if (i < n && act[i / 10]) {
+        const double dinv = 1.0 / (A[(size_t)i * n + i] + 1e-3);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double alpha = pAp[c] != 0.0 ? rz[c] / pAp[c] : 0.0;
+            x[3 * i + c] += alpha * p[3 * i + c];
+            const double rr = r[3 * i + c] - alpha * Ap[3 * i + c];
+            r[3 * i + c] = rr;
+            const double zz = rr * dinv;
+            z[3 * i + c] = zz;
+            acc[c] = rr * zz;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(kFull, acc[c], o);
+        if ((threadIdx.x & 31) == 0 && acc[c] != 0.0) atomicAdd(rz_new + c, acc[c]);
+    }
+}
+// p = z + (rz_new/rz) p ; then rotate scalars: rz <- rz_new, zero rz_new and pAp for the next iteration
+__global__ void __launch_bounds__(256) pcg_direction_kernel(const unsigned char *__restrict__ act, int n, const double *__restrict__ z,
+                                                            double *__restrict__ p, const double *__restrict__ rz,
+                                                            const double *__restrict__ rz_new) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !act[i / 10]) return;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double beta = rz[c] != 0.0 ? rz_new[c] / rz[c] : 0.0;
+        p[3 * i + c] = z[3 * i + c] + beta * p[3 * i + c];
+    }
+}
+__global__ void pcg_rotate_kernel(double *rz, double *rz_new, double *pAp) {
+    if (threadIdx.x < 3) { rz[threadIdx.x] = rz_new[threadIdx.x]; rz_new[threadIdx.x] = 0.0; pAp[threadIdx.x] = 0.0; }
+}
+// x = 0 ; r = b (active rows) ; z = r/diag ; p = z ; rz = sum r z
+__global__ void __launch_bounds__(256) pcg_init_kernel(const double *__restrict__ A, const unsigned char *__restrict__ act, int n,
+                                                       const double *__restrict__ b, double *__restrict__ x, double *__restrict__ r,
+                                                       double *__restrict__ z, double *__restrict__ p, double *__restrict__ rz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[3] = {0, 0, 0};
+    if (i < n) {
+        const bool on = act[i / 10] != 0;
+        const double dinv = on ? 1.0 / (A[(size_t)i * n + i] + 1e-3) : 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double rr = on ? b[3 * i + c] : 0.0;
+            x[3 * i + c] = 0.0; r[3 * i + c] = rr;
+            const double zz = rr * dinv;
+            z[3 * i + c] = zz; p[3 * i + c] = zz;
+            acc[c] = rr * zz;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(kFull, acc[c], o);
+        if ((threadIdx.x & 31) == 0 && acc[c] != 0.0) atomicAdd(rz + c, acc[c]);
+    }
+}
+__global__ void add_rest_kernel(const double *__restrict__ rest, const double *__restrict__ x, int n3, double *__restrict__ dof) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) dof[i] = rest[i] + x[i];
+}
+
+// ---------------------------------------------------------------- IP info / positions / force
+// update_F_kernel + the fp32 re-layout of get_IP_info (cuda_utils.py:206-233, solver.py:402-424): one warp per IP
+__global__ void __launch_bounds__(128) ip_info_kernel(const int *__restrict__ topo, const double *__restrict__ dof,
+                                                      const double *__restrict__ Nx, const double *__restrict__ dNx,
+                                                      const double *__restrict__ ddNx, int n_ip, float *__restrict__ pos,
+                                                      float *__restrict__ Fo, float *__restrict__ dFo) {
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (v >= n_ip) return;
+    const double *N = Nx + (size_t)v * 80, *dN = dNx + (size_t)v * 240, *ddN = ddNx + (size_t)v * 720;
+    double acc[39];  // pos[3], F[r*3+c] (9), dF[(j*3+r)*3+c] (27)
+#pragma unroll
+    for (int k = 0; k < 39; k++) acc[k] = 0;
+    for (int e = lane; e < 80; e += 32) {
+        const int i = e / 10, x = e % 10;
+        const double *d = dof + 3 * (size_t)(topo[8 * v + i] * 10 + x);
+        const double dv[3] = {d[0], d[1], d[2]};
+        const double nv = N[i * 10 + x];
+        double g[3], h[9];
+#pragma unroll
+        for (int c = 0; c < 3; c++) g[c] = dN[(i * 3 + c) * 10 + x];
+#pragma unroll
+        for (int c = 0; c < 9; c++) h[c] = ddN[(i * 9 + c) * 10 + x];  // h[j*3+c]
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            acc[r] += nv * dv[r];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                acc[3 + r * 3 + c] += dv[r] * g[c];
+#pragma unroll
+                for (int j = 0; j < 3; j++) acc[12 + (j * 3 + r) * 3 + c] += dv[r] * h[j * 3 + c];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 39; k++)
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(kFull, acc[k], o);
+    if (lane == 0) {
+        for (int r = 0; r < 3; r++) pos[3 * v + r] = (float)acc[r];
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Fo[9 * v + a * 3 + b] = (float)acc[3 + b * 3 + a];
+        for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) for (int j = 0; j < 3; j++)
+            dFo[27 * v + c * 9 + r * 3 + j] = (float)acc[12 + (j * 3 + r) * 3 + c];
+    }
+}
+
+__global__ void update_pos_kernel(const int *__restrict__ topo, const double *__restrict__ dof, const double *__restrict__ Nx,
+                                  int n_pts, double *__restrict__ pos) {  // cuda_utils.py:191-203
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_pts) return;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int i = 0; i < 8; i++) {
+        const double *d = dof + 3 * (size_t)(topo[8 * v + i] * 10);
+        for (int j = 0; j < 10; j++) {
+            const double w = Nx[(size_t)v * 80 + i * 10 + j];
+            a0 += w * d[3 * j]; a1 += w * d[3 * j + 1]; a2 += w * d[3 * j + 2];
+        }
+    }
+    pos[3 * v] = a0; pos[3 * v + 1] = a1; pos[3 * v + 2] = a2;
+}
+
+__global__ void update_force_kernel(int vid, double f0, double f1, double f2, const int *__restrict__ topo,
+                                    const double *__restrict__ Nx, const double *__restrict__ rho, double dx3,
+                                    double *__restrict__ dof_f) {  // solver.py:578-588 (dof_f already zeroed)
+    const int e = threadIdx.x;
+    if (e >= 80) return;
+    const int i = e / 10, j = e % 10;
+    const double m = rho[vid] * dx3 * Nx[(size_t)vid * 80 + i * 10 + j];
+    double *o = dof_f + 3 * (size_t)(topo[8 * vid + i] * 10 + j);
+    // kernels of one IP are distinct, so rows are disjoint; atomics keep it safe if two corners alias kernel 0
+    atomicAdd(o, m * f0); atomicAdd(o + 1, m * f1); atomicAdd(o + 2, m * f2);
+}
+
+}  // namespace
+
+// =============================================================================================== C-ABI
+extern "C" int pn_qgmls_shape_functions(double r, const double *pos, const int *topo, const double *kernel_pos, int n,
+                                        double *Nx, double *dNx, double *ddNx, int *status, void *stream) {
+    PN_REQUIRE(pos && topo && kernel_pos && Nx && status, "null pointer");
+    PN_REQUIRE(!ddNx || dNx, "ddNx requires dNx");
+    if (n <= 0) return PN_OK;
+    cudaStream_t st = PN_STREAM(stream);
+    PN_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+    shape_kernel<<<div_up(n, 64), 64, 0, st>>>(r, pos, topo, kernel_pos, n, Nx, dNx, ddNx, status);
+    PN_LAUNCH_CHECK("shape_kernel");
+    return PN_OK;
+}
+
+extern "C" int pn_qgmls_collect_param(const int *pts_ip, const double *mu, const double *lam, const double *mass,
+                                      int n_pts, int n_ip, double dx, double *ip_mu, double *ip_lam, double *ip_rho,
+                                      void *stream) {
+    PN_REQUIRE(pts_ip && mu && lam && mass && ip_mu && ip_lam && ip_rho, "null pointer");
+    cudaStream_t st = PN_STREAM(stream);
+    PN_CUDA(cudaMemsetAsync(ip_mu, 0, sizeof(double) * n_ip, st));
+    PN_CUDA(cudaMemsetAsync(ip_lam, 0, sizeof(double) * n_ip, st));
+    PN_CUDA(cudaMemsetAsync(ip_rho, 0, sizeof(double) * n_ip, st));
+    collect_param_kernel<<<div_up(n_pts, 256), 256, 0, st>>>(pts_ip, mu, lam, mass, n_pts, ip_mu, ip_lam, ip_rho);
+    finish_param_kernel<<<div_up(n_ip, 256), 256, 0, st>>>(n_ip, dx * dx * dx, ip_mu, ip_lam, ip_rho);
+    PN_LAUNCH_CHECK("collect_param");
+    return PN_OK;
+}
+
+extern "C" int pn_qgmls_build_ip_global(double dx, double dt, const int *topo, const double *mu, const double *lam,
+                                        const double *rho, const double *Nx, const double *dNx, const double *ddNx,
+                                        int n_ip, int n, double *mat, void *stream) {
+    PN_REQUIRE(topo && rho && Nx && dNx && ddNx && mat, "null pointer");
+    if (n_ip <= 0) return PN_OK;
+    build_ip_global_kernel<<<div_up(n_ip * 80, 128), 128, 0, PN_STREAM(stream)>>>(dx, dt, topo, mu, lam, rho, Nx, dNx, ddNx, n_ip, n, mat);
+    PN_LAUNCH_CHECK("build_ip_global_kernel");
+    return PN_OK;
+}
+
+extern "C" int pn_qgmls_build_pin_global(double stiff, const int *vidx, int n_pin, const int *topo, const double *Nx,
+                                         int n, double *mat, void *stream) {
+    if (n_pin <= 0) return PN_OK;
+    PN_REQUIRE(vidx && topo && Nx && mat, "null pointer");
+    build_pin_global_kernel<<<div_up(n_pin * 64, 128), 128, 0, PN_STREAM(stream)>>>(stiff, vidx, n_pin, topo, Nx, n, mat);
+    PN_LAUNCH_CHECK("build_pin_global_kernel");
+    return PN_OK;
+}
+
+extern "C" int pn_qgmls_collect_gravity(double dx, const int *topo, const double *Nx, const double *g, const double *rho,
+                                        int n_ip, double *rhs, void *stream) {
+    PN_REQUIRE(topo && Nx && g && rho && rhs, "null pointer");
+    if (n_ip <= 0) return PN_OK;
+    collect_gravity_kernel<<<div_up(n_ip * 80, 256), 256, 0, PN_STREAM(stream)>>>(dx, topo, Nx, g[0], g[1], g[2], rho, n_ip, rhs);
+    PN_LAUNCH_CHECK("collect_gravity_kernel");
+    return PN_OK;
+}
+
+extern "C" int pn_qgmls_build_rhs(double dx, const int *topo, const double *mu, const double *lam, const double *dNx,
+                                  const double *dof, int n_ip, int n_k, const int *adj_bgn, const int *adj,
+                                  double *ip_stress, double *rhs, void *stream) {
+    PN_REQUIRE(topo && mu && lam && dNx && dof && adj_bgn && adj && ip_stress && rhs, "null pointer");
+    cudaStream_t st = PN_STREAM(stream);
+    ip_stress_kernel<<<div_up(n_ip * 32, 128), 128, 0, st>>>(dx * dx * dx, topo, mu, lam, dNx, dof, n_ip, ip_stress);
+    rhs_gather_kernel<<<div_up(n_k * 10 * 32, 128), 128, 0, st>>>(adj_bgn, adj, ip_stress, dNx, n_k * 10, nullptr, nullptr, rhs);
+    PN_LAUNCH_CHECK("build_rhs");
+    return PN_OK;
+}
+
+extern "C" int pn_qgmls_matvec3(const double *mat, const double *x, int n, double *y, void *stream) {
+    PN_REQUIRE(mat && x && y, "null pointer");
+    if (n <= 0) return PN_OK;
+    matvec3_kernel<<<div_up(n * 32, 256), 256, 0, PN_STREAM(stream)>>>(mat, x, n, nullptr, nullptr, nullptr, y);
+    PN_LAUNCH_CHECK("matvec3_kernel");
+    return PN_OK;
+}
+
+extern "C" uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k) {
+    return 9ull * n_ip + 9ull * 30 * n_k + 16;
+}
+
+extern "C" int pn_qgmls_step(const pn_qgmls_step_t *s, int solver, void *stream) {
+    PN_REQUIRE(s && s->topo && s->mu && s->lam && s->dNx && s->adj_bgn && s->adj && s->M && s->dof_rest && s->dof_f &&
+                   s->rhs_rest && s->rhs_gravity && s->dof && s->dof_vel && s->scratch, "null pointer");
+    PN_REQUIRE(solver == 0 || solver == 1, "solver must be 0 (dense inverse) or 1 (PCG)");
+    PN_REQUIRE(solver == 1 ? (s->A && s->active) : (s->Ainv != nullptr), "missing system matrix for the chosen solver");
+    cudaStream_t st = PN_STREAM(stream);
+    const int n = 10 * s->n_k, n3 = 3 * n;
+    double *stress = s->scratch;
+    double *tilde = stress + 9 * (size_t)s->n_ip;
+    double *last = tilde + n3, *mom = last + n3, *rhs = mom + n3, *x = rhs + n3;
+    double *pcg = x + n3;  // r, z, p, Ap (4*n3) + 9 scalars, only touched by the PCG path
+    const double dx3 = s->dx * s->dx * s->dx;
+    const int eb = div_up(n3, 256);
+    axpy_tilde_kernel<<<eb, 256, 0, st>>>(s->dof, s->dof_vel, s->dt, n3, tilde, last);
+    // momentum = M/dt^2 @ dof_tilde + dof_f + rhs_gravity  (solver.py:576)
+    matvec3_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(s->M, tilde, n, s->dof_f, s->rhs_gravity, nullptr, mom);
+    for (int it = 0; it < s->iters; it++) {
+        ip_stress_kernel<<<div_up(s->n_ip * 32, 128), 128, 0, st>>>(dx3, s->topo, s->mu, s->lam, s->dNx, s->dof, s->n_ip, stress);
+        rhs_gather_kernel<<<div_up(n * 32, 128), 128, 0, st>>>(s->adj_bgn, s->adj, stress, s->dNx, n, mom, s->rhs_rest, rhs);
+        if (solver == 0) {
+            // dof = dof_rest + Ainv rhs  (solver.py:600-601)
+            matvec3_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(s->Ainv, rhs, n, s->dof_rest, nullptr, nullptr, s->dof);
+        } else {
+            double *r = pcg, *z = r + n3, *p = z + n3, *Ap = p + n3, *sc = Ap + n3;  // sc: rz[3], rz_new[3], pAp[3]
+            PN_CUDA(cudaMemsetAsync(sc, 0, 9 * sizeof(double), st));
+            const int nb = div_up(n, 256);
+            pcg_init_kernel<<<nb, 256, 0, st>>>(s->A, s->active, n, rhs, x, r, z, p, sc);
+            for (int k = 0; k < s->pcg_iters; k++) {
+                pcg_matvec_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(s->A, s->active, p, n, Ap, sc + 6);
+                pcg_update_kernel<<<nb, 256, 0, st>>>(s->A, s->active, n, sc, sc + 6, p, Ap, x, r, z, sc + 3);
+                pcg_direction_kernel<<<nb, 256, 0, st>>>(s->active, n, z, p, sc, sc + 3);
+                pcg_rotate_kernel<<<1, 32, 0, st>>>(sc, sc + 3, sc + 6);
+            }
+            add_rest_kernel<<<eb, 256, 0, st>>>(s->dof_rest, x, n3, s->dof);
+        }
+    }
+    finish_step_kernel<<<eb, 256, 0, st>>>(s->dof, last, s->dt, n3, s->dof_vel);
+    PN_LAUNCH_CHECK("qgmls_step");
+    return PN_OK;
+}
+
+extern "C" int pn_qgmls_ip_info(const int *topo, const double *dof, const double *Nx, const double *dNx,
+                                const double *ddNx, int n_ip, float *pos, float *F, float *dF, void *stream) {
+    PN_REQUIRE(topo && dof && Nx && dNx && ddNx && pos && F && dF, "null pointer");
+    if (n_ip <= 0) return PN_OK;
+    ip_info_kernel<<<div_up(n_ip * 32, 128), 128, 0, PN_STREAM(stream)>>>(topo, dof, Nx, dNx, ddNx, n_ip, pos, F, dF);
+    PN_LAUNCH_CHECK("ip_info_kernel");
+    return PN_OK;
+}
+
+extern "C" int pn_qgmls_update_pos(const int *topo, const double *dof, const double *Nx, int n_pts, double *pos,
+                                   void *stream) {
+    PN_REQUIRE(topo && dof && Nx && pos, "null pointer");
+    if (n_pts <= 0) return PN_OK;
+    update_pos_kernel<<<div_up(n_pts, 128), 128, 0, PN_STREAM(stream)>>>(topo, dof, Nx, n_pts, pos);
+    PN_LAUNCH_CHECK("update_pos_kernel");
+    return PN_OK;
+}
+
+extern "C" int pn_qgmls_update_force(int vid, const double *f, const int *topo, const double *Nx, const double *rho,
+                                     double dx, int n, double *dof_f, void *stream) {
+    PN_REQUIRE(topo && Nx && rho && dof_f, "null pointer");
+    cudaStream_t st = PN_STREAM(stream);
+    PN_CUDA(cudaMemsetAsync(dof_f, 0, sizeof(double) * 3 * (size_t)n, st));
+    if (vid < 0) return PN_OK;
+    PN_REQUIRE(f, "null force");
+    update_force_kernel<<<1, 96, 0, st>>>(vid, f[0], f[1], f[2], topo, Nx, rho, dx * dx * dx, dof_f);
+    PN_LAUNCH_CHECK("update_force_kernel");
+    return PN_OK;
+}

@@ -1,0 +1,516 @@
+// Device-resident deformed-space frame renderer + its per-frame preparation kernels.
+//
+// Replaces the host-driven wavefront loop of nerf/renderer.py:755-907 (rund_cuda) and the torch / Warp glue
+// around it (nerf/utils.py:55-138 get_rays, :355-443 get_pnts_in_grids, renderer.py:782-797 bbox + near/far)
+// with four launches and no host synchronisation:
+//   1. ip_bbox_kernel        bbox of deformed IP centres -> bbmin/bbmax/resolution (device)
+//   2. ip_grid_*             deterministic counting sort of IPs into the hgs grid
+//   3. frame_setup_kernel    near/far, output init, compaction of the rays that hit the IP box
+//   4. render_persistent     one lane = one ray until it dies, then the lane pulls the next ray from a global
+//                            queue (warp-aggregated atomic): march -> inverse warp -> 16-level hash encode ->
+//                            sigma/colour MLP -> composite, all in registers, weights in shared memory.
+// The per-ray sample sequence is exactly the reference's (the wavefront loop only batches it differently), so
+// images agree to MLP rounding; see DESIGN.md for the one documented deviation (per-ray cap = max_steps).
+#include "field_device.cuh"
+#include "march_device.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------- get_rays
+__global__ void __launch_bounds__(256) get_rays_kernel(float r00, float r01, float r02, float r10, float r11, float r12,
+                                                       float r20, float r21, float r22, float tx, float ty, float tz,
+                                                       float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                                                       float *__restrict__ rays_o, float *__restrict__ rays_d) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= H * W) return;
+    const float i = (float)(n % W) + 0.5f, j = (float)(n / W) + 0.5f;
+    const float xs = (i - cx) / fx * 1.0f, ys = (j - cy) / fy * 1.0f, zs = 1.0f;
+    const float nrm = sqrtf(xs * xs + ys * ys + zs * zs);
+    const float ux = xs / nrm, uy = ys / nrm, uz = zs / nrm;
+    rays_d[3 * n] = ux * r00 + uy * r01 + uz * r02;
+    rays_d[3 * n + 1] = ux * r10 + uy * r11 + uz * r12;
+    rays_d[3 * n + 2] = ux * r20 + uy * r21 + uz * r22;
+    rays_o[3 * n] = tx; rays_o[3 * n + 1] = ty; rays_o[3 * n + 2] = tz;
+}
+
+// ------------------------------------------------------------------------------------------- IP bbox
+struct FrameGeom {  // lives in the workspace, written by ip_bbox_kernel
+    float bbmin[3], bbmax[3], hi[3];
+    int res[3];
+    int n_grid;
+};
+
+__global__ void __launch_bounds__(1024) ip_bbox_kernel(const float *__restrict__ p, int n, float hgs, int cut, float bound,
+                                                       FrameGeom *__restrict__ g, float *__restrict__ bbmin_out,
+                                                       float *__restrict__ bbmax_out, int *__restrict__ res_out) {
+    __shared__ float smin[3][32], smax[3][32];
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { const float v = p[3 * i + c]; lo[c] = fminf(lo[c], v); hi[c] = fmaxf(hi[c], v); }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if ((threadIdx.x & 31) == 0) { smin[c][threadIdx.x >> 5] = lo[c]; smax[c][threadIdx.x >> 5] = hi[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int c = threadIdx.x;
+        float a = FLT_MAX, b = -FLT_MAX;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a = fminf(a, smin[c][w]); b = fmaxf(b, smax[c][w]); }
+        if (cut) { a = -bound; b = bound; }                       // renderer.py:784-786
+        const float mn = a - 1e-3f, mx = b + 1e-3f;               // renderer.py:787-789
+        // renderer.py:791: tensor / python-scalar on CUDA multiplies by the fp32 reciprocal
+        const int r = (int)ceilf((mx - mn) * (1.0f / hgs));
+        if (g) { g->bbmin[c] = mn; g->bbmax[c] = mx; g->hi[c] = (float)((double)mx - 1e-6); g->res[c] = r; }
+        if (bbmin_out) { bbmin_out[c] = mn; bbmax_out[c] = mx; res_out[c] = r; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && g) g->n_grid = g->res[0] * g->res[1] * g->res[2];
+}
+
+// ------------------------------------------------------------------------------------------- IP grid
+__device__ __forceinline__ int ip_cell(const float *__restrict__ p, int i, const float *bbmin, float hgs, const int *res) {
+    // nerf/utils.py:388-408 p2g (true fp32 division)
+    const int g0 = (int)floorf((p[3 * i] - bbmin[0]) / hgs);
+    const int g1 = (int)floorf((p[3 * i + 1] - bbmin[1]) / hgs);
+    const int g2 = (int)floorf((p[3 * i + 2] - bbmin[2]) / hgs);
+    return (g2 * res[1] + g1) * res[0] + g0;
+}
+
+__global__ void __launch_bounds__(256) ip_grid_count(const float *__restrict__ p, int n, const float *__restrict__ bbmin,
+                                                     float hgs, const int *__restrict__ res, int n_grid_cap,
+                                                     int *__restrict__ cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int gid = ip_cell(p, i, bbmin, hgs, res);
+    if (gid >= 0 && gid < n_grid_cap) atomicAdd(cnt + gid, 1);
+}
+
+// single-block exclusive scan over n_grid cells (n_grid <= a few 1e5): bgn = cumsum(cnt) - cnt
+__global__ void __launch_bounds__(1024) ip_grid_scan(const int *__restrict__ cnt, const int *__restrict__ res,
+                                                     int n_grid_cap, int *__restrict__ bgn, int *__restrict__ fill) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int n_grid = min(res[0] * res[1] * res[2], n_grid_cap);
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_grid; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_grid ? cnt[i] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warp_tot[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += t; }
+            warp_tot[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int before = carry + ((threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0) + incl - v;
+        if (i < n_grid) { bgn[i] = before; fill[i] = 0; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) ip_grid_fill(const float *__restrict__ p, int n, const float *__restrict__ bbmin,
+                                                    float hgs, const int *__restrict__ res, int n_grid_cap,
+                                                    const int *__restrict__ bgn, int *__restrict__ fill,
+                                                    int *__restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int gid = ip_cell(p, i, bbmin, hgs, res);
+    if (gid >= 0 && gid < n_grid_cap) idx[bgn[gid] + atomicAdd(fill + gid, 1)] = i;
+}
+
+// make the within-cell order deterministic (ascending IP index); cells hold a handful of IPs
+__global__ void __launch_bounds__(256) ip_grid_sort(const int *__restrict__ cnt, const int *__restrict__ bgn,
+                                                    const int *__restrict__ res, int n_grid_cap, int *__restrict__ idx) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_grid = min(res[0] * res[1] * res[2], n_grid_cap);
+    if (c >= n_grid) return;
+    const int n = cnt[c];
+    int *a = idx + bgn[c];
+    for (int i = 1; i < n; i++) {
+        const int v = a[i];
+        int j = i - 1;
+        while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; }
+        a[j + 1] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- frame setup
+struct FrameQueue { int n_active; int next; long long samples; long long pad; };
+
+__global__ void __launch_bounds__(256) frame_setup_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                                                          uint32_t N, const FrameGeom *__restrict__ g, float min_near,
+                                                          float bg, float *__restrict__ nears, float *__restrict__ fars,
+                                                          int *__restrict__ active, FrameQueue *__restrict__ q,
+                                                          float *__restrict__ image, float *__restrict__ depth,
+                                                          float *__restrict__ depth0, float *__restrict__ wsum) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    if (n < N) {
+        const float ox = rays_o[3 * n], oy = rays_o[3 * n + 1], oz = rays_o[3 * n + 2];
+        const float rdx = 1 / rays_d[3 * n], rdy = 1 / rays_d[3 * n + 1], rdz = 1 / rays_d[3 * n + 2];
+        float near = (g->bbmin[0] - ox) * rdx, far = (g->bbmax[0] - ox) * rdx;
+        if (near > far) { const float s = near; near = far; far = s; }
+        float ny = (g->bbmin[1] - oy) * rdy, fy = (g->bbmax[1] - oy) * rdy;
+        if (ny > fy) { const float s = ny; ny = fy; fy = s; }
+        bool miss = near > fy || ny > far;
+        if (!miss) {
+            if (ny > near) near = ny;
+            if (fy < far) far = fy;
+            float nz = (g->bbmin[2] - oz) * rdz, fz = (g->bbmax[2] - oz) * rdz;
+            if (nz > fz) { const float s = nz; nz = fz; fz = s; }
+            miss = near > fz || nz > far;
+            if (!miss) {
+                if (nz > near) near = nz;
+                if (fz < far) far = fz;
+                if (near < min_near) near = min_near;
+            }
+        }
+        if (miss) near = far = FLT_MAX;
+        nears[n] = near; fars[n] = far;
+        hit = near < far;  // a ray with t >= far never emits a sample
+        if (!hit) {
+            // what rund_cuda leaves for a ray that never composites anything (renderer.py:896-901)
+            image[3 * n] = bg; image[3 * n + 1] = bg; image[3 * n + 2] = bg;
+            depth0[n] = 0.f; wsum[n] = 0.f;
+            depth[n] = fmaxf(0.f - near, 0.f) / (far - near);  // NaN for a miss, as in the reference
+        }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&q->n_active, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) active[base + __popc(m & ((1u << lane) - 1))] = (int)n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- persistent renderer
+struct RenderArgs {
+    pn_field_t field;
+    pn::MarchCfg march;
+    pn::BendCfg bend;  // bbmin/bbmax/hi/res filled on device from FrameGeom
+    const FrameGeom *geom;
+    const float *rays_o, *rays_d, *nears, *fars;
+    const int *active;
+    FrameQueue *queue;
+    float *image, *depth, *depth0, *wsum;
+    float density_scale, T_thresh, bg;
+    uint32_t max_samples;
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(128, 3) render_persistent(const RenderArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pn::FieldSmem &fs = *reinterpret_cast<pn::FieldSmem *>(smem_raw);
+    pn::field_smem_fill(fs, A.field);
+    pn::BendCfg bc = A.bend;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        bc.bbmin[i] = A.geom->bbmin[i]; bc.bbmax[i] = A.geom->bbmax[i]; bc.hi[i] = A.geom->hi[i]; bc.res[i] = A.geom->res[i];
+    }
+    __syncthreads();
+    const pn::MarchCfg m = A.march;
+    const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
+    const int lane = threadIdx.x & 31;
+    const int n_active = A.queue->n_active;
+
+    // per-lane ray state
+    bool alive = false, exhausted = false;
+    int ray = -1;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, rdx = 0, rdy = 0, rdz = 0;
+    float t = 0, last_t = 0, far = 0, near = 0, tdepth = 0;
+    float ws = 0, dep = 0, cr = 0, cg = 0, cb = 0;
+    float sh[16];
+    uint32_t nsamp = 0;
+    long long my_samples = 0;
+
+    while (true) {
+        // ---- refill dead lanes from the global queue (one atomic per warp)
+        const uint32_t need = __ballot_sync(0xffffffffu, !alive && !exhausted);
+        if (need) {
+            int base = 0;
+            if (lane == __ffs(need) - 1) base = atomicAdd(&A.queue->next, __popc(need));
+            base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+            if (!alive && !exhausted) {
+                const int slot = base + __popc(need & ((1u << lane) - 1));
+                if (slot < n_active) {
+                    ray = A.active[slot];
+                    ox = A.rays_o[3 * ray]; oy = A.rays_o[3 * ray + 1]; oz = A.rays_o[3 * ray + 2];
+                    dx = A.rays_d[3 * ray]; dy = A.rays_d[3 * ray + 1]; dz = A.rays_d[3 * ray + 2];
+                    rdx = 1 / dx; rdy = 1 / dy; rdz = 1 / dz;
+                    near = A.nears[ray]; far = A.fars[ray];
+                    t = near;                     // rays_t = nears.clone(); noise = 0 (perturb off in the sim GUI)
+                    last_t = t; tdepth = near;
+                    ws = dep = cr = cg = cb = 0.f;
+                    nsamp = 0;
+                    pn::sh_eval<4>(dx, dy, dz, sh);
+                    alive = true;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+
+        // ---- march this lane's ray to its next kept sample
+        bool have = false;
+        float x = 0, y = 0, z = 0, dt = 0, dreal = 0;
+        if (alive) {
+            while (t < far) {
+                pn::deformed_sample(bc, ox, oy, oz, dx, dy, dz, t, x, y, z);
+                const bool found = pn::bend_sample<KMAX>(bc, x, y, z);
+                dt = pn::step_size(m, t);
+                float tt;
+                const bool occ = pn::occupancy_and_exit(m, x, y, z, t, dt, dx, dy, dz, rdx, rdy, rdz, tt);
+                if (occ && found) {
+                    t += dt;
+                    dreal = t - last_t;
+                    last_t = t;
+                    have = true;
+                    break;
+                }
+                do { t += pn::step_size(m, t); } while (t < tt);
+            }
+        }
+        bool finish = alive && !have;
+
+        // ---- field + composite for lanes that produced a sample
+        if (have) {
+            float sigma, r, g, b;
+            pn::field_eval(fs, table, A.field.bound, x, y, z, sh, sigma, r, g, b);
+            sigma = A.density_scale * sigma;
+            const float alpha = 1.0f - __expf(-sigma * dt);
+            const float T = 1 - ws;
+            const float w = alpha * T;
+            ws += w;
+            tdepth += dreal;
+            dep += w * tdepth;
+            cr += w * r; cg += w * g; cb += w * b;
+            nsamp++;
+            my_samples++;
+            if (T < A.T_thresh || nsamp >= A.max_samples) finish = true;
+        }
+        if (finish) {
+            // renderer.py:896-901
+            A.image[3 * ray] = cr + (1 - ws) * A.bg;
+            A.image[3 * ray + 1] = cg + (1 - ws) * A.bg;
+            A.image[3 * ray + 2] = cb + (1 - ws) * A.bg;
+            A.depth0[ray] = dep;
+            A.depth[ray] = fmaxf(dep - near, 0.f) / (far - near);
+            A.wsum[ray] = ws;
+            alive = false;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) my_samples += __shfl_xor_sync(0xffffffffu, my_samples, o);
+    if (lane == 0 && my_samples) atomicAdd((unsigned long long *)&A.queue->samples, (unsigned long long)my_samples);
+}
+
+__global__ void copy_stats_kernel(const FrameQueue *q, long long *stats) {
+    stats[0] = q->samples;
+    stats[1] = q->n_active;
+}
+
+// stand-alone field pass over M samples (the body of NeRFNetwork.forward as one kernel)
+__global__ void __launch_bounds__(128, 3) field_forward_kernel(const pn_field_t f, const float *__restrict__ xyzs,
+                                                               const float *__restrict__ dirs, uint32_t M,
+                                                               float *__restrict__ sigmas, float *__restrict__ rgbs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pn::FieldSmem &fs = *reinterpret_cast<pn::FieldSmem *>(smem_raw);
+    pn::field_smem_fill(fs, f);
+    __syncthreads();
+    const float2 *table = reinterpret_cast<const float2 *>(f.embeddings);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        float sh[16];
+        pn::sh_eval<4>(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], sh);
+        float sigma, r, g, b;
+        pn::field_eval(fs, table, f.bound, xyzs[3 * i], xyzs[3 * i + 1], xyzs[3 * i + 2], sh, sigma, r, g, b);
+        sigmas[i] = sigma;
+        rgbs[3 * i] = r; rgbs[3 * i + 1] = g; rgbs[3 * i + 2] = b;
+    }
+}
+
+struct WorkspaceLayout {
+    size_t geom, queue, nears, fars, active, pig_cnt, pig_bgn, pig_fill, pig_idx, total;
+};
+
+WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
+    WorkspaceLayout w;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~size_t(255); return r; };
+    w.geom = take(sizeof(FrameGeom));
+    w.queue = take(sizeof(FrameQueue));
+    w.nears = take(sizeof(float) * N);
+    w.fars = take(sizeof(float) * N);
+    w.active = take(sizeof(int) * N);
+    w.pig_cnt = take(sizeof(int) * (size_t)max_cells);
+    w.pig_bgn = take(sizeof(int) * (size_t)max_cells);
+    w.pig_fill = take(sizeof(int) * (size_t)max_cells);
+    w.pig_idx = take(sizeof(int) * (size_t)n_vtx);
+    w.total = o;
+    return w;
+}
+
+int max_cells_for(float bound, float hgs) {
+    const int r = (int)ceilf((2 * bound + 2e-3f) / hgs) + 1;
+    return r * r * r;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) { pn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PN_ECUDA; }
+    }
+    return PN_OK;
+}
+
+}  // namespace
+
+extern "C" int pn_get_rays(const float *pose, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                           float *rays_o, float *rays_d, void *stream) {
+    PN_REQUIRE(pose && rays_o && rays_d, "null pointer");
+    if (H * W == 0) return PN_OK;
+    get_rays_kernel<<<div_up(H * W, 256u), 256, 0, PN_STREAM(stream)>>>(pose[0], pose[1], pose[2], pose[4], pose[5],
+                                                                        pose[6], pose[8], pose[9], pose[10], pose[3],
+                                                                        pose[7], pose[11], fx, fy, cx, cy, H, W, rays_o,
+                                                                        rays_d);
+    PN_LAUNCH_CHECK("get_rays_kernel");
+    return PN_OK;
+}
+
+extern "C" int pn_ip_bbox(const float *p_def, int n_vtx, float hgs, int cut, float bound, float *bbmin, float *bbmax,
+                          int *resolution, void *stream) {
+    PN_REQUIRE(p_def && bbmin && bbmax && resolution && n_vtx > 0, "null pointer / empty IP set");
+    ip_bbox_kernel<<<1, 1024, 0, PN_STREAM(stream)>>>(p_def, n_vtx, hgs, cut, bound, nullptr, bbmin, bbmax, resolution);
+    PN_LAUNCH_CHECK("ip_bbox_kernel");
+    return PN_OK;
+}
+
+static int build_ip_grid_impl(const float *p_def, int n_vtx, const float *bbmin, float hgs, const int *res, int n_grid_cap,
+                              int *cnt, int *bgn, int *fill, int *idx, cudaStream_t st) {
+    PN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)n_grid_cap, st));
+    ip_grid_count<<<div_up(n_vtx, 256), 256, 0, st>>>(p_def, n_vtx, bbmin, hgs, res, n_grid_cap, cnt);
+    ip_grid_scan<<<1, 1024, 0, st>>>(cnt, res, n_grid_cap, bgn, fill);
+    ip_grid_fill<<<div_up(n_vtx, 256), 256, 0, st>>>(p_def, n_vtx, bbmin, hgs, res, n_grid_cap, bgn, fill, idx);
+    ip_grid_sort<<<div_up(n_grid_cap, 256), 256, 0, st>>>(cnt, bgn, res, n_grid_cap, idx);
+    PN_LAUNCH_CHECK("ip_grid");
+    return PN_OK;
+}
+
+extern "C" int pn_build_ip_grid(const float *p_def, int n_vtx, const float *bbmin, float hgs, const int *resolution,
+                                int n_grid, int *pig_cnt, int *pig_bgn, int *pig_idx, void *stream) {
+    PN_REQUIRE(p_def && bbmin && resolution && pig_cnt && pig_bgn && pig_idx, "null pointer");
+    PN_REQUIRE(n_vtx > 0 && n_grid > 0, "empty IP set / grid");
+    int *fill = nullptr;
+    cudaStream_t st = PN_STREAM(stream);
+    PN_CUDA(cudaMallocAsync(&fill, sizeof(int) * (size_t)n_grid, st));
+    const int rc = build_ip_grid_impl(p_def, n_vtx, bbmin, hgs, resolution, n_grid, pig_cnt, pig_bgn, fill, pig_idx, st);
+    cudaFreeAsync(fill, st);
+    return rc;
+}
+
+extern "C" int pn_field_forward(const pn_field_t *f, const float *xyzs, const float *dirs, uint32_t M, float *sigmas,
+                                float *rgbs, int mode, void *stream) {
+    PN_REQUIRE(f && xyzs && dirs && sigmas && rgbs, "null pointer");
+    PN_REQUIRE(f->L == pn::kLevels, "fused field expects the 16-level C=2 D=3 grid of nerf/network.py");
+    PN_REQUIRE(mode == 0, "unknown field mode");
+    if (M == 0) return PN_OK;
+    const size_t smem = sizeof(pn::FieldSmem);
+    if (int rc = set_smem(field_forward_kernel, smem)) return rc;
+    const uint32_t blocks = min(div_up(M, 128u), (uint32_t)pn_sm_count_cached() * 3u);
+    field_forward_kernel<<<blocks, 128, smem, PN_STREAM(stream)>>>(*f, xyzs, dirs, M, sigmas, rgbs);
+    PN_LAUNCH_CHECK("field_forward_kernel");
+    return PN_OK;
+}
+
+static cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+extern "C" int pn_set_profile_events(void *start, void *stop) {
+    g_prof_start = (cudaEvent_t)start;
+    g_prof_stop = (cudaEvent_t)stop;
+    return PN_OK;
+}
+
+extern "C" uint64_t pn_render_workspace_bytes(uint32_t N, int n_vtx, float bound, float hgs) {
+    return layout(N, n_vtx, max_cells_for(bound, hgs)).total;
+}
+
+extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, const float *rays_o, const float *rays_d,
+                                  uint32_t N, float *image, float *depth, float *depth_0, float *weights_sum,
+                                  void *workspace, uint64_t workspace_bytes, long long *stats, int mode, void *stream) {
+    PN_REQUIRE(f && d && rays_o && rays_d && image && depth && depth_0 && weights_sum && workspace, "null pointer");
+    PN_REQUIRE(f->L == pn::kLevels, "fused field expects the 16-level C=2 D=3 grid of nerf/network.py");
+    PN_REQUIRE(mode == 0, "unknown render mode");
+    PN_REQUIRE(d->n_vtx > 0 && d->num_seek_IP >= 1 && d->num_seek_IP <= 3, "need IPs and num_seek_IP in 1..3");
+    PN_REQUIRE(d->cascade >= 1 && d->cascade <= 8 && d->grid_size == 128, "cascade/grid_size out of range");
+    if (N == 0) return PN_OK;
+    cudaStream_t st = PN_STREAM(stream);
+    const int max_cells = max_cells_for(d->bound, d->hgs);
+    const WorkspaceLayout w = layout(N, d->n_vtx, max_cells);
+    PN_REQUIRE(workspace_bytes >= w.total, "workspace too small (see pn_render_workspace_bytes)");
+    unsigned char *base = (unsigned char *)workspace;
+    FrameGeom *geom = (FrameGeom *)(base + w.geom);
+    FrameQueue *queue = (FrameQueue *)(base + w.queue);
+    float *nears = (float *)(base + w.nears), *fars = (float *)(base + w.fars);
+    int *active = (int *)(base + w.active);
+    int *cnt = (int *)(base + w.pig_cnt), *bgn = (int *)(base + w.pig_bgn), *fill = (int *)(base + w.pig_fill), *idx = (int *)(base + w.pig_idx);
+
+    PN_CUDA(cudaMemsetAsync(queue, 0, sizeof(FrameQueue), st));
+    ip_bbox_kernel<<<1, 1024, 0, st>>>(d->p_def, d->n_vtx, d->hgs, d->cut, d->bound, geom, nullptr, nullptr, nullptr);
+    if (int rc = build_ip_grid_impl(d->p_def, d->n_vtx, geom->bbmin, d->hgs, geom->res, max_cells, cnt, bgn, fill, idx, st)) return rc;
+    frame_setup_kernel<<<div_up(N, 256u), 256, 0, st>>>(rays_o, rays_d, N, geom, d->min_near, d->bg_color, nears, fars,
+                                                         active, queue, image, depth, depth_0, weights_sum);
+    PN_LAUNCH_CHECK("frame_setup_kernel");
+
+    RenderArgs A{};
+    A.field = *f;
+    A.march.bound = d->bound; A.march.dt_gamma = d->dt_gamma;
+    A.march.dt_min = 2 * 1.7320508075688772f / d->max_steps;
+    A.march.dt_max = 2 * 1.7320508075688772f * (1 << (d->cascade - 1)) / d->grid_size;
+    A.march.cascade = (int)d->cascade; A.march.H = (int)d->grid_size; A.march.bits = d->density_bitfield;
+    A.bend.pig_cnt = cnt; A.bend.pig_bgn = bgn; A.bend.pig_idx = idx;
+    A.bend.p_ori = d->p_ori; A.bend.p_def = d->p_def; A.bend.F = d->F_IP; A.bend.dF = d->dF_IP;
+    A.bend.n_grid = max_cells; A.bend.max_iter = d->max_iter_num; A.bend.K = d->num_seek_IP;
+    A.bend.hgs = d->hgs; A.bend.IP_dx = d->IP_dx; A.bend.bound = d->bound; A.bend.cut = d->cut != 0;
+    for (int i = 0; i < 6; i++) A.bend.cb[i] = d->cut_bounds[i];
+    A.geom = geom; A.rays_o = rays_o; A.rays_d = rays_d; A.nears = nears; A.fars = fars; A.active = active; A.queue = queue;
+    A.image = image; A.depth = depth; A.depth0 = depth_0; A.wsum = weights_sum;
+    A.density_scale = d->density_scale; A.T_thresh = d->T_thresh; A.bg = d->bg_color; A.max_samples = d->max_steps;
+
+    const size_t smem = sizeof(pn::FieldSmem);
+    const uint32_t blocks = (uint32_t)pn_sm_count_cached() * 3u;
+    if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
+    switch (d->num_seek_IP) {
+        case 1:
+            if (int rc = set_smem(render_persistent<1>, smem)) return rc;
+            render_persistent<1><<<blocks, 128, smem, st>>>(A);
+            break;
+        case 2:
+            if (int rc = set_smem(render_persistent<2>, smem)) return rc;
+            render_persistent<2><<<blocks, 128, smem, st>>>(A);
+            break;
+        default:
+            if (int rc = set_smem(render_persistent<3>, smem)) return rc;
+            render_persistent<3><<<blocks, 128, smem, st>>>(A);
+            break;
+    }
+    PN_LAUNCH_CHECK("render_persistent");
+    if (g_prof_stop) PN_CUDA(cudaEventRecord(g_prof_stop, st));
+    if (stats) {
+        copy_stats_kernel<<<1, 1, 0, st>>>(queue, stats);
+        PN_LAUNCH_CHECK("copy_stats_kernel");
+    }
+    return PN_OK;
+}

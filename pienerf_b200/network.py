@@ -1,0 +1,244 @@
+"""Host-side mirror of nerf/network.py `NeRFNetwork` + the two CUDA-ray render loops of nerf/renderer.py
+(`run_cuda` eval branch :332-388, `rund_cuda` :755-907) over the B200 operators, plus the fused entry points.
+
+Two ways to render a deformed frame, same inputs, same outputs:
+  * `rund_cuda(...)`           the reference's wavefront loop verbatim (host-driven, per-op drop-in kernels) —
+                               exists for A/B parity against the reference structure;
+  * `render_deformed(...)`     ONE C-ABI call (`pn_render_deformed`): device-resident, no host sync — the product path.
+State-dict keys match torch-ngp checkpoints (trainer.py:799-818): encoder.embeddings, encoder.offsets,
+sigma_net.{0,1}.weight, color_net.{0,1,2}.weight, density_bitfield, aabb_train, aabb_infer.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import raymarching
+from ._lib import DeformT, FieldT, check, dptr, lib, stream_ptr
+from .gridencoder import GridEncoder
+from .shencoder import SHEncoder
+
+
+class NeRFNetwork(nn.Module):
+    def __init__(self, encoding="hashgrid", encoding_dir="sphere_harmonics", num_layers=2, hidden_dim=64, geo_feat_dim=15,
+                 num_layers_color=3, hidden_dim_color=64, bound=1, cuda_ray=True, density_scale=1, min_near=0.2,
+                 density_thresh=0.01, bg_radius=-1, **kwargs):
+        super().__init__()
+        if encoding != "hashgrid" or encoding_dir != "sphere_harmonics":
+            raise NotImplementedError("the hot path is hashgrid + sphere_harmonics (main_gui.py:24-32)")
+        if bg_radius > 0:
+            raise NotImplementedError("background model (bg_radius > 0) is outside the sim+render hot path")
+        # nerf/renderer.py:74-113
+        self.bound = bound
+        self.cascade = 1 + math.ceil(math.log2(bound))
+        self.grid_size = 128
+        self.density_scale = density_scale
+        self.min_near = min_near
+        self.density_thresh = density_thresh
+        self.bg_radius = bg_radius
+        self.cuda_ray = cuda_ray
+        aabb = torch.FloatTensor([-bound, -bound, -bound, bound, bound, bound])
+        self.register_buffer("aabb_train", aabb)
+        self.register_buffer("aabb_infer", aabb.clone())
+        self.register_buffer("density_bitfield", torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
+        # nerf/network.py:30-71
+        self.num_layers, self.hidden_dim, self.geo_feat_dim = num_layers, hidden_dim, geo_feat_dim
+        self.encoder = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
+                                   desired_resolution=2048 * bound, gridtype="hash", align_corners=False)
+        self.in_dim = self.encoder.output_dim
+        self.sigma_net = nn.ModuleList([
+            nn.Linear(self.in_dim if l == 0 else hidden_dim, 1 + geo_feat_dim if l == num_layers - 1 else hidden_dim, bias=False)
+            for l in range(num_layers)])
+        self.num_layers_color, self.hidden_dim_color = num_layers_color, hidden_dim_color
+        self.encoder_dir = SHEncoder(input_dim=3, degree=4)
+        self.in_dim_dir = self.encoder_dir.output_dim
+        self.color_net = nn.ModuleList([
+            nn.Linear(self.in_dim_dir + geo_feat_dim if l == 0 else hidden_dim_color, 3 if l == num_layers_color - 1 else hidden_dim_color, bias=False)
+            for l in range(num_layers_color)])
+        # deformation state wired on by the frame driver (main_gui.py:50-56)
+        self.p_ori = self.p_def = self.IP_F = self.IP_dF = None
+        self.IP_dx = None
+        self._workspace = None
+        self._stats = None
+
+    # ------------------------------------------------------------------ synthetic field loading
+    def load_field(self, field):
+        """Load a pienerf_b200.synthetic.make_field() dict (random-init stand-in for a checkpoint)."""
+        with torch.no_grad():
+            self.encoder.embeddings.copy_(torch.from_numpy(field["embeddings"]))
+            for lin, w in zip(self.sigma_net, field["sigma_net"]):
+                lin.weight.copy_(torch.from_numpy(w))
+            for lin, w in zip(self.color_net, field["color_net"]):
+                lin.weight.copy_(torch.from_numpy(w))
+        return self
+
+    # ------------------------------------------------------------------ nerf/network.py:98-127
+    @torch.no_grad()
+    def forward(self, x, d):
+        """Per-op path: hash-grid kernel -> torch fp32 Linear stack -> SH kernel -> Linear stack."""
+        x = self.encoder(x, bound=self.bound)
+        h = x
+        for l in range(self.num_layers):
+            h = self.sigma_net[l](h)
+            if l != self.num_layers - 1:
+                h = F.relu(h, inplace=True)
+        sigma = torch.exp(h[..., 0])                                 # trunc_exp forward (activation.py:9-11)
+        geo_feat = h[..., 1:]
+        d = self.encoder_dir(d)
+        h = torch.cat([d, geo_feat], dim=-1)
+        for l in range(self.num_layers_color):
+            h = self.color_net[l](h)
+            if l != self.num_layers_color - 1:
+                h = F.relu(h, inplace=True)
+        return sigma, torch.sigmoid(h)
+
+    def _field_struct(self):
+        f = FieldT()
+        self._keep = [self.encoder.embeddings.data, self.encoder.offsets] + [l.weight.data for l in self.sigma_net] + [l.weight.data for l in self.color_net]
+        f.embeddings, f.offsets = dptr(self._keep[0], "embeddings", torch.float32), dptr(self._keep[1], "offsets", torch.int32)
+        f.S = float(np.log2(self.encoder.per_level_scale)); f.H = int(self.encoder.base_resolution); f.L = int(self.encoder.num_levels)
+        f.bound = float(self.bound)
+        f.w_sigma0, f.w_sigma1 = dptr(self._keep[2], "sigma_net.0", torch.float32), dptr(self._keep[3], "sigma_net.1", torch.float32)
+        f.w_color0, f.w_color1, f.w_color2 = (dptr(self._keep[4], "color_net.0", torch.float32), dptr(self._keep[5], "color_net.1", torch.float32),
+                                              dptr(self._keep[6], "color_net.2", torch.float32))
+        return f
+
+    @torch.no_grad()
+    def forward_fused(self, x, d, mode=0):
+        """Whole NeRFNetwork.forward as one kernel (pn_field_forward)."""
+        x = x.to(torch.float32).contiguous().view(-1, 3); d = d.to(torch.float32).contiguous().view(-1, 3)
+        M = x.shape[0]
+        sigmas = torch.empty(M, dtype=torch.float32, device=x.device)
+        rgbs = torch.empty(M, 3, dtype=torch.float32, device=x.device)
+        f = self._field_struct()
+        check(lib.pn_field_forward(C.byref(f), dptr(x), dptr(d), M, dptr(sigmas), dptr(rgbs), int(mode), stream_ptr()))
+        return sigmas, rgbs
+
+    # ------------------------------------------------------------------ nerf/renderer.py:332-388
+    @torch.no_grad()
+    def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024, T_thresh=1e-2, fused_field=False, **kwargs):
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3); rays_d = rays_d.contiguous().view(-1, 3)
+        N = rays_o.shape[0]; device = rays_o.device
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_infer, self.min_near)
+        if bg_color is None:
+            bg_color = 1
+        weights_sum = torch.zeros(N, dtype=torch.float32, device=device)
+        depth = torch.zeros(N, dtype=torch.float32, device=device)
+        image = torch.zeros(N, 3, dtype=torch.float32, device=device)
+        rays_alive = torch.arange(N, dtype=torch.int32, device=device)
+        rays_t = nears.clone()
+        step = 0
+        field = self.forward_fused if fused_field else self.forward
+        while step < max_steps:
+            n_alive = rays_alive.shape[0]
+            if n_alive <= 0:
+                break
+            n_step = max(min(N // n_alive, 8), 1)
+            xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
+                                                        self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128,
+                                                        perturb if step == 0 else False, dt_gamma, max_steps)
+            sigmas, rgbs = field(xyzs, dirs)
+            sigmas = self.density_scale * sigmas
+            raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
+            rays_alive = rays_alive[rays_alive >= 0]
+            step += n_step
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        return {"depth": depth.view(*prefix), "image": image.view(*prefix, 3), "weights_sum": weights_sum}
+
+    # ------------------------------------------------------------------ nerf/renderer.py:755-907
+    @torch.no_grad()
+    def rund_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024, T_thresh=1e-2, fused_field=False,
+                  return_stats=False, **kwargs):
+        dtype = torch.float32
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3); rays_d = rays_d.contiguous().view(-1, 3)
+        N = rays_o.shape[0]; device = rays_o.device
+        max_iter_num = kwargs.get("max_iter_num"); hgs = kwargs.get("hash_grid_size"); bound = kwargs.get("bound", self.bound)
+        cut = bool(kwargs.get("cut")); num_seek_IP = kwargs.get("num_seek_IP")
+        cut_bounds = torch.tensor(kwargs.get("cut_bounds") or [0.0] * 6, dtype=dtype, device=device)
+        p_def = self.p_def.contiguous().cuda(); p_ori = self.p_ori.contiguous().cuda()
+        F_IP = self.IP_F.contiguous().cuda(); dF_IP = self.IP_dF.contiguous().cuda()
+        bbmin, bbmax, resolution = raymarching.ip_bbox(p_def, hgs, cut, bound)      # renderer.py:782-791, one kernel
+        aabb = torch.cat((bbmin, bbmax), dim=0)
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, aabb, self.min_near)
+        if bg_color is None:
+            bg_color = 1
+        weights_sum = torch.zeros(N, dtype=dtype, device=device)
+        depth = torch.zeros(N, dtype=dtype, device=device)
+        image = torch.zeros(N, 3, dtype=dtype, device=device)
+        n_vtx = p_ori.shape[0]
+        n_grid = int(resolution[2] * resolution[1] * resolution[0])                  # host sync, as in the reference
+        assert p_def.shape == p_ori.shape and n_vtx > 0
+        pig_cnt, pig_bgn, pig_idx = raymarching.get_pnts_in_grids(n_vtx, n_grid, p_def, bbmin, bbmax, hgs, resolution)
+        rays_alive = torch.arange(N, dtype=torch.int32, device=device)
+        rays_t = nears.clone()
+        step = 0; n_samples = 0; iters = 0
+        field = self.forward_fused if fused_field else self.forward
+        while step < max_steps:
+            n_alive = rays_alive.shape[0]
+            if n_alive <= 0:
+                break
+            n_step = max(min(N // n_alive, 8), 1)
+            xyzs, dirs, deltas = raymarching.march_rays_quadratic_bending(
+                pig_cnt, pig_bgn, pig_idx, n_vtx, n_grid, p_def, p_ori, F_IP, dF_IP, max_iter_num, bbmin, bbmax, hgs, resolution,
+                num_seek_IP, self.IP_dx, cut, cut_bounds, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
+                self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128, perturb if step == 0 else False, dt_gamma, max_steps)
+            sigmas, rgbs = field(xyzs, dirs)
+            sigmas = self.density_scale * sigmas
+            if return_stats:
+                n_samples += int((deltas[:, 0] != 0).sum()); iters += 1
+            raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
+            rays_alive = rays_alive[rays_alive >= 0]
+            step += n_step
+        depth_0 = depth
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        out = {"depth": depth.view(*prefix), "image": image.view(*prefix, 3), "depth_0": depth_0.view(*prefix), "weights_sum": weights_sum}
+        if return_stats:
+            out["n_samples"] = n_samples; out["iters"] = iters
+        return out
+
+    # ------------------------------------------------------------------ fused frame (product path)
+    @torch.no_grad()
+    def render_deformed(self, rays_o, rays_d, staged=False, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024, T_thresh=1e-2,
+                        mode=0, out=None, **kwargs):
+        """renderer.py:587-599 -> rund_cuda semantics in one device-resident call.  Returns the same dict."""
+        if perturb:
+            raise NotImplementedError("perturb is only used with spp>1 accumulation, which the sim GUI never does (gui.py:620-622)")
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.to(torch.float32).contiguous().view(-1, 3); rays_d = rays_d.to(torch.float32).contiguous().view(-1, 3)
+        N = rays_o.shape[0]; device = rays_o.device
+        hgs = float(kwargs.get("hash_grid_size")); bound = float(kwargs.get("bound", self.bound))
+        d = DeformT()
+        keep = [self.p_def.to(torch.float32).contiguous(), self.p_ori.to(torch.float32).contiguous(),
+                self.IP_F.to(torch.float32).contiguous(), self.IP_dF.to(torch.float32).contiguous()]
+        d.p_def, d.p_ori, d.F_IP, d.dF_IP = [dptr(t) for t in keep]
+        d.n_vtx = keep[0].shape[0]; d.IP_dx = float(self.IP_dx)
+        d.density_bitfield = dptr(self.density_bitfield, "density_bitfield", torch.uint8)
+        d.bound, d.cascade, d.grid_size = float(self.bound), int(self.cascade), int(self.grid_size)
+        d.min_near, d.density_scale, d.dt_gamma = float(self.min_near), float(self.density_scale), float(dt_gamma)
+        d.max_steps, d.T_thresh, d.max_iter_num = int(max_steps), float(T_thresh), int(kwargs.get("max_iter_num"))
+        d.hgs, d.cut = hgs, int(bool(kwargs.get("cut")))
+        cb = kwargs.get("cut_bounds") or [0.0] * 6
+        for i in range(6):
+            d.cut_bounds[i] = float(cb[i])
+        d.num_seek_IP = int(kwargs.get("num_seek_IP"))
+        d.bg_color = 1.0 if bg_color is None else float(bg_color)
+        need = int(lib.pn_render_workspace_bytes(N, d.n_vtx, bound, hgs))
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
+            self._stats = torch.zeros(4, dtype=torch.int64, device=device)
+        if out is None:
+            out = {"image": torch.empty(N, 3, dtype=torch.float32, device=device), "depth": torch.empty(N, dtype=torch.float32, device=device),
+                   "depth_0": torch.empty(N, dtype=torch.float32, device=device), "weights_sum": torch.empty(N, dtype=torch.float32, device=device)}
+        f = self._field_struct()
+        check(lib.pn_render_deformed(C.byref(f), C.byref(d), dptr(rays_o), dptr(rays_d), N, dptr(out["image"]), dptr(out["depth"]),
+                                     dptr(out["depth_0"]), dptr(out["weights_sum"]), dptr(self._workspace), need, dptr(self._stats),
+                                     int(mode), stream_ptr()))
+        return {"image": out["image"].view(*prefix, 3), "depth": out["depth"].view(*prefix), "depth_0": out["depth_0"].view(*prefix),
+                "weights_sum": out["weights_sum"], "stats": self._stats}

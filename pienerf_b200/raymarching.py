@@ -1,0 +1,184 @@
+"""Host-side mirror of raymarching/raymarching.py (inference functions) plus the two per-frame helpers the
+renderer takes from nerf/utils.py (get_rays, get_pnts_in_grids).  Same names, argument order, return values and
+caller-allocates-zeroed-outputs convention as the reference wrappers."""
+import torch
+
+from . import _raymarching as _backend
+from ._lib import check, dptr, lib, stream_ptr
+
+
+def _f32c(t):
+    return t.to(torch.float32).contiguous()
+
+
+@torch.no_grad()
+def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):
+    """raymarching.py:21-51."""
+    if not rays_o.is_cuda: rays_o = rays_o.cuda()
+    if not rays_d.is_cuda: rays_d = rays_d.cuda()
+    rays_o = _f32c(rays_o).view(-1, 3)
+    rays_d = _f32c(rays_d).view(-1, 3)
+    N = rays_o.shape[0]
+    nears = torch.empty(N, dtype=rays_o.dtype, device=rays_o.device)
+    fars = torch.empty(N, dtype=rays_o.dtype, device=rays_o.device)
+    _backend.near_far_from_aabb(rays_o, rays_d, _f32c(aabb), N, min_near, nears, fars)
+    return nears, fars
+
+
+@torch.no_grad()
+def sph_from_ray(rays_o, rays_d, radius):
+    """raymarching.py:54-82."""
+    rays_o = _f32c(rays_o.cuda()).view(-1, 3)
+    rays_d = _f32c(rays_d.cuda()).view(-1, 3)
+    N = rays_o.shape[0]
+    coords = torch.empty(N, 2, dtype=rays_o.dtype, device=rays_o.device)
+    _backend.sph_from_ray(rays_o, rays_d, radius, N, coords)
+    return coords
+
+
+@torch.no_grad()
+def morton3D(coords):
+    """raymarching.py:85-106."""
+    if not coords.is_cuda: coords = coords.cuda()
+    N = coords.shape[0]
+    indices = torch.empty(N, dtype=torch.int32, device=coords.device)
+    _backend.morton3D(coords.int().contiguous(), N, indices)
+    return indices
+
+
+@torch.no_grad()
+def morton3D_invert(indices):
+    """raymarching.py:108-128."""
+    if not indices.is_cuda: indices = indices.cuda()
+    N = indices.shape[0]
+    coords = torch.empty(N, 3, dtype=torch.int32, device=indices.device)
+    _backend.morton3D_invert(indices.int().contiguous(), N, coords)
+    return coords
+
+
+@torch.no_grad()
+def packbits(grid, thresh, bitfield=None):
+    """raymarching.py:131-157."""
+    if not grid.is_cuda: grid = grid.cuda()
+    grid = _f32c(grid)
+    C, H3 = grid.shape[0], grid.shape[1]
+    N = C * H3 // 8
+    if bitfield is None:
+        bitfield = torch.empty(N, dtype=torch.uint8, device=grid.device)
+    _backend.packbits(grid, N, thresh, bitfield)
+    return bitfield
+
+
+def _alloc_samples(n_alive, n_step, align, like):
+    M = n_alive * n_step
+    if align > 0:
+        M += align - (M % align)                               # raymarching.py:337-338: always pads 1..align rows
+    xyzs = torch.zeros(M, 3, dtype=like.dtype, device=like.device)
+    dirs = torch.zeros(M, 3, dtype=like.dtype, device=like.device)
+    deltas = torch.zeros(M, 2, dtype=like.dtype, device=like.device)
+    return xyzs, dirs, deltas
+
+
+@torch.no_grad()
+def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, density_bitfield, C, H, near, far, align=-1,
+               perturb=False, dt_gamma=0, max_steps=1024):
+    """raymarching.py:299-359."""
+    if not rays_o.is_cuda: rays_o = rays_o.cuda()
+    if not rays_d.is_cuda: rays_d = rays_d.cuda()
+    rays_o = _f32c(rays_o).view(-1, 3)
+    rays_d = _f32c(rays_d).view(-1, 3)
+    xyzs, dirs, deltas = _alloc_samples(n_alive, n_step, align, rays_o)
+    if perturb:
+        noises = torch.rand(n_alive, dtype=rays_o.dtype, device=rays_o.device)
+    else:
+        noises = torch.zeros(n_alive, dtype=rays_o.dtype, device=rays_o.device)
+    _backend.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
+                        density_bitfield, near, far, xyzs, dirs, deltas, noises)
+    return xyzs, dirs, deltas
+
+
+@torch.no_grad()
+def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2):
+    """raymarching.py:362-384 (in-place on rays_alive, rays_t, weights_sum, depth, image)."""
+    _backend.composite_rays(n_alive, n_step, T_thresh, rays_alive, rays_t, _f32c(sigmas), _f32c(rgbs), deltas, weights_sum,
+                            depth, image)
+    return tuple()
+
+
+@torch.no_grad()
+def march_rays_quadratic_bending(pig_cnt, pig_bgn, pig_idx, n_vtx, n_grid, p_def, p_ori, F_IP, dF_IP, max_iter_num, bbmin,
+                                 bbmax, hgs, res, num_seek_IP, IP_dx, cut, cut_bounds, n_alive, n_step, rays_alive, rays_t,
+                                 rays_o, rays_d, bound, density_bitfield, C, H, near, far, align=-1, perturb=False,
+                                 dt_gamma=0, max_steps=1024):
+    """raymarching.py:387-441."""
+    if not rays_o.is_cuda: rays_o = rays_o.cuda()
+    if not rays_d.is_cuda: rays_d = rays_d.cuda()
+    rays_o = _f32c(rays_o).view(-1, 3)
+    rays_d = _f32c(rays_d).view(-1, 3)
+    xyzs, dirs, deltas = _alloc_samples(n_alive, n_step, align, rays_o)
+    if perturb:
+        noises = torch.rand(n_alive, dtype=rays_o.dtype, device=rays_o.device)
+    else:
+        noises = torch.zeros(n_alive, dtype=rays_o.dtype, device=rays_o.device)
+    _backend.march_rays_quadratic_bending(
+        pig_cnt, pig_bgn, pig_idx, int(n_vtx), int(n_grid), _f32c(p_def), _f32c(p_ori), _f32c(F_IP), _f32c(dF_IP),
+        max_iter_num, _f32c(bbmin), _f32c(bbmax), hgs, res, num_seek_IP, IP_dx, cut, _f32c(cut_bounds),
+        n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, density_bitfield, near, far,
+        xyzs, dirs, deltas, noises)
+    return xyzs, dirs, deltas
+
+
+def _not_hot_path(*a, **k):
+    _backend.march_rays_train()
+
+
+march_rays_train = _not_hot_path
+composite_rays_train = _not_hot_path
+
+
+# ---- nerf/utils.py pieces of the hot path --------------------------------------------------------------
+
+@torch.no_grad()
+def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1):
+    """nerf/utils.py:55-138 for the full-frame case the GUI path uses (N=-1, B=1)."""
+    if N > 0 or error_map is not None or patch_size != 1:
+        raise NotImplementedError("ray sub-sampling is training-side; the hot path renders full frames (N=-1)")
+    poses = torch.as_tensor(poses, dtype=torch.float32)
+    if poses.dim() == 3:
+        if poses.shape[0] != 1:
+            raise NotImplementedError("B must be 1")
+        poses = poses[0]
+    pose_host = poses.detach().cpu().contiguous()
+    fx, fy, cx, cy = [float(torch.tensor(float(v), dtype=torch.float32)) for v in intrinsics]
+    dev = torch.device("cuda")
+    rays_o = torch.empty(1, H * W, 3, dtype=torch.float32, device=dev)
+    rays_d = torch.empty(1, H * W, 3, dtype=torch.float32, device=dev)
+    import ctypes
+    check(lib.pn_get_rays(ctypes.c_void_p(pose_host.data_ptr()), fx, fy, cx, cy, int(H), int(W), dptr(rays_o), dptr(rays_d),
+                          stream_ptr()))
+    return {"rays_o": rays_o, "rays_d": rays_d, "inds": None}
+
+
+@torch.no_grad()
+def ip_bbox(p_def, hgs, cut=False, bound=1.0):
+    """nerf/renderer.py:782-791 as one kernel: returns bbmin[3], bbmax[3] (f32) and resolution[3] (i32) on device."""
+    p_def = _f32c(p_def)
+    bbmin = torch.empty(3, dtype=torch.float32, device=p_def.device)
+    bbmax = torch.empty(3, dtype=torch.float32, device=p_def.device)
+    res = torch.empty(3, dtype=torch.int32, device=p_def.device)
+    check(lib.pn_ip_bbox(dptr(p_def), p_def.shape[0], float(hgs), int(bool(cut)), float(bound), dptr(bbmin), dptr(bbmax),
+                         dptr(res), stream_ptr()))
+    return bbmin, bbmax, res
+
+
+@torch.no_grad()
+def get_pnts_in_grids(n_vtx, n_grid, pnts, bbmin, bbmax, hgs, resolution):
+    """nerf/utils.py:355-386: (pig_cnt, pig_bgn, pig_idx).  Within-cell order is ascending IP index."""
+    n_grid = int(n_grid)
+    pnts = _f32c(pnts)
+    pig_idx = torch.zeros((n_vtx,), dtype=torch.int32, device=pnts.device)
+    pig_cnt = torch.zeros((n_grid,), dtype=torch.int32, device=pnts.device)
+    pig_bgn = torch.zeros((n_grid,), dtype=torch.int32, device=pnts.device)
+    check(lib.pn_build_ip_grid(dptr(pnts), int(n_vtx), dptr(_f32c(bbmin)), float(hgs), dptr(resolution.to(torch.int32).contiguous()),
+                               n_grid, dptr(pig_cnt), dptr(pig_bgn), dptr(pig_idx), stream_ptr()))
+    return pig_cnt, pig_bgn, pig_idx

@@ -1,0 +1,116 @@
+"""CPU tests of host-side logic: synthetic fixtures, options, ply I/O, tile sharding and the N>1 gather/broadcast
+path on the gloo backend with world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from pienerf_b200.synthetic import CONFIGS, make_body, make_field, occupancy_bitfield, orbit_intrinsics, orbit_pose, sim_lattice
+
+
+def test_bodies_match_survey_sizes():
+    assert make_body("block512")["pos"].shape[0] == 512
+    assert make_body("chair2k")["pos"].shape[0] == 2028
+    assert make_body("block4k")["pos"].shape[0] == 4096
+    assert make_body("block8k", bound=2.0)["pos"].shape[0] == 8000
+    c = make_body("chairlike")
+    assert 1900 < c["pos"].shape[0] < 2200 and np.abs(c["pos"]).max() < 0.75
+    base, res = sim_lattice(1.0, 0.05)
+    assert res == 40 and abs(base[0] + 1.01) < 1e-6
+    b = make_body("block64")
+    cells = np.floor((b["pos"] - base) / 0.05).astype(int)
+    assert len({tuple(c) for c in cells}) == 64 and (cells == b["cells"]).all()       # one point per simulator cell
+    assert b["pin"].sum() == 16 and np.allclose(b["mass"], 1e3 * 0.05 ** 3)
+
+
+def test_field_and_bitfield():
+    f = make_field(bound=1.0)
+    assert f["embeddings"].shape == (6119864, 2) and f["sigma_net"][0].shape == (64, 32) and f["color_net"][0].shape == (64, 31)
+    assert f["color_net"][2].shape == (3, 64) and f["sigma_net"][1].shape == (16, 64)
+    b = make_body("block64")
+    bits = occupancy_bitfield(b["pos"], 0.03, bound=1.0)
+    assert bits.shape == (128 ** 3 // 8,) and 0 < np.unpackbits(bits).sum() < 4000
+    bits2 = occupancy_bitfield(make_body("block64", bound=2.0)["pos"], 0.03, bound=2.0)
+    assert bits2.shape == (2 * 128 ** 3 // 8,)
+
+
+def test_camera_and_options():
+    from pienerf_b200.frame import Options
+    p = orbit_pose(radius=2.5)
+    R = p[:3, :3]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-6) and abs(np.linalg.norm(p[:3, 3]) - 2.5) < 1e-5
+    intr = orbit_intrinsics(800, 800, 50)
+    assert intr[2] == 400 and abs(intr[0] - 800 / (2 * np.tan(np.radians(25)))) < 1e-9
+    o = Options.defaults(num_seek_IP=7, sim_dx=0.05)
+    assert o.num_seek_IP == 3 and abs(o.hash_grid_size - 0.06) < 1e-12 and o.max_iter_num == 100
+    assert set(CONFIGS) >= {"chair", "trex", "synth1080", "step512"}
+
+
+def test_ply_io_roundtrip(tmp_path):
+    from pienerf_b200.ply import read_ply_vertices, write_ply_xyz
+    b = make_body("block64")
+    path = str(tmp_path / "b.ply")
+    write_ply_xyz(path, b["pos"], extra={"mass": b["mass"], "pin": b["pin"].astype(float)})
+    v = read_ply_vertices(path)
+    assert np.array_equal(v["x"], b["pos"][:, 0]) and np.array_equal(v["mass"], b["mass"]) and v["pin"].sum() == 16
+    with open(str(tmp_path / "a.ply"), "w") as fh:
+        fh.write("ply\nformat ascii 1.0\nelement vertex 2\nproperty float x\nproperty float y\nproperty float z\nend_header\n1 2 3\n4 5 6\n")
+    v = read_ply_vertices(str(tmp_path / "a.ply"))
+    assert v["z"].tolist() == [3.0, 6.0]
+
+
+def test_tile_partition_covers_frame():
+    from pienerf_b200.dist import tile_partition
+    for ws in (1, 2, 4, 8):
+        parts = tile_partition(800, 800, ws)
+        allp = np.concatenate(parts)
+        assert allp.size == 640000 and np.array_equal(np.sort(allp), np.arange(640000))
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 0.02 * 640000 / ws + 256
+        # balance over the centre of the frame (where the object is)
+        centre = np.zeros((800, 800), bool); centre[250:550, 250:550] = True
+        c = [int(centre.reshape(-1)[p].sum()) for p in parts]
+        assert max(c) - min(c) <= 0.1 * 90000 / ws + 512
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pienerf_b200.dist import FrameGather, broadcast_ip_state, pack_ip_state, tile_partition, unpack_ip_state
+    try:
+        n = 50
+        buf = torch.zeros(n, 39)
+        if rank == 0:
+            g = torch.Generator().manual_seed(0)
+            buf = pack_ip_state(torch.rand(n, 3, generator=g), torch.rand(n, 9, generator=g), torch.rand(n, 27, generator=g))
+        broadcast_ip_state(buf)
+        g = torch.Generator().manual_seed(0)
+        want = pack_ip_state(torch.rand(n, 3, generator=g), torch.rand(n, 9, generator=g), torch.rand(n, 27, generator=g))
+        ok = torch.equal(buf, want) and unpack_ip_state(buf)[2].shape == (n, 27)
+        H, W = 40, 56
+        parts = tile_partition(H, W, world, tile=8)
+        gather = FrameGather(parts, 3, "cpu")
+        full = torch.arange(H * W * 3, dtype=torch.float32).reshape(H * W, 3)
+        frame = gather(full[torch.from_numpy(parts[rank])])
+        if rank == 0:
+            ok = ok and torch.equal(frame, full)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_and_gather_world_size_2():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
