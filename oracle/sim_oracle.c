@@ -429,7 +429,8 @@ int qo_initialize(QO *s, int n_pts, const double *pos, const double *mass, const
     for (int i = 0, k = 0; i < R0; i++) for (int j = 0; j < R1; j++) for (int l = 0; l < R2; l++)
         if (mask[((size_t)i*R1 + j)*R2 + l]) {             /* solver.py:162-177 */
             int g[3] = {i, j, l};
-            for (int c = 0; c < 3; c++) { s->ip_grid[3*k+c] = g[c]; s->ip_pos[3*k+c] = (g[c] + 0.5)*s->dx + s->base[c]; }
+            /* solver.py:177: `(IP_grid + 0.5) * dx` is int32 + python float -> float32 in torch, widened by `+ base` */
+            for (int c = 0; c < 3; c++) { s->ip_grid[3*k+c] = g[c]; s->ip_pos[3*k+c] = (double)(((float)g[c] + 0.5f)*(float)s->dx) + s->base[c]; }
             k++;
         }
     int rmax = R0 > R1 ? (R0 > R2 ? R0 : R2) : (R1 > R2 ? R1 : R2);

@@ -43,7 +43,7 @@ def test_frame_vs_oracle(amp, K):
     fused = model.render_deformed(ro_, rd_, **kw, **opt)
     torch.cuda.synchronize()
     hit = want["weights_sum"] > 0
-    assert hit.sum() > 100 and want["n_samples"] > 2000
+    assert hit.sum() > 100 and want["n_samples"] > 1000
     for name, got in (("loop", loop), ("fused", fused)):
         img = got["image"][0].cpu().numpy(); ws = got["weights_sum"].cpu().numpy(); d0 = got["depth_0"][0].cpu().numpy()
         # knife-edge occupancy flips (fp32 FMA contraction) can move a handful of silhouette pixels
