@@ -214,7 +214,9 @@ struct RenderArgs {
 template <int KMAX>
 __global__ void __launch_bounds__(128, 3) render_persistent(const RenderArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    pn::FieldSmem &fs = *reinterpret_cast<pn::FieldSmem *>(smem_raw);
+    pn::FieldBlockSmem &fbs = *reinterpret_cast<pn::FieldBlockSmem *>(smem_raw);
+    pn::FieldSmem &fs = fbs.w;
+    float *scratch = fbs.scratch + threadIdx.x;
     pn::field_smem_fill(fs, A.field);
     pn::BendCfg bc = A.bend;
 #pragma unroll
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(128, 3) render_persistent(const RenderArgs A) 
         // ---- field + composite for lanes that produced a sample
         if (have) {
             float sigma, r, g, b;
-            pn::field_eval(fs, table, A.field.bound, x, y, z, sh, sigma, r, g, b);
+            pn::field_eval(fs, table, A.field.bound, x, y, z, sh, scratch, pn::kFieldThreads, sigma, r, g, b);
             sigma = A.density_scale * sigma;
             const float alpha = 1.0f - __expf(-sigma * dt);
             const float T = 1 - ws;
@@ -319,8 +321,9 @@ __global__ void __launch_bounds__(128, 3) render_persistent(const RenderArgs A) 
 }
 
 __global__ void copy_stats_kernel(const FrameQueue *q, long long *stats) {
-    stats[0] = q->samples;
-    stats[1] = q->n_active;
+    stats[0] = q->samples;   // composited samples
+    stats[1] = q->n_active;  // rays that hit the IP box
+    stats[2] = q->pad;       // field evaluations (>= stats[0]: samples marched past an early termination)
 }
 
 // stand-alone field pass over M samples (the body of NeRFNetwork.forward as one kernel)
@@ -328,7 +331,9 @@ __global__ void __launch_bounds__(128, 3) field_forward_kernel(const pn_field_t 
                                                                const float *__restrict__ dirs, uint32_t M,
                                                                float *__restrict__ sigmas, float *__restrict__ rgbs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    pn::FieldSmem &fs = *reinterpret_cast<pn::FieldSmem *>(smem_raw);
+    pn::FieldBlockSmem &fbs = *reinterpret_cast<pn::FieldBlockSmem *>(smem_raw);
+    pn::FieldSmem &fs = fbs.w;
+    float *scratch = fbs.scratch + threadIdx.x;
     pn::field_smem_fill(fs, f);
     __syncthreads();
     const float2 *table = reinterpret_cast<const float2 *>(f.embeddings);
@@ -336,14 +341,14 @@ __global__ void __launch_bounds__(128, 3) field_forward_kernel(const pn_field_t 
         float sh[16];
         pn::sh_eval<4>(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], sh);
         float sigma, r, g, b;
-        pn::field_eval(fs, table, f.bound, xyzs[3 * i], xyzs[3 * i + 1], xyzs[3 * i + 2], sh, sigma, r, g, b);
+        pn::field_eval(fs, table, f.bound, xyzs[3 * i], xyzs[3 * i + 1], xyzs[3 * i + 2], sh, scratch, pn::kFieldThreads, sigma, r, g, b);
         sigmas[i] = sigma;
         rgbs[3 * i] = r; rgbs[3 * i + 1] = g; rgbs[3 * i + 2] = b;
     }
 }
 
 struct WorkspaceLayout {
-    size_t geom, queue, nears, fars, active, pig_cnt, pig_bgn, pig_fill, pig_idx, total;
+    size_t geom, queue, nears, fars, active, pig_cnt, pig_bgn, pig_fill, pig_idx, ip_pos, ip_rec, total;
 };
 
 WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
@@ -356,9 +361,11 @@ WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
     w.fars = take(sizeof(float) * N);
     w.active = take(sizeof(int) * N);
     w.pig_cnt = take(sizeof(int) * (size_t)max_cells);
-    w.pig_bgn = take(sizeof(int) * (size_t)max_cells);
+    w.pig_bgn = take(sizeof(int) * ((size_t)max_cells + 1));
     w.pig_fill = take(sizeof(int) * (size_t)max_cells);
     w.pig_idx = take(sizeof(int) * (size_t)n_vtx);
+    w.ip_pos = take(sizeof(float4) * (size_t)n_vtx);
+    w.ip_rec = take(sizeof(float) * 16 * (size_t)n_vtx);
     w.total = o;
     return w;
 }
@@ -378,6 +385,8 @@ int set_smem(K kernel, size_t bytes) {
 }
 
 }  // namespace
+
+#include "render_warp.cuh"
 
 extern "C" int pn_get_rays(const float *pose, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
                            float *rays_o, float *rays_d, void *stream) {
@@ -428,7 +437,7 @@ extern "C" int pn_field_forward(const pn_field_t *f, const float *xyzs, const fl
     PN_REQUIRE(f->L == pn::kLevels, "fused field expects the 16-level C=2 D=3 grid of nerf/network.py");
     PN_REQUIRE(mode == 0, "unknown field mode");
     if (M == 0) return PN_OK;
-    const size_t smem = sizeof(pn::FieldSmem);
+    const size_t smem = sizeof(pn::FieldBlockSmem);
     if (int rc = set_smem(field_forward_kernel, smem)) return rc;
     const uint32_t blocks = min(div_up(M, 128u), (uint32_t)pn_sm_count_cached() * 3u);
     field_forward_kernel<<<blocks, 128, smem, PN_STREAM(stream)>>>(*f, xyzs, dirs, M, sigmas, rgbs);
@@ -452,7 +461,7 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
                                   void *workspace, uint64_t workspace_bytes, long long *stats, int mode, void *stream) {
     PN_REQUIRE(f && d && rays_o && rays_d && image && depth && depth_0 && weights_sum && workspace, "null pointer");
     PN_REQUIRE(f->L == pn::kLevels, "fused field expects the 16-level C=2 D=3 grid of nerf/network.py");
-    PN_REQUIRE(mode == 0, "unknown render mode");
+    PN_REQUIRE(mode == 0 || mode == 1, "render mode: 0 = warp-cooperative (default), 1 = one lane per ray");
     PN_REQUIRE(d->n_vtx > 0 && d->num_seek_IP >= 1 && d->num_seek_IP <= 3, "need IPs and num_seek_IP in 1..3");
     PN_REQUIRE(d->cascade >= 1 && d->cascade <= 8 && d->grid_size == 128, "cascade/grid_size out of range");
     if (N == 0) return PN_OK;
@@ -489,8 +498,31 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
     A.image = image; A.depth = depth; A.depth0 = depth_0; A.wsum = weights_sum;
     A.density_scale = d->density_scale; A.T_thresh = d->T_thresh; A.bg = d->bg_color; A.max_samples = d->max_steps;
 
-    const size_t smem = sizeof(pn::FieldSmem);
     const uint32_t blocks = (uint32_t)pn_sm_count_cached() * 3u;
+    if (mode == 0) {
+        float4 *ip_pos = (float4 *)(base + w.ip_pos);
+        float *ip_rec = (float *)(base + w.ip_rec);
+        ip_pack_kernel<<<div_up(d->n_vtx, 256), 256, 0, st>>>(d->p_def, d->p_ori, d->F_IP, idx, d->n_vtx, geom->res, max_cells, bgn, ip_pos, ip_rec);
+        PN_LAUNCH_CHECK("ip_pack_kernel");
+        IpPack P{ip_pos, ip_rec, bgn};
+        const size_t smem = ((sizeof(pn::FieldBlockSmem) + 15) & ~size_t(15)) + 4 * sizeof(WarpShared);
+        if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
+        switch (d->num_seek_IP) {
+            case 1:
+                if (int rc = set_smem(render_warp_kernel<1>, smem)) return rc;
+                render_warp_kernel<1><<<blocks, 128, smem, st>>>(A, P);
+                break;
+            case 2:
+                if (int rc = set_smem(render_warp_kernel<2>, smem)) return rc;
+                render_warp_kernel<2><<<blocks, 128, smem, st>>>(A, P);
+                break;
+            default:
+                if (int rc = set_smem(render_warp_kernel<3>, smem)) return rc;
+                render_warp_kernel<3><<<blocks, 128, smem, st>>>(A, P);
+                break;
+        }
+    } else {
+    const size_t smem = sizeof(pn::FieldBlockSmem);
     if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
     switch (d->num_seek_IP) {
         case 1:
@@ -505,6 +537,7 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
             if (int rc = set_smem(render_persistent<3>, smem)) return rc;
             render_persistent<3><<<blocks, 128, smem, st>>>(A);
             break;
+    }
     }
     PN_LAUNCH_CHECK("render_persistent");
     if (g_prof_stop) PN_CUDA(cudaEventRecord(g_prof_stop, st));

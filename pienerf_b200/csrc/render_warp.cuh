@@ -1,0 +1,401 @@
+// Warp-cooperative deformed-space renderer (render mode 0).  Included by render_fused.cu.
+//
+// Observation that makes this exact: every t the reference's march loop ever visits on a ray lies on ONE
+// deterministic lattice t_{k+1} = t_k + clamp(t_k * dt_gamma, dt_min, dt_max), t_0 = near, whether the step is an
+// emitted sample (`t += dt`) or part of the empty-space skip loop (`do t += dt while (t < tt)`),
+// raymarching.cu:1385-1432.  So the 32 lanes of a warp evaluate 32 consecutive lattice points of the SAME ray in
+// parallel (inverse warp + occupancy), and a ballot-driven resolve replays the reference's visit order
+// (emit -> next point, skip -> first point with t >= voxel exit).  Consequences:
+//   * neighbouring lanes sit ~dt apart: their IP-grid cells, IP records and hash-grid cells mostly coincide,
+//     so gathers coalesce into a few cache lines instead of 32;
+//   * the work unit is a 32-sample chunk, not a ray: load balance no longer depends on rays per lane;
+//   * emitted samples go through a per-warp FIFO (tagged by ray) so the field kernel always runs on full
+//     32-sample tiles even when rays are short; compositing replays the reference's sequential recurrence in
+//     order (bit-identical accumulation order), with early termination fed back to the marcher.
+#pragma once
+
+namespace {
+
+struct IpPack {
+    const float4 *pos;      // [n] (p_def.xyz, bitcast original ip) in cell order
+    const float *rec;       // [n,16]: p_ori(0..2) p_def(3..5) Finv(6..14) for the max_iter_num == 1 fast path
+    const int *cell_start;  // [n_grid+1]
+};
+
+// Per-frame packing of the IP state in IP-grid cell order.  Finv uses the very arithmetic of the per-sample
+// inverse (pn::adjugate_inverse), so hoisting it out of the march loop changes no bit when max_iter_num == 1
+// (first Newton iterate: q = 0 => A = F exactly, b = -q_ exactly; raymarching.cu:1268-1304).
+__global__ void __launch_bounds__(256) ip_pack_kernel(const float *__restrict__ p_def, const float *__restrict__ p_ori,
+                                                      const float *__restrict__ F, const int *__restrict__ idx, int n,
+                                                      const int *__restrict__ res, int n_grid_cap, int *__restrict__ bgn,
+                                                      float4 *__restrict__ pos_out, float *__restrict__ rec_out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) bgn[min(res[0] * res[1] * res[2], n_grid_cap)] = n;  // terminal entry of the CSR
+    if (k >= n) return;
+    const int ip = idx[k];
+    const float px = p_def[3 * ip], py = p_def[3 * ip + 1], pz = p_def[3 * ip + 2];
+    pos_out[k] = make_float4(px, py, pz, __int_as_float(ip));
+    float A[9], Ai[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) A[i] = F[9 * ip + i] + 0.0f;  // Fk[m] + dFk_q[m] with dFk_q == +0
+    pn::adjugate_inverse(A, Ai);
+    float *r = rec_out + 16 * (size_t)k;
+    r[0] = p_ori[3 * ip]; r[1] = p_ori[3 * ip + 1]; r[2] = p_ori[3 * ip + 2];
+    r[3] = px; r[4] = py; r[5] = pz;
+#pragma unroll
+    for (int i = 0; i < 9; i++) r[6 + i] = Ai[i];
+    r[15] = 0.f;
+}
+
+__device__ __forceinline__ bool key_less(float d, int r, float d2, int r2) { return d < d2 || (d == d2 && r < r2); }
+
+// Nearest-K search over the 27 cells around (g0,g1,g2) with the reference's semantics (raymarching.cu:986-1118):
+// candidates are ranked by (distance^2, order in which the reference would have visited them) so that exact ties
+// resolve as the reference's strict-less insertion does, independent of our traversal order.
+// rank[27] maps (dz+1)*9+(dy+1)*3+(dx+1) -> visit order of that cell.  Returns the number of slots filled;
+// ks[] are positions in the cell-sorted arrays.
+template <int KMAX>
+__device__ __forceinline__ int nearest_sorted(const IpPack &P, const pn::BendCfg &c, const unsigned char *rank, float x,
+                                              float y, float z, int g0, int g1, int g2, bool own_cell_only, float dmax,
+                                              int (&ks)[KMAX]) {
+    float bd[KMAX];
+    int br[KMAX];
+#pragma unroll
+    for (int i = 0; i < KMAX; i++) { bd[i] = dmax; br[i] = 0x7fffffff; ks[i] = -1; }
+    const int lo = max(g0 - 1, 0), hi = min(g0 + 1, c.res[0] - 1);
+    for (int dz = -1; dz <= 1; dz++) {
+        const int a2 = g2 + dz;
+        if (a2 < 0 || a2 >= c.res[2]) continue;
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; dy++) {
+            const int a1 = g1 + dy;
+            if (a1 < 0 || a1 >= c.res[1]) continue;
+            if (own_cell_only && (dz != 0 || dy != 0)) continue;
+            const int row = (a2 * c.res[1] + a1) * c.res[0];
+            // cells lo..hi of a row are contiguous in the cell-sorted array: one range, <= 4 boundaries
+            int b[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = (lo + j <= hi + 1) ? __ldg(P.cell_start + row + lo + j) : 0x7fffffff;
+            const int nb = hi - lo + 1, own = g0 - lo;                     // nb in 1..3 cells, own in 0..1
+            int first = b[0], last = nb == 3 ? b[3] : (nb == 2 ? b[2] : b[1]);
+            if (own_cell_only) { first = own == 0 ? b[0] : b[1]; last = own == 0 ? b[1] : b[2]; }
+            for (int k = first; k < last; k++) {
+                const float4 q = __ldg(P.pos + k);
+                const float d = (q.x - x) * (q.x - x) + (q.y - y) * (q.y - y) + (q.z - z) * (q.z - z);
+                const int cell = lo + (k >= b[1]) + (k >= b[2]);      // which of the <=3 cells this entry is in
+                const int cbeg = cell == lo ? b[0] : (cell == lo + 1 ? b[1] : b[2]);
+                const int r = ((int)rank[(dz + 1) * 9 + (dy + 1) * 3 + (cell - g0 + 1)] << 8) + (k - cbeg);
+                if (KMAX == 1) {
+                    if (key_less(d, r, bd[0], br[0])) { bd[0] = d; br[0] = r; ks[0] = k; }
+                } else if (KMAX == 2) {
+                    if (key_less(d, r, bd[KMAX - 1], br[KMAX - 1])) {
+                        if (key_less(d, r, bd[0], br[0])) { bd[KMAX - 1] = bd[0]; br[KMAX - 1] = br[0]; ks[KMAX - 1] = ks[0]; bd[0] = d; br[0] = r; ks[0] = k; }
+                        else { bd[KMAX - 1] = d; br[KMAX - 1] = r; ks[KMAX - 1] = k; }
+                    }
+                } else {
+                    if (key_less(d, r, bd[KMAX - 1], br[KMAX - 1])) {
+                        if (key_less(d, r, bd[1 % KMAX], br[1 % KMAX])) {
+                            bd[KMAX - 1] = bd[1 % KMAX]; br[KMAX - 1] = br[1 % KMAX]; ks[KMAX - 1] = ks[1 % KMAX];
+                            if (key_less(d, r, bd[0], br[0])) {
+                                bd[1 % KMAX] = bd[0]; br[1 % KMAX] = br[0]; ks[1 % KMAX] = ks[0];
+                                bd[0] = d; br[0] = r; ks[0] = k;
+                            } else { bd[1 % KMAX] = d; br[1 % KMAX] = r; ks[1 % KMAX] = k; }
+                        } else { bd[KMAX - 1] = d; br[KMAX - 1] = r; ks[KMAX - 1] = k; }
+                    }
+                }
+            }
+        }
+    }
+    int found = 0;
+#pragma unroll
+    for (int i = 0; i < KMAX; i++) found += ks[i] != -1;
+    return found;
+}
+
+// bend_sample (march_device.cuh) over the packed, cell-sorted IP state.  Identical decisions and arithmetic.
+template <int KMAX>
+__device__ __forceinline__ bool bend_sample_packed(const IpPack &P, const pn::BendCfg &c, const unsigned char *rankA,
+                                                   const unsigned char *rankB, float &x, float &y, float &z) {
+    if (c.cut && !(x > c.cb[0] && x < c.cb[1] && y > c.cb[2] && x < c.cb[3] && z > c.cb[4] && z < c.cb[5])) return true;
+    int g0 = (int)floorf((x - c.bbmin[0]) / c.hgs);
+    int g1 = (int)floorf((y - c.bbmin[1]) / c.hgs);
+    int g2 = (int)floorf((z - c.bbmin[2]) / c.hgs);
+    g0 = min(max(g0, 0), c.res[0] - 1); g1 = min(max(g1, 0), c.res[1] - 1); g2 = min(max(g2, 0), c.res[2] - 1);
+    int ks[KMAX];
+    int n_ip;
+    if (KMAX == 1) {
+        // find_closest_IP: own cell; the neighbours only if the own cell holds nothing closer than 9999.9
+        n_ip = nearest_sorted<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, true, 9999.9f, ks);
+        if (n_ip == 0) n_ip = nearest_sorted<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, false, 9999.9f, ks);
+    } else {
+        n_ip = nearest_sorted<KMAX>(P, c, rankA, x, y, z, g0, g1, g2, false, FLT_MAX, ks);
+    }
+    if (n_ip <= 0) return false;
+    for (int k = 0; k < n_ip; k++) {  // boundary filter with the shrinking loop bound (raymarching.cu:1246-1251)
+        const float4 q = __ldg(P.pos + ks[k < KMAX ? k : 0]);
+        if (q.x <= c.bbmin[0] || q.y <= c.bbmin[1] || q.z < c.bbmin[2] || q.x >= c.bbmax[0] || q.y >= c.bbmax[1] || q.z >= c.bbmax[2]) n_ip--;
+    }
+    if (n_ip <= 0) return false;
+    float ps[KMAX][3], po[KMAX][3];
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) { ps[k][0] = ps[k][1] = ps[k][2] = 0.f; po[k][0] = po[k][1] = po[k][2] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+        if (k < n_ip) {
+            float p[3];
+            if (c.max_iter == 1) {
+                const float4 *r4 = reinterpret_cast<const float4 *>(P.rec + 16 * (size_t)ks[k]);
+                const float4 r0 = __ldg(r4), r1 = __ldg(r4 + 1), r2 = __ldg(r4 + 2), r3 = __ldg(r4 + 3);
+                po[k][0] = r0.x; po[k][1] = r0.y; po[k][2] = r0.z;
+                const float Ai[9] = {r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z};
+                const float q_[3] = {x - r0.w, y - r1.x, z - r1.y};
+                float b[3], dq[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) b[i] = (float)((double)0.0f + 0.5 * (double)0.0f - (double)q_[i]);
+                pn::matvec_cm(Ai, b, dq);
+                p[0] = po[k][0] - dq[0]; p[1] = po[k][1] - dq[1]; p[2] = po[k][2] - dq[2];
+            } else {
+                const int ip = __float_as_int(__ldg(P.pos + ks[k]).w);
+                pn::newton_rest_point(c, ip, x, y, z, p);
+                po[k][0] = c.p_ori[3 * ip]; po[k][1] = c.p_ori[3 * ip + 1]; po[k][2] = c.p_ori[3 * ip + 2];
+            }
+            if (fabsf(p[0] - po[k][0]) > c.IP_dx || fabsf(p[1] - po[k][1]) > c.IP_dx || fabsf(p[2] - po[k][2]) > c.IP_dx) n_ip--;
+            ps[k][0] = p[0]; ps[k][1] = p[1]; ps[k][2] = p[2];
+        }
+    }
+    float xm = 0.f, ym = 0.f, zm = 0.f;
+    if (n_ip == 1) {
+        xm = ps[0][0]; ym = ps[0][1]; zm = ps[0][2];
+    } else if (KMAX >= 2 && n_ip == 2) {
+        float d[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) d[k] = sqrtf((po[k % KMAX][0] - x) * (po[k % KMAX][0] - x) + (po[k % KMAX][1] - y) * (po[k % KMAX][1] - y) + (po[k % KMAX][2] - z) * (po[k % KMAX][2] - z));
+        const float s = d[0] + d[1], w0 = d[1] / s, w1 = d[0] / s;
+        xm = w0 * ps[0][0] + w1 * ps[1 % KMAX][0];
+        ym = w0 * ps[0][1] + w1 * ps[1 % KMAX][1];
+        zm = w0 * ps[0][2] + w1 * ps[1 % KMAX][2];
+    } else if (KMAX >= 3 && n_ip == 3) {
+        float d[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) d[k] = sqrtf((po[k % KMAX][0] - x) * (po[k % KMAX][0] - x) + (po[k % KMAX][1] - y) * (po[k % KMAX][1] - y) + (po[k % KMAX][2] - z) * (po[k % KMAX][2] - z));
+        const float s = d[0] * d[1] + d[1] * d[2] + d[2] * d[0];
+        const float w0 = d[1] * d[2] / s, w1 = d[0] * d[2] / s, w2 = d[0] * d[1] / s;
+        xm = w0 * ps[0][0] + w1 * ps[1 % KMAX][0] + w2 * ps[2 % KMAX][0];
+        ym = w0 * ps[0][1] + w1 * ps[1 % KMAX][1] + w2 * ps[2 % KMAX][1];
+        zm = w0 * ps[0][2] + w1 * ps[1 % KMAX][2] + w2 * ps[2 % KMAX][2];
+    }
+    x = xm; y = ym; z = zm;
+    return true;
+}
+
+constexpr int kQueue = 64;   // per-warp sample FIFO (power of two)
+constexpr int kRing = 128;   // in-flight ray descriptors per warp (> kQueue + 2)
+
+struct WarpShared {
+    float q[kQueue][8];     // x y z dirx diry dirz dt t_after
+    int qtag[kQueue];
+    int ring_ray[kRing];    // per in-flight ray (tag % kRing): pixel id, near, far
+    float ring_near[kRing], ring_far[kRing];
+    float st_alpha[32], st_r[32], st_g[32], st_b[32];
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(128, 3) render_warp_kernel(const RenderArgs A, const IpPack P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pn::FieldBlockSmem &fbs = *reinterpret_cast<pn::FieldBlockSmem *>(smem_raw);
+    pn::FieldSmem &fs = fbs.w;
+    float *scratch = fbs.scratch + threadIdx.x;
+    WarpShared *wsh_all = reinterpret_cast<WarpShared *>(smem_raw + ((sizeof(pn::FieldBlockSmem) + 15) & ~size_t(15)));
+    __shared__ unsigned char rankA[27], rankB[27];
+    pn::field_smem_fill(fs, A.field);
+    if (threadIdx.x < 27) {
+        // visit order of each of the 27 cells in the reference's two search routines (0 = own cell)
+        const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
+        int ra = 0, rb = 0;
+        for (int q = 0; q < 26; q++) {
+            if (pn::kNeigh[q][0] == dx && pn::kNeigh[q][1] == dy && pn::kNeigh[q][2] == dz) ra = q + 1;  // (x,y,z) offsets
+            if (pn::kNeigh[q][0] == dz && pn::kNeigh[q][1] == dy && pn::kNeigh[q][2] == dx) rb = q + 1;  // (z,y,x) offsets
+        }
+        rankA[threadIdx.x] = (unsigned char)ra; rankB[threadIdx.x] = (unsigned char)rb;
+    }
+    pn::BendCfg bc = A.bend;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { bc.bbmin[i] = A.geom->bbmin[i]; bc.bbmax[i] = A.geom->bbmax[i]; bc.hi[i] = A.geom->hi[i]; bc.res[i] = A.geom->res[i]; }
+    __syncthreads();
+    const pn::MarchCfg m = A.march;
+    const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    WarpShared &W = wsh_all[threadIdx.x >> 5];
+    const int n_active = A.queue->n_active;
+
+    // marcher state (warp-uniform)
+    bool m_have = false, exhausted = false;
+    int m_tag = -1, next_tag = 0, m_emitted = 0;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, rdx = 0, rdy = 0, rdz = 0, m_far = 0, m_near = 0;
+    float t_next = 0, skip_until = 0;
+    int m_ray = -1;
+    // FIFO
+    int qhead = 0, qcount = 0;
+    // compositor state (warp-uniform, every lane runs the same recurrence)
+    int c_tag = -1;
+    bool c_done = true;
+    float ws = 0, dep = 0, cr = 0, cg = 0, cb = 0, tdepth = 0, last_t = 0;
+    long long kept = 0, evaluated = 0;
+
+    auto finalize = [&](int tag) {
+        if (lane == 0) {
+            const int ray = W.ring_ray[tag & (kRing - 1)];
+            const float near = W.ring_near[tag & (kRing - 1)], far = W.ring_far[tag & (kRing - 1)];
+            A.image[3 * ray] = cr + (1 - ws) * A.bg; A.image[3 * ray + 1] = cg + (1 - ws) * A.bg; A.image[3 * ray + 2] = cb + (1 - ws) * A.bg;
+            A.depth0[ray] = dep;
+            A.depth[ray] = fmaxf(dep - near, 0.f) / (far - near);
+            A.wsum[ray] = ws;
+        }
+    };
+
+    while (true) {
+        // ------------------------------------------------------------------ march until a full tile is queued
+        while (qcount < 32 && !(exhausted && !m_have)) {
+            if (!m_have) {
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(&A.queue->next, 1);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (slot >= n_active) { exhausted = true; break; }
+                m_ray = A.active[slot];
+                ox = A.rays_o[3 * m_ray]; oy = A.rays_o[3 * m_ray + 1]; oz = A.rays_o[3 * m_ray + 2];
+                dx = A.rays_d[3 * m_ray]; dy = A.rays_d[3 * m_ray + 1]; dz = A.rays_d[3 * m_ray + 2];
+                rdx = 1 / dx; rdy = 1 / dy; rdz = 1 / dz;
+                m_near = A.nears[m_ray]; m_far = A.fars[m_ray];
+                t_next = m_near; skip_until = 0.f;
+                m_tag = next_tag++; m_emitted = 0; m_have = true;
+                __syncwarp();
+                if (lane == 0) { W.ring_ray[m_tag & (kRing - 1)] = m_ray; W.ring_near[m_tag & (kRing - 1)] = m_near; W.ring_far[m_tag & (kRing - 1)] = m_far; }
+            }
+            // lane i evaluates lattice point t_i = f^i(t_next)
+            float t = t_next;
+            for (int i = 0; i < lane; i++) t += pn::step_size(m, t);
+            const float dt = pn::step_size(m, t);
+            const float t_after = t + dt;
+            const bool valid = t < m_far;
+            const bool need = valid && t >= skip_until;
+            float x = 0, y = 0, z = 0, tt = 0;
+            bool emit = false;
+            if (need) {
+                pn::deformed_sample(bc, ox, oy, oz, dx, dy, dz, t, x, y, z);
+                const bool found = bend_sample_packed<KMAX>(P, bc, rankA, rankB, x, y, z);
+                const bool occ = pn::occupancy_and_exit(m, x, y, z, t, dt, dx, dy, dz, rdx, rdy, rdz, tt);
+                emit = occ && found;
+            }
+            const uint32_t valid_m = __ballot_sync(0xffffffffu, valid);
+            const uint32_t need_m = __ballot_sync(0xffffffffu, need);
+            const uint32_t emit_m = __ballot_sync(0xffffffffu, emit);
+            // replay the reference's visit order over this chunk
+            uint32_t take = 0;
+            float carry = skip_until;
+            int i = need_m ? __ffs(need_m) - 1 : (valid_m == 0xffffffffu ? 32 : __popc(valid_m));
+            while (i < 32 && ((valid_m >> i) & 1u)) {
+                if ((emit_m >> i) & 1u) {
+                    const uint32_t inv = ~(emit_m >> i);
+                    const int run = inv ? __ffs(inv) - 1 : 32;           // consecutive emits: each advances one point
+                    take |= ((run >= 32 ? 0xffffffffu : ((1u << run) - 1u)) << i);
+                    i += run;
+                    carry = 0.f;
+                } else {
+                    const float tti = __shfl_sync(0xffffffffu, tt, i);
+                    const uint32_t ge = __ballot_sync(0xffffffffu, valid && t >= tti) & ~((2u << i) - 1u);
+                    const uint32_t inval = ~valid_m & ~((2u << i) - 1u);
+                    if (ge) { i = __ffs(ge) - 1; carry = 0.f; }
+                    else if (inval) { i = __ffs(inval) - 1; }            // skipped past `far` inside this chunk
+                    else { i = 32; carry = tti; }
+                }
+            }
+            const bool ray_left = i < 32;                                // reached a lattice point with t >= far
+            // per-ray sample cap (the reference's loop stops issuing steps after max_steps)
+            int ntake = __popc(take);
+            if (m_emitted + ntake > (int)A.max_samples) {
+                int keep = (int)A.max_samples - m_emitted;
+                uint32_t tk = take, out = 0;
+                while (keep-- > 0 && tk) { const uint32_t lowest = tk & (0u - tk); out |= lowest; tk ^= lowest; }
+                take = out; ntake = __popc(take);
+            }
+            if ((take >> lane) & 1u) {
+                const int s = (qhead + qcount + __popc(take & lt_mask)) & (kQueue - 1);
+                float *e = W.q[s];
+                e[0] = x; e[1] = y; e[2] = z; e[3] = dx; e[4] = dy; e[5] = dz; e[6] = dt; e[7] = t_after;
+                W.qtag[s] = m_tag;
+            }
+            qcount += ntake; m_emitted += ntake;
+            const bool capped = m_emitted >= (int)A.max_samples;
+            if (ray_left || capped) {
+                if (m_emitted == 0) {
+                    // crossed the IP box without a single kept sample: what rund_cuda leaves for such a ray
+                    if (lane == 0) {
+                        A.image[3 * m_ray] = A.bg; A.image[3 * m_ray + 1] = A.bg; A.image[3 * m_ray + 2] = A.bg;
+                        A.depth0[m_ray] = 0.f; A.wsum[m_ray] = 0.f;
+                        A.depth[m_ray] = fmaxf(0.f - m_near, 0.f) / (m_far - m_near);
+                    }
+                    next_tag--;                                            // nothing queued: the tag (ring slot) is free again
+                }
+                m_have = false;
+            } else {
+                t_next = __shfl_sync(0xffffffffu, t_after, 31);
+                skip_until = carry;
+            }
+            __syncwarp();
+        }
+        if (qcount == 0) break;
+        // ------------------------------------------------------------------ field on a 32-sample tile
+        const int n = min(32, qcount);
+        float alpha = 0.f, r = 0.f, g = 0.f, b = 0.f;
+        if (lane < n) {
+            const float *e = W.q[(qhead + lane) & (kQueue - 1)];
+            float sh[16];
+            pn::sh_eval<4>(e[3], e[4], e[5], sh);
+            float sigma;
+            pn::field_eval(fs, table, A.field.bound, e[0], e[1], e[2], sh, scratch, pn::kFieldThreads, sigma, r, g, b);
+            sigma = A.density_scale * sigma;
+            alpha = 1.0f - __expf(-sigma * e[6]);
+        }
+        W.st_alpha[lane] = alpha; W.st_r[lane] = r; W.st_g[lane] = g; W.st_b[lane] = b;
+        __syncwarp();
+        evaluated += n;
+        // ------------------------------------------------------------------ composite, in FIFO order (raymarching.cu:862-913)
+        for (int j = 0; j < n; j++) {
+            const int s = (qhead + j) & (kQueue - 1);
+            const int tag = W.qtag[s];
+            if (tag != c_tag) {
+                if (c_tag >= 0 && !c_done) finalize(c_tag);
+                c_tag = tag; c_done = false;
+                ws = dep = cr = cg = cb = 0.f;
+                tdepth = W.ring_near[tag & (kRing - 1)]; last_t = tdepth;
+            }
+            if (c_done) continue;                                          // samples marched past an early termination
+            const float a = W.st_alpha[j];
+            const float T = 1 - ws;
+            const float w = a * T;
+            ws += w;
+            const float ta = W.q[s][7];
+            tdepth += ta - last_t;
+            last_t = ta;
+            dep += w * tdepth;
+            cr += w * W.st_r[j]; cg += w * W.st_g[j]; cb += w * W.st_b[j];
+            kept++;
+            if (T < A.T_thresh) {
+                finalize(c_tag);
+                c_done = true;
+                if (m_have && m_tag == c_tag) m_have = false;              // stop marching a saturated ray
+            }
+        }
+        qhead = (qhead + n) & (kQueue - 1);
+        qcount -= n;
+        __syncwarp();
+    }
+    if (c_tag >= 0 && !c_done) finalize(c_tag);
+    if (lane == 0 && (kept || evaluated)) {
+        atomicAdd((unsigned long long *)&A.queue->samples, (unsigned long long)kept);
+        atomicAdd((unsigned long long *)&A.queue->pad, (unsigned long long)evaluated);
+    }
+}
+
+}  // namespace

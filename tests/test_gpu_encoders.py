@@ -141,7 +141,8 @@ def test_against_reference_kernels(rng):
     ge.grid_encode_forward(x, emb, o, b, 100000, 3, 2, 16, S, 16, None, 0, False, 0)
     torch.cuda.synchronize()
     assert torch.equal(a, b), float((a - b).abs().max())
-    d = _gpu(rng.normal(size=(10000, 3)).astype(np.float32))
+    dn = rng.normal(size=(10000, 3)); dn /= np.linalg.norm(dn, axis=1, keepdims=True)
+    d = _gpu(dn.astype(np.float32))
     for deg in (1, 4, 8):
         ya = torch.empty(10000, deg * deg, device="cuda"); yb = torch.empty_like(ya)
         rs.sh_encode_forward(d, ya, 10000, 3, deg, None); se.sh_encode_forward(d, yb, 10000, 3, deg, None)
@@ -149,4 +150,4 @@ def test_against_reference_kernels(rng):
         if deg <= 4:                                                          # the hot-path degree: bit-exact
             assert torch.equal(ya, yb), (deg, float((ya - yb).abs().max()))
         else:                                                                 # bands 5-8: nvcc contracts a few FMAs differently (1 ulp)
-            assert torch.allclose(ya, yb, rtol=2e-6, atol=1e-6), (deg, float((ya - yb).abs().max()))
+            assert torch.allclose(ya, yb, rtol=0, atol=2e-6), (deg, float((ya - yb).abs().max()))

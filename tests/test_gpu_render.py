@@ -41,10 +41,11 @@ def test_frame_vs_oracle(amp, K):
     ro_, rd_ = _gpu(rays_o)[None], _gpu(rays_d)[None]
     loop = model.rund_cuda(ro_, rd_, return_stats=True, **kw, **opt)
     fused = model.render_deformed(ro_, rd_, **kw, **opt)
+    lane = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in model.render_deformed(ro_, rd_, mode=1, **kw, **opt).items()}
     torch.cuda.synchronize()
     hit = want["weights_sum"] > 0
     assert hit.sum() > 100 and want["n_samples"] > 1000
-    for name, got in (("loop", loop), ("fused", fused)):
+    for name, got in (("loop", loop), ("fused", fused), ("fused-lane", lane)):
         img = got["image"][0].cpu().numpy(); ws = got["weights_sum"].cpu().numpy(); d0 = got["depth_0"][0].cpu().numpy()
         # knife-edge occupancy flips (fp32 FMA contraction) can move a handful of silhouette pixels
         assert _bad_fraction(img, want["image"], 1e-3) <= 0.01, (name, _bad_fraction(img, want["image"], 1e-3))
