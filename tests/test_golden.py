@@ -1,0 +1,92 @@
+"""Pins oracle/render_oracle.py against golden vectors produced by the REFERENCE's own CUDA kernels
+(tests/golden/ref_kernels.npz, generated on a B200 by tests/golden/make_golden.py from oracle/_ref/*.so).
+Runs on CPU.  Integer/bit outputs must match exactly; fp32 outputs within the stated tolerances (numpy does
+not model nvcc's FMA contraction: last-ulp differences, amplified by grid resolution for the hash grid)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import render_oracle as ro
+
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_kernels.npz")
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def G():
+    return dict(np.load(PATH))
+
+
+def test_grid_encode_golden(G):
+    got = ro.grid_encode(G["grid_x"], G["grid_emb"], G["grid_off"], np.log2(float(G["grid_scale"])), 16)
+    want = G["grid_out"]
+    assert (want[:, 2] == 0).all() and (want[:, 3] == 0).all() and (got[:, 2] == 0).all() and (got[:, 3] == 0).all()
+    for l in range(8):
+        tol = 2e-6 + 6e-7 * 16 * float(G["grid_scale"]) ** l
+        assert np.abs(got[l] - want[l]).max() < tol, l
+    got2 = ro.grid_encode(G["grid2_x"], G["grid2_emb"], G["grid2_off"], np.log2(float(G["grid2_scale"])), 16, gridtype=1, align_corners=True, interp=1)
+    assert np.abs(got2 - G["grid2_out"]).max() < 2e-4
+
+
+def test_sh_golden(G):
+    assert np.abs(ro.sh_encode(G["sh_d"], 4) - G["sh_out"]).max() < 1e-6
+
+
+def test_morton_packbits_golden(G):
+    c = G["mo_c"]
+    assert np.array_equal(ro.morton3D(c[:, 0], c[:, 1], c[:, 2]).astype(np.int32), G["mo_idx"])
+    assert np.array_equal(G["mo_back"], c)
+    assert np.array_equal(ro.packbits(G["pk_grid"], 10.0), G["pk_bits"])
+
+
+def _bits(G):
+    b = np.zeros(int(G["rm_bits_len"]), np.uint8)
+    b[G["rm_bits_idx"]] = G["rm_bits_val"]
+    return b
+
+
+def _agree(xyz_a, del_a, xyz_b, del_b, tol):
+    ea = del_a[:, 0] != 0; eb = del_b[:, 0] != 0
+    both = ea & eb
+    ok = ea == eb
+    ok[both] &= (np.abs(xyz_a[both] - xyz_b[both]).max(1) < tol) & (np.abs(del_a[both] - del_b[both]).max(1) < 1e-6)
+    return float(ok.mean()), int(both.sum())
+
+
+def test_near_far_golden(G):
+    n, f = ro.near_far_from_aabb(G["rm_rays_o"], G["rm_rays_d"], np.concatenate([G["rm_bbmin"], G["rm_bbmax"]]), 0.2)
+    miss = G["rm_nears"] == np.finfo(f32).max
+    assert np.array_equal(n == np.finfo(f32).max, miss)
+    assert np.abs(n[~miss] - G["rm_nears"][~miss]).max() < 1e-6 and np.abs(f[~miss] - G["rm_fars"][~miss]).max() < 1e-6
+
+
+@pytest.mark.parametrize("K,mi", [(1, 1), (3, 1), (3, 100)])
+def test_bending_march_golden(G, K, mi):
+    """Sample-for-sample against the reference kernel.  An fp32 knife-edge decision (occupancy cell / nearest IP)
+    may flip under FMA contraction, after which that ray's later rows shift: require >= 98.5% identical rows."""
+    bits = _bits(G)
+    N = G["rm_rays_o"].shape[0]
+    cnt, bgn, idx = ro.get_pnts_in_grids(G["rm_p_def"], G["rm_bbmin"], 0.06, G["rm_res"])
+    x, d, dl = ro.march_rays_quadratic_bending(cnt, bgn, idx, G["rm_p_ori"].shape[0], int(np.prod(G["rm_res"])), G["rm_p_def"], G["rm_p_ori"], G["rm_F"],
+                                               G["rm_dF"], mi, G["rm_bbmin"], G["rm_bbmax"], 0.06, G["rm_res"], K, 0.0525, False, np.zeros(6, f32), N, 6,
+                                               np.arange(N, dtype=np.int32), G["rm_nears"].copy(), G["rm_rays_o"], G["rm_rays_d"], 1.0, 0.0, 256, 1, 128,
+                                               bits, G["rm_nears"], G["rm_fars"], None, 128)
+    frac, both = _agree(x, dl, G[f"rm_xyzs_K{K}_it{mi}"], G[f"rm_deltas_K{K}_it{mi}"], 2e-6)
+    assert both > 150 and frac >= 0.985, (frac, both)
+
+
+def test_plain_march_and_composite_golden(G):
+    bits = _bits(G)
+    N = G["rm_rays_o"].shape[0]
+    x, d, dl = ro.march_rays(N, 4, np.arange(N, dtype=np.int32), G["mr_nears"].copy(), G["rm_rays_o"], G["rm_rays_d"], 1.0, 1 / 128, 256, 1, 128, bits,
+                             G["mr_nears"], G["mr_fars"], None, -1)
+    frac, both = _agree(x, dl, G["mr_xyzs"], G["mr_deltas"], 2e-6)
+    assert both > 50 and frac >= 0.985, (frac, both)
+    # composite: identical inputs (the reference's own deltas) on both sides
+    alive = np.arange(N, dtype=np.int32); t = G["rm_nears"].copy(); ws = np.zeros(N, f32); dp = np.zeros(N, f32); im = np.zeros((N, 3), f32)
+    ro.composite_rays(N, 6, 1e-2, alive, t, G["cp_sig"], G["cp_rgb"], G["rm_deltas_K3_it1"], ws, dp, im)
+    assert np.array_equal(alive, G["cp_alive"])
+    live = alive >= 0
+    assert np.abs(t[live] - G["cp_t"][live]).max() < 1e-6 if live.any() else True
+    assert np.abs(ws - G["cp_ws"]).max() < 2e-6 and np.abs(dp - G["cp_depth"]).max() < 1e-5 and np.abs(im - G["cp_image"]).max() < 2e-6
