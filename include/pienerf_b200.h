@@ -101,7 +101,8 @@ int pn_ip_bbox(const float *p_def, int n_vtx, float hgs, int cut, float bound, f
 /* nerf/network.py:98-127 NeRFNetwork.forward as ONE kernel over M samples:
  * hash-grid (L=16,C=2,D=3) -> 32->64->16 -> trunc_exp | SH(4) || geo(15) -> 31->64->64->3 -> sigmoid.
  * weights: w_sigma0 [64,32], w_sigma1 [16,64], w_color0 [64,31], w_color1 [64,64], w_color2 [3,64] (torch
- * nn.Linear row-major [out,in], f32).  xyzs in [-bound,bound].  mode 0 = fp32 SIMT. */
+ * nn.Linear row-major [out,in], f32).  xyzs in [-bound,bound].
+ * mode 0 = fp32 SIMT; mode 1 = tcgen05 tensor cores, each GEMM as 3 bf16 MMAs (hi/lo split) with fp32 TMEM accumulators. */
 typedef struct {
     const float *embeddings; const int *offsets; float S; uint32_t H; uint32_t L; float bound;
     const float *w_sigma0, *w_sigma1, *w_color0, *w_color1, *w_color2;

@@ -1,0 +1,299 @@
+// Tensor-core (tcgen05 / TMEM) evaluation of the sigma/colour MLP of nerf/network.py:98-127 for 128-sample tiles.
+//
+// One "tile group" = 4 warps = 128 threads = 128 samples (thread r owns row r of every activation matrix and TMEM
+// lane r).  Per layer: every thread writes its activation row into shared memory as bf16 hi/lo parts in the UMMA
+// canonical K-major no-swizzle layout (chunk-major: 16-byte k-chunks of all 128 rows are contiguous, so the 128
+// threads store 2 KB contiguous — conflict-free), one elected thread issues tcgen05.mma (M=128, N=64 or 16, K=16 per
+// instruction) with the accumulator in TMEM, tcgen05.commit signals an mbarrier, and each warp reads its 32 TMEM
+// lanes back with tcgen05.ld for the ReLU / exp / sigmoid epilogue.
+//
+// Precision: the reference MLP is fp32 SGEMM with TF32 off and the parity bar is 1e-3 absolute RGB with
+// sigma = exp(h) amplifying errors, so single-pass bf16 is not enough.  Each GEMM is computed as three bf16 MMAs
+//   A W^T ~= A_lo W_hi^T + A_hi W_lo^T + A_hi W_hi^T      (fp32 accumulate in TMEM)
+// which keeps ~16 mantissa bits per operand (dropped term <= 2^-18 relative).
+#pragma once
+#include <cuda_bf16.h>
+#include "grid_device.cuh"
+#include "sh_device.cuh"
+
+namespace pn {
+namespace tc {
+
+constexpr int kTile = 128;             // rows per tile group
+constexpr uint32_t kTmemCols = 128;    // per tile group: two 64-column fp32 accumulators (ping-pong)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE_%=;\n"
+        "bra LAB_WAIT_%=;\n"
+        "LAB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int group) {  // named barrier 1+group over the group's 128 threads
+    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+// ---- TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {    // same warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp bit layouts)
+// K-major, no swizzle: 8x(16 B) core matrices; LBO = byte distance between the two 16-byte k-chunks of one MMA,
+// SBO = byte distance between 8-row groups.  version = 1 (sm_100), layout_type = 0 (SWIZZLE_NONE / interleave).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::f16, A = B = bf16, D = fp32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t instr_desc_bf16(uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- shared-memory images
+// Weight matrix [N,K] (nn.Linear [out,in]) as B operand: element (n,k) of part p at  p*N*K*2 + (k/8)*(N*16) + n*16 + (k%8)*2.
+struct Weights {
+    __nv_bfloat16 w1[2][64 * 32];   // sigma_net[0]   N=64 K=32   [hi|lo]
+    __nv_bfloat16 w2[2][16 * 64];   // sigma_net[1]   N=16 K=64
+    __nv_bfloat16 w3[2][64 * 32];   // color_net[0]   N=64 K=32 (input 31 zero-padded)
+    __nv_bfloat16 w4[2][64 * 64];   // color_net[1]   N=64 K=64
+    __nv_bfloat16 w5[2][16 * 64];   // color_net[2]   N=16 (3 used) K=64
+    LevelGeom geo[16];
+    uint32_t level_off[16];
+};
+// Activations of one tile group: [128 rows, 64 k] bf16, hi and lo images, chunk-major: (r,k) at (k/8)*2048 + r*16 + (k%8)*2
+struct TileSmem {
+    __nv_bfloat16 a[2][kTile * 64];
+    uint64_t bar;
+    uint32_t tmem;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// whole block cooperates; W row-major [N_src, K_src] fp32 in global, zero-padded to [N,K]
+template <int N, int K>
+__device__ __forceinline__ void load_weight(__nv_bfloat16 *hi, __nv_bfloat16 *lo, const float *__restrict__ W, int n_src, int k_src) {
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+        const int n = i / K, k = i % K;
+        const float v = (n < n_src && k < k_src) ? __ldg(W + n * k_src + k) : 0.f;
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        const int o = (k >> 3) * (N * 8) + n * 8 + (k & 7);
+        hi[o] = h; lo[o] = l;
+    }
+}
+
+__device__ __forceinline__ void weights_fill(Weights &w, const pn_field_t &f) {
+    load_weight<64, 32>(w.w1[0], w.w1[1], f.w_sigma0, 64, 32);
+    load_weight<16, 64>(w.w2[0], w.w2[1], f.w_sigma1, 16, 64);
+    load_weight<64, 32>(w.w3[0], w.w3[1], f.w_color0, 64, 31);
+    load_weight<64, 64>(w.w4[0], w.w4[1], f.w_color1, 64, 64);
+    load_weight<16, 64>(w.w5[0], w.w5[1], f.w_color2, 3, 64);
+    if (threadIdx.x < 16) {
+        w.geo[threadIdx.x] = level_geom(threadIdx.x, f.S, f.H, f.offsets, false);
+        w.level_off[threadIdx.x] = (uint32_t)f.offsets[threadIdx.x];
+    }
+}
+
+// store 8 consecutive k-values (one 16-byte chunk) of this thread's row into the hi and lo activation images
+__device__ __forceinline__ void store_chunk(TileSmem &t, int row, int chunk, const float (&v)[8]) {
+    __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) split_bf16(v[i], h[i], l[i]);
+    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(t.a[0]) + chunk * 2048 + row * 16) = *reinterpret_cast<const uint4 *>(h);
+    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(t.a[1]) + chunk * 2048 + row * 16) = *reinterpret_cast<const uint4 *>(l);
+}
+
+// D[128,N] (TMEM columns d_col..) = A[128,K] W[N,K]^T with the 3-term bf16 split.  Called by ONE thread of the group.
+template <int N, int K>
+__device__ __forceinline__ void issue_layer(const TileSmem &t, const __nv_bfloat16 *w_hi, const __nv_bfloat16 *w_lo, uint32_t tmem_d) {
+    constexpr uint32_t idesc = instr_desc_bf16(N);
+    const uint32_t a_hi = smem_u32(t.a[0]), a_lo = smem_u32(t.a[1]);
+    const uint32_t b_hi = smem_u32(w_hi), b_lo = smem_u32(w_lo);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int term = 0; term < 3; term++) {  // small terms first, hi*hi last
+        const uint32_t a = term == 0 ? a_lo : a_hi;
+        const uint32_t b = term == 1 ? b_lo : b_hi;
+#pragma unroll
+        for (int ks = 0; ks < K / 16; ks++) {
+            const uint64_t ad = smem_desc(a + ks * 2 * 2048, 2048, 128);
+            const uint64_t bd = smem_desc(b + ks * 2 * (N * 16), N * 16, 128);
+            umma_bf16(tmem_d, ad, bd, idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
+// Full MLP for one tile.  Preconditions: this thread's 32 encoded features are already stored (chunks 0..3 of t.a);
+// `sh` = SH(4) of the sample's ray direction.  `phase` is the group's running mbarrier parity (updated).
+// All 128 threads of the group must call this together.
+__device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int group, int row, const float (&sh)[16], uint32_t &phase,
+                                         float &sigma, float &r, float &g, float &b) {
+    const uint32_t tm = t.tmem + ((uint32_t)(row & ~31) << 16);  // this warp's 32 TMEM lanes
+    const bool leader = (row == 0);
+    float v[16], c8[8];
+
+    // ---- sigma_net[0]: [128,32] x [64,32]^T -> cols 0..63
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(group);
+    if (leader) { tc_fence_after(); issue_layer<64, 32>(t, w.w1[0], w.w1[1], t.tmem); umma_commit(&t.bar); }
+    mbar_wait(&t.bar, phase); phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        tmem_ld16(tm + q * 16, v);
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) c8[i] = fmaxf(v[hh * 8 + i], 0.f);
+            store_chunk(t, row, q * 2 + hh, c8);
+        }
+    }
+    // ---- sigma_net[1]: [128,64] x [16,64]^T -> cols 64..79
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(group);
+    if (leader) { tc_fence_after(); issue_layer<16, 64>(t, w.w2[0], w.w2[1], t.tmem + 64); umma_commit(&t.bar); }
+    mbar_wait(&t.bar, phase); phase ^= 1;
+    tc_fence_after();
+    tmem_ld16(tm + 64, v);
+    sigma = expf(v[0]);
+    // colour-net input row: SH(16) | geo(15) | 0
+#pragma unroll
+    for (int i = 0; i < 8; i++) c8[i] = sh[i];
+    store_chunk(t, row, 0, c8);
+#pragma unroll
+    for (int i = 0; i < 8; i++) c8[i] = sh[8 + i];
+    store_chunk(t, row, 1, c8);
+#pragma unroll
+    for (int i = 0; i < 8; i++) c8[i] = v[1 + i];
+    store_chunk(t, row, 2, c8);
+#pragma unroll
+    for (int i = 0; i < 7; i++) c8[i] = v[9 + i];
+    c8[7] = 0.f;
+    store_chunk(t, row, 3, c8);
+    // ---- color_net[0]: [128,32] x [64,32]^T -> cols 0..63
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(group);
+    if (leader) { tc_fence_after(); issue_layer<64, 32>(t, w.w3[0], w.w3[1], t.tmem); umma_commit(&t.bar); }
+    mbar_wait(&t.bar, phase); phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        tmem_ld16(tm + q * 16, v);
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) c8[i] = fmaxf(v[hh * 8 + i], 0.f);
+            store_chunk(t, row, q * 2 + hh, c8);
+        }
+    }
+    // ---- color_net[1]: [128,64] x [64,64]^T -> cols 64..127
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(group);
+    if (leader) { tc_fence_after(); issue_layer<64, 64>(t, w.w4[0], w.w4[1], t.tmem + 64); umma_commit(&t.bar); }
+    mbar_wait(&t.bar, phase); phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        tmem_ld16(tm + 64 + q * 16, v);
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) c8[i] = fmaxf(v[hh * 8 + i], 0.f);
+            store_chunk(t, row, q * 2 + hh, c8);
+        }
+    }
+    // ---- color_net[2]: [128,64] x [16,64]^T -> cols 0..15 (3 used)
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(group);
+    if (leader) { tc_fence_after(); issue_layer<16, 64>(t, w.w5[0], w.w5[1], t.tmem); umma_commit(&t.bar); }
+    mbar_wait(&t.bar, phase); phase ^= 1;
+    tc_fence_after();
+    tmem_ld16(tm, v);
+    r = 1.0f / (1.0f + expf(-v[0]));
+    g = 1.0f / (1.0f + expf(-v[1]));
+    b = 1.0f / (1.0f + expf(-v[2]));
+    tc_fence_before();  // order these TMEM reads before the next tile's first MMA (which follows a group_sync)
+}
+
+// Encode one sample and store its 32 features (chunks 0..3) for sigma_net[0].  Zero row for invalid samples.
+__device__ __forceinline__ void encode_to_tile(TileSmem &t, const Weights &w, const float2 *__restrict__ table, float bound, int row,
+                                               bool valid, float x, float y, float z) {
+    const float inv = 1.0f / (2 * bound);
+    const float u = (x + bound) * inv, vv = (y + bound) * inv, ww = (z + bound) * inv;
+    const bool in = valid && !(u < 0 || u > 1 || vv < 0 || vv > 1 || ww < 0 || ww > 1);
+#pragma unroll 1
+    for (int c = 0; c < 4; c++) {
+        float c8[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int l = c * 4 + q;
+            float2 e = make_float2(0.f, 0.f);
+            if (in) e = lookup3_c2(table + w.level_off[l], w.geo[l], u, vv, ww, 0);
+            c8[2 * q] = e.x; c8[2 * q + 1] = e.y;
+        }
+        store_chunk(t, row, c, c8);
+    }
+}
+
+}  // namespace tc
+}  // namespace pn

@@ -346,37 +346,44 @@ __global__ void __launch_bounds__(128) ip_stress_kernel(double dx3, const int *_
     }
 }
 
-// collect_rhs_IP as a gather (cuda_utils.py:124-151 semantics, :153-188 structure): one warp per DOF row.
-// rhs[row] = sum over (ip,corner) adjacent to kernel k of stress[ip] . dN[ip,corner,:,x]
-// out = base_add[row] + sum - base_sub[row] when the optional bases are given (fuses `momentum + rhs - rhs_rest`).
+// collect_rhs_IP as a gather (cuda_utils.py:124-151 semantics, :153-188 structure): one CTA per kernel k.
+// Each thread walks the kernel's (ip,corner) adjacency with stride blockDim, reads the IP's 3x3 stress once and
+// the corner's contiguous 30-double gradient block, and accumulates all 10 slots x 3 components; a fixed-order
+// shuffle + shared-memory tree makes the result bit-reproducible (no fp64 atomics).
+// out[row] = (base_add[row] + sum) - base_sub[row] when the optional bases are given (`momentum + rhs - rhs_rest`).
 __global__ void __launch_bounds__(128) rhs_gather_kernel(const int *__restrict__ adj_bgn, const int *__restrict__ adj,
                                                          const double *__restrict__ stress, const double *__restrict__ dNx,
-                                                         int n_rows, const double *__restrict__ base_add,
+                                                         int n_k, const double *__restrict__ base_add,
                                                          const double *__restrict__ base_sub, double *__restrict__ out) {
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (row >= n_rows) return;
-    const int k = row / 10, x = row % 10;
-    double a0 = 0, a1 = 0, a2 = 0;
-    for (int e = adj_bgn[k] + lane; e < adj_bgn[k + 1]; e += 32) {
+    __shared__ double part[4][30];
+    const int k = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (k >= n_k) return;
+    double acc[30];
+#pragma unroll
+    for (int i = 0; i < 30; i++) acc[i] = 0.0;
+    for (int e = adj_bgn[k] + threadIdx.x; e < adj_bgn[k + 1]; e += blockDim.x) {
         const int code = adj[e], v = code >> 3, i = code & 7;
         const double *S = stress + (size_t)v * 9;
-        const double *dN = dNx + (size_t)v * 240 + (i * 3) * 10 + x;
-        const double g0 = dN[0], g1 = dN[10], g2 = dN[20];
-        a0 += S[0] * g0 + S[1] * g1 + S[2] * g2;
-        a1 += S[3] * g0 + S[4] * g1 + S[5] * g2;
-        a2 += S[6] * g0 + S[7] * g1 + S[8] * g2;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(kFull, a0, o); a1 += __shfl_xor_sync(kFull, a1, o); a2 += __shfl_xor_sync(kFull, a2, o);
-    }
-    if (lane == 0) {
-        if (base_add) {  // (momentum + rhs) - rhs_rest in the reference's order (solver.py:599)
-            out[3 * row] = (base_add[3 * row] + a0) - base_sub[3 * row];
-            out[3 * row + 1] = (base_add[3 * row + 1] + a1) - base_sub[3 * row + 1];
-            out[3 * row + 2] = (base_add[3 * row + 2] + a2) - base_sub[3 * row + 2];
-        } else {
-            out[3 * row] = a0; out[3 * row + 1] = a1; out[3 * row + 2] = a2;
+        const double *dN = dNx + (size_t)v * 240 + i * 30;   // [c][x], 30 contiguous doubles
+        const double s0 = S[0], s1 = S[1], s2 = S[2], s3 = S[3], s4 = S[4], s5 = S[5], s6 = S[6], s7 = S[7], s8 = S[8];
+#pragma unroll
+        for (int x = 0; x < 10; x++) {
+            const double g0 = dN[x], g1 = dN[10 + x], g2 = dN[20 + x];
+            acc[3 * x] += s0 * g0 + s1 * g1 + s2 * g2;
+            acc[3 * x + 1] += s3 * g0 + s4 * g1 + s5 * g2;
+            acc[3 * x + 2] += s6 * g0 + s7 * g1 + s8 * g2;
         }
+    }
+#pragma unroll
+    for (int i = 0; i < 30; i++) {
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(kFull, acc[i], o);
+        if (lane == 0) part[wid][i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 30) {
+        const int row3 = k * 30 + threadIdx.x;               // (k*10 + x)*3 + r
+        const double sum = ((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x];
+        out[row3] = base_add ? (base_add[row3] + sum) - base_sub[row3] : sum;   // solver.py:599 order
     }
 }
 
@@ -663,7 +670,7 @@ extern "C" int pn_qgmls_build_rhs(double dx, const int *topo, const double *mu, 
     PN_REQUIRE(topo && mu && lam && dNx && dof && adj_bgn && adj && ip_stress && rhs, "null pointer");
     cudaStream_t st = PN_STREAM(stream);
     ip_stress_kernel<<<div_up(n_ip * 32, 128), 128, 0, st>>>(dx * dx * dx, topo, mu, lam, dNx, dof, n_ip, ip_stress);
-    rhs_gather_kernel<<<div_up(n_k * 10 * 32, 128), 128, 0, st>>>(adj_bgn, adj, ip_stress, dNx, n_k * 10, nullptr, nullptr, rhs);
+    rhs_gather_kernel<<<n_k, 128, 0, st>>>(adj_bgn, adj, ip_stress, dNx, n_k, nullptr, nullptr, rhs);
     PN_LAUNCH_CHECK("build_rhs");
     return PN_OK;
 }
@@ -698,7 +705,7 @@ extern "C" int pn_qgmls_step(const pn_qgmls_step_t *s, int solver, void *stream)
     matvec3_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(s->M, tilde, n, s->dof_f, s->rhs_gravity, nullptr, mom);
     for (int it = 0; it < s->iters; it++) {
         ip_stress_kernel<<<div_up(s->n_ip * 32, 128), 128, 0, st>>>(dx3, s->topo, s->mu, s->lam, s->dNx, s->dof, s->n_ip, stress);
-        rhs_gather_kernel<<<div_up(n * 32, 128), 128, 0, st>>>(s->adj_bgn, s->adj, stress, s->dNx, n, mom, s->rhs_rest, rhs);
+        rhs_gather_kernel<<<s->n_k, 128, 0, st>>>(s->adj_bgn, s->adj, stress, s->dNx, s->n_k, mom, s->rhs_rest, rhs);
         if (solver == 0) {
             // dof = dof_rest + Ainv rhs  (solver.py:600-601)
             matvec3_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(s->Ainv, rhs, n, s->dof_rest, nullptr, nullptr, s->dof);

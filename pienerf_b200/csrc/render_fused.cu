@@ -388,6 +388,9 @@ int set_smem(K kernel, size_t bytes) {
 
 #include "render_warp.cuh"
 
+int pn_field_forward_tc(const pn_field_t *f, const float *xyzs, const float *dirs, uint32_t M, float *sigmas, float *rgbs,
+                        cudaStream_t st);
+
 extern "C" int pn_get_rays(const float *pose, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
                            float *rays_o, float *rays_d, void *stream) {
     PN_REQUIRE(pose && rays_o && rays_d, "null pointer");
@@ -435,8 +438,9 @@ extern "C" int pn_field_forward(const pn_field_t *f, const float *xyzs, const fl
                                 float *rgbs, int mode, void *stream) {
     PN_REQUIRE(f && xyzs && dirs && sigmas && rgbs, "null pointer");
     PN_REQUIRE(f->L == pn::kLevels, "fused field expects the 16-level C=2 D=3 grid of nerf/network.py");
-    PN_REQUIRE(mode == 0, "unknown field mode");
+    PN_REQUIRE(mode == 0 || mode == 1, "field mode: 0 = fp32 SIMT, 1 = tcgen05 (bf16x3 split)");
     if (M == 0) return PN_OK;
+    if (mode == 1) return pn_field_forward_tc(f, xyzs, dirs, M, sigmas, rgbs, PN_STREAM(stream));
     const size_t smem = sizeof(pn::FieldBlockSmem);
     if (int rc = set_smem(field_forward_kernel, smem)) return rc;
     const uint32_t blocks = min(div_up(M, 128u), (uint32_t)pn_sm_count_cached() * 3u);
@@ -461,7 +465,7 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
                                   void *workspace, uint64_t workspace_bytes, long long *stats, int mode, void *stream) {
     PN_REQUIRE(f && d && rays_o && rays_d && image && depth && depth_0 && weights_sum && workspace, "null pointer");
     PN_REQUIRE(f->L == pn::kLevels, "fused field expects the 16-level C=2 D=3 grid of nerf/network.py");
-    PN_REQUIRE(mode == 0 || mode == 1, "render mode: 0 = warp-cooperative (default), 1 = one lane per ray");
+    PN_REQUIRE(mode >= 0 && mode <= 2, "render mode: 0 = warp-cooperative + tcgen05 MLP (default), 1 = warp-cooperative fp32 SIMT, 2 = one lane per ray");
     PN_REQUIRE(d->n_vtx > 0 && d->num_seek_IP >= 1 && d->num_seek_IP <= 3, "need IPs and num_seek_IP in 1..3");
     PN_REQUIRE(d->cascade >= 1 && d->cascade <= 8 && d->grid_size == 128, "cascade/grid_size out of range");
     if (N == 0) return PN_OK;
@@ -499,28 +503,32 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
     A.density_scale = d->density_scale; A.T_thresh = d->T_thresh; A.bg = d->bg_color; A.max_samples = d->max_steps;
 
     const uint32_t blocks = (uint32_t)pn_sm_count_cached() * 3u;
-    if (mode == 0) {
+    if (mode == 0 || mode == 1) {
         float4 *ip_pos = (float4 *)(base + w.ip_pos);
         float *ip_rec = (float *)(base + w.ip_rec);
         ip_pack_kernel<<<div_up(d->n_vtx, 256), 256, 0, st>>>(d->p_def, d->p_ori, d->F_IP, idx, d->n_vtx, geom->res, max_cells, bgn, ip_pos, ip_rec);
         PN_LAUNCH_CHECK("ip_pack_kernel");
         IpPack P{ip_pos, ip_rec, bgn};
-        const size_t smem = ((sizeof(pn::FieldBlockSmem) + 15) & ~size_t(15)) + 4 * sizeof(WarpShared);
+        const bool tc = mode == 0;
+        const size_t smem = tc ? (((sizeof(RenderTcSmem) + 127) & ~size_t(127)) + kTcGroups * 4 * sizeof(WarpShared) + 128)
+                               : (((sizeof(pn::FieldBlockSmem) + 127) & ~size_t(127)) + 4 * sizeof(WarpShared) + 128);
+        const uint32_t nblk = tc ? (uint32_t)pn_sm_count_cached() : blocks;
+        const uint32_t nthr = tc ? kTcGroups * 128 : 128;
         if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
-        switch (d->num_seek_IP) {
-            case 1:
-                if (int rc = set_smem(render_warp_kernel<1>, smem)) return rc;
-                render_warp_kernel<1><<<blocks, 128, smem, st>>>(A, P);
-                break;
-            case 2:
-                if (int rc = set_smem(render_warp_kernel<2>, smem)) return rc;
-                render_warp_kernel<2><<<blocks, 128, smem, st>>>(A, P);
-                break;
-            default:
-                if (int rc = set_smem(render_warp_kernel<3>, smem)) return rc;
-                render_warp_kernel<3><<<blocks, 128, smem, st>>>(A, P);
-                break;
+#define PN_LAUNCH_WARP(K)                                                                       \
+        if (tc) {                                                                               \
+            if (int rc = set_smem(render_warp_kernel<K, true>, smem)) return rc;                \
+            render_warp_kernel<K, true><<<nblk, nthr, smem, st>>>(A, P);                        \
+        } else {                                                                                \
+            if (int rc = set_smem(render_warp_kernel<K, false>, smem)) return rc;               \
+            render_warp_kernel<K, false><<<nblk, nthr, smem, st>>>(A, P);                       \
         }
+        switch (d->num_seek_IP) {
+            case 1: PN_LAUNCH_WARP(1) break;
+            case 2: PN_LAUNCH_WARP(2) break;
+            default: PN_LAUNCH_WARP(3) break;
+        }
+#undef PN_LAUNCH_WARP
     } else {
     const size_t smem = sizeof(pn::FieldBlockSmem);
     if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));

@@ -13,6 +13,7 @@
 //     32-sample tiles even when rays are short; compositing replays the reference's sequential recurrence in
 //     order (bit-identical accumulation order), with early termination fed back to the marcher.
 #pragma once
+#include "field_tc.cuh"
 
 namespace {
 
@@ -199,15 +200,36 @@ struct WarpShared {
     float st_alpha[32], st_r[32], st_g[32], st_b[32];
 };
 
-template <int KMAX>
-__global__ void __launch_bounds__(128, 3) render_warp_kernel(const RenderArgs A, const IpPack P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+constexpr int kTcGroups = 3;   // 128-sample tile groups per CTA in tensor-core mode (384 threads, 1 CTA / SM)
+struct __align__(128) RenderTcSmem {
+    pn::tc::Weights w;
+    pn::tc::TileSmem tile[kTcGroups];
+    uint32_t tmem_base;
+    int nq[kTcGroups][4];       // samples each warp of a group contributes to the current tile
+};
+
+// TC = false: fp32 SIMT field (128 threads, 3 CTAs / SM).  TC = true: MLP on tcgen05 (field_tc.cuh), 384 threads.
+template <int KMAX, bool TC>
+__global__ void __launch_bounds__(TC ? kTcGroups * 128 : 128, TC ? 1 : 3) render_warp_kernel(const RenderArgs A, const IpPack P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     pn::FieldBlockSmem &fbs = *reinterpret_cast<pn::FieldBlockSmem *>(smem_raw);
     pn::FieldSmem &fs = fbs.w;
     float *scratch = fbs.scratch + threadIdx.x;
-    WarpShared *wsh_all = reinterpret_cast<WarpShared *>(smem_raw + ((sizeof(pn::FieldBlockSmem) + 15) & ~size_t(15)));
+    RenderTcSmem &TS = *reinterpret_cast<RenderTcSmem *>(smem_raw);
+    const int group = threadIdx.x >> 7, row = threadIdx.x & 127;
+    WarpShared *wsh_all = reinterpret_cast<WarpShared *>(smem_raw + (((TC ? sizeof(RenderTcSmem) : sizeof(pn::FieldBlockSmem)) + 127) & ~size_t(127)));
     __shared__ unsigned char rankA[27], rankB[27];
-    pn::field_smem_fill(fs, A.field);
+    uint32_t phase = 0;
+    if constexpr (TC) {
+        pn::tc::weights_fill(TS.w, A.field);
+        if (row == 0) pn::tc::mbar_init(&TS.tile[group].bar, 1);
+        pn::tc::fence_barrier_init();
+        if (threadIdx.x < 32) pn::tc::tmem_alloc(&TS.tmem_base, 512);
+        pn::tc::fence_async_smem();
+        pn::tc::tc_fence_before();
+    } else {
+        pn::field_smem_fill(fs, A.field);
+    }
     if (threadIdx.x < 27) {
         // visit order of each of the 27 cells in the reference's two search routines (0 = own cell)
         const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
@@ -222,6 +244,11 @@ __global__ void __launch_bounds__(128, 3) render_warp_kernel(const RenderArgs A,
 #pragma unroll
     for (int i = 0; i < 3; i++) { bc.bbmin[i] = A.geom->bbmin[i]; bc.bbmax[i] = A.geom->bbmax[i]; bc.hi[i] = A.geom->hi[i]; bc.res[i] = A.geom->res[i]; }
     __syncthreads();
+    if constexpr (TC) {
+        pn::tc::tc_fence_after();
+        if (row == 0) TS.tile[group].tmem = TS.tmem_base + group * pn::tc::kTmemCols;
+        pn::tc::group_sync(group);
+    }
     const pn::MarchCfg m = A.march;
     const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
     const int lane = threadIdx.x & 31;
@@ -344,18 +371,38 @@ __global__ void __launch_bounds__(128, 3) render_warp_kernel(const RenderArgs A,
             }
             __syncwarp();
         }
-        if (qcount == 0) break;
         // ------------------------------------------------------------------ field on a 32-sample tile
         const int n = min(32, qcount);
         float alpha = 0.f, r = 0.f, g = 0.f, b = 0.f;
-        if (lane < n) {
-            const float *e = W.q[(qhead + lane) & (kQueue - 1)];
+        if constexpr (TC) {
+            // the 4 warps of a group pool their tiles into one 128-row tensor-core tile; the group leaves together
+            if (lane == 0) TS.nq[group][(threadIdx.x >> 5) & 3] = n;
+            pn::tc::group_sync(group);
+            const int total = TS.nq[group][0] + TS.nq[group][1] + TS.nq[group][2] + TS.nq[group][3];
+            pn::tc::group_sync(group);
+            if (total == 0) break;
+            const bool valid = lane < n;
+            const float *e = W.q[(qhead + (valid ? lane : 0)) & (kQueue - 1)];
             float sh[16];
-            pn::sh_eval<4>(e[3], e[4], e[5], sh);
+            pn::sh_eval<4>(valid ? e[3] : 0.f, valid ? e[4] : 0.f, valid ? e[5] : 1.f, sh);
+            pn::tc::encode_to_tile(TS.tile[group], TS.w, table, A.field.bound, row, valid, e[0], e[1], e[2]);
             float sigma;
-            pn::field_eval(fs, table, A.field.bound, e[0], e[1], e[2], sh, scratch, pn::kFieldThreads, sigma, r, g, b);
-            sigma = A.density_scale * sigma;
-            alpha = 1.0f - __expf(-sigma * e[6]);
+            pn::tc::mlp_tile(TS.tile[group], TS.w, group, row, sh, phase, sigma, r, g, b);
+            if (valid) {
+                sigma = A.density_scale * sigma;
+                alpha = 1.0f - __expf(-sigma * e[6]);
+            }
+        } else {
+            if (qcount == 0) break;
+            if (lane < n) {
+                const float *e = W.q[(qhead + lane) & (kQueue - 1)];
+                float sh[16];
+                pn::sh_eval<4>(e[3], e[4], e[5], sh);
+                float sigma;
+                pn::field_eval(fs, table, A.field.bound, e[0], e[1], e[2], sh, scratch, pn::kFieldThreads, sigma, r, g, b);
+                sigma = A.density_scale * sigma;
+                alpha = 1.0f - __expf(-sigma * e[6]);
+            }
         }
         W.st_alpha[lane] = alpha; W.st_r[lane] = r; W.st_g[lane] = g; W.st_b[lane] = b;
         __syncwarp();
@@ -395,6 +442,11 @@ __global__ void __launch_bounds__(128, 3) render_warp_kernel(const RenderArgs A,
     if (lane == 0 && (kept || evaluated)) {
         atomicAdd((unsigned long long *)&A.queue->samples, (unsigned long long)kept);
         atomicAdd((unsigned long long *)&A.queue->pad, (unsigned long long)evaluated);
+    }
+    if constexpr (TC) {
+        pn::tc::tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x < 32) pn::tc::tmem_dealloc(TS.tmem_base, 512);
     }
 }
 

@@ -207,7 +207,8 @@ class NeRFNetwork(nn.Module):
     @torch.no_grad()
     def render_deformed(self, rays_o, rays_d, staged=False, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024, T_thresh=1e-2,
                         mode=0, out=None, **kwargs):
-        """renderer.py:587-599 -> rund_cuda semantics in one device-resident call.  Returns the same dict."""
+        """renderer.py:587-599 -> rund_cuda semantics in one device-resident call.  Returns the same dict.
+        mode 0: warp-cooperative march + tcgen05 MLP (default); 1: same with the fp32 SIMT MLP; 2: one lane per ray."""
         if perturb:
             raise NotImplementedError("perturb is only used with spp>1 accumulation, which the sim GUI never does (gui.py:620-622)")
         prefix = rays_o.shape[:-1]

@@ -151,3 +151,23 @@ def test_against_reference_kernels(rng):
             assert torch.equal(ya, yb), (deg, float((ya - yb).abs().max()))
         else:                                                                 # bands 5-8: nvcc contracts a few FMAs differently (1 ulp)
             assert torch.allclose(ya, yb, rtol=0, atol=2e-6), (deg, float((ya - yb).abs().max()))
+
+
+def test_field_tensor_core_mode(rng):
+    """pn_field_forward mode 1 (tcgen05, bf16x3 split GEMMs, fp32 TMEM accumulators) vs mode 0 (fp32 SIMT) and the
+    fp64-accumulate numpy oracle.  Tolerance: 2e-4 relative on sigma, 1e-4 absolute on rgb (the bar is 1e-3 RGB)."""
+    from pienerf_b200.network import NeRFNetwork
+    field = make_field(bound=1.0, seed=5)
+    model = NeRFNetwork(bound=1).cuda().load_field(field)
+    for M in (1000, 128 * 7, 50001):
+        x = rng.uniform(-1, 1, size=(M, 3)).astype(np.float32); x[0] = [1.5, 0, 0]
+        d = rng.normal(size=(M, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        s0, c0 = model.forward_fused(_gpu(x), _gpu(d), mode=0)
+        s1, c1 = model.forward_fused(_gpu(x), _gpu(d), mode=1)
+        torch.cuda.synchronize()
+        s0 = s0.cpu().numpy(); c0 = c0.cpu().numpy(); s1 = s1.cpu().numpy(); c1 = c1.cpu().numpy()
+        assert np.isfinite(s1).all() and np.isfinite(c1).all()
+        assert np.abs(s1 / s0 - 1).max() < 2e-4, np.abs(s1 / s0 - 1).max()
+        assert np.abs(c1 - c0).max() < 1e-4, np.abs(c1 - c0).max()
+    s_ref, c_ref = ro.OracleField(field, accumulate=np.float64)(x[:2000], d[:2000])
+    assert np.abs(s1[:2000] / s_ref - 1).max() < 5e-4 and np.abs(c1[:2000] - c_ref).max() < 2e-4
