@@ -157,23 +157,40 @@ __device__ __forceinline__ void store_chunk(TileSmem &t, int row, int chunk, con
     *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(t.a[1]) + chunk * 2048 + row * 16) = *reinterpret_cast<const uint4 *>(l);
 }
 
-// D[128,N] (TMEM columns d_col..) = A[128,K] W[N,K]^T with the 3-term bf16 split.  Called by ONE thread of the group.
+// D[128,N] (TMEM columns tmem_d..) = A[128,K] W[N,K]^T with the 3-term bf16 split.  Called by ONE thread of the group.
+// Rolled loops with incremental descriptors: this runs on a single thread, code size matters more than issue rate.
 template <int N, int K>
 __device__ __forceinline__ void issue_layer(const TileSmem &t, const __nv_bfloat16 *w_hi, const __nv_bfloat16 *w_lo, uint32_t tmem_d) {
     constexpr uint32_t idesc = instr_desc_bf16(N);
-    const uint32_t a_hi = smem_u32(t.a[0]), a_lo = smem_u32(t.a[1]);
-    const uint32_t b_hi = smem_u32(w_hi), b_lo = smem_u32(w_lo);
+    const uint64_t a_hi = smem_desc(smem_u32(t.a[0]), 2048, 128), a_lo = smem_desc(smem_u32(t.a[1]), 2048, 128);
+    const uint64_t b_hi = smem_desc(smem_u32(w_hi), N * 16, 128), b_lo = smem_desc(smem_u32(w_lo), N * 16, 128);
     uint32_t acc = 0;
-#pragma unroll
+#pragma unroll 1
     for (int term = 0; term < 3; term++) {  // small terms first, hi*hi last
-        const uint32_t a = term == 0 ? a_lo : a_hi;
-        const uint32_t b = term == 1 ? b_lo : b_hi;
-#pragma unroll
+        uint64_t ad = term == 0 ? a_lo : a_hi;
+        uint64_t bd = term == 1 ? b_lo : b_hi;
+#pragma unroll 1
         for (int ks = 0; ks < K / 16; ks++) {
-            const uint64_t ad = smem_desc(a + ks * 2 * 2048, 2048, 128);
-            const uint64_t bd = smem_desc(b + ks * 2 * (N * 16), N * 16, 128);
             umma_bf16(tmem_d, ad, bd, idesc, acc);
             acc = 1;
+            ad += (2 * 2048) >> 4;          // start-address field counts 16-byte units: next 16 k-values = 2 chunks
+            bd += (2 * N * 16) >> 4;
+        }
+    }
+}
+
+// ReLU epilogue of a 64-wide hidden layer: TMEM columns [col, col+64) of this thread's lane -> bf16 hi/lo activation row.
+// Deliberately not inlined: it is used three times per tile and the frame kernel is instruction-fetch sensitive.
+static __device__ __noinline__ void epilogue_relu64(TileSmem &t, int row, uint32_t taddr) {
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        float v[16], c8[8];
+        tmem_ld16(taddr + q * 16, v);
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) c8[i] = fmaxf(v[hh * 8 + i], 0.f);
+            store_chunk(t, row, q * 2 + hh, c8);
         }
     }
 }
@@ -194,16 +211,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     if (leader) { tc_fence_after(); issue_layer<64, 32>(t, w.w1[0], w.w1[1], t.tmem); umma_commit(&t.bar); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        tmem_ld16(tm + q * 16, v);
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) c8[i] = fmaxf(v[hh * 8 + i], 0.f);
-            store_chunk(t, row, q * 2 + hh, c8);
-        }
-    }
+    epilogue_relu64(t, row, tm);
     // ---- sigma_net[1]: [128,64] x [16,64]^T -> cols 64..79
     fence_async_smem();
     tc_fence_before();
@@ -234,16 +242,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     if (leader) { tc_fence_after(); issue_layer<64, 32>(t, w.w3[0], w.w3[1], t.tmem); umma_commit(&t.bar); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        tmem_ld16(tm + q * 16, v);
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) c8[i] = fmaxf(v[hh * 8 + i], 0.f);
-            store_chunk(t, row, q * 2 + hh, c8);
-        }
-    }
+    epilogue_relu64(t, row, tm);
     // ---- color_net[1]: [128,64] x [64,64]^T -> cols 64..127
     fence_async_smem();
     tc_fence_before();
@@ -251,16 +250,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     if (leader) { tc_fence_after(); issue_layer<64, 64>(t, w.w4[0], w.w4[1], t.tmem + 64); umma_commit(&t.bar); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        tmem_ld16(tm + 64 + q * 16, v);
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) c8[i] = fmaxf(v[hh * 8 + i], 0.f);
-            store_chunk(t, row, q * 2 + hh, c8);
-        }
-    }
+    epilogue_relu64(t, row, tm + 64);
     // ---- color_net[2]: [128,64] x [16,64]^T -> cols 0..15 (3 used)
     fence_async_smem();
     tc_fence_before();
@@ -275,23 +265,23 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     tc_fence_before();  // order these TMEM reads before the next tile's first MMA (which follows a group_sync)
 }
 
-// Encode one sample and store its 32 features (chunks 0..3) for sigma_net[0].  Zero row for invalid samples.
+// Encode one sample and store its 32 features (k = 2*level, 2*level+1; chunks 0..3) for sigma_net[0].  Zero row for
+// invalid samples.  One level per rolled iteration (small code), each level writes its bf16x2 hi and lo words directly.
 __device__ __forceinline__ void encode_to_tile(TileSmem &t, const Weights &w, const float2 *__restrict__ table, float bound, int row,
                                                bool valid, float x, float y, float z) {
     const float inv = 1.0f / (2 * bound);
     const float u = (x + bound) * inv, vv = (y + bound) * inv, ww = (z + bound) * inv;
     const bool in = valid && !(u < 0 || u > 1 || vv < 0 || vv > 1 || ww < 0 || ww > 1);
-#pragma unroll 1
-    for (int c = 0; c < 4; c++) {
-        float c8[8];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int l = c * 4 + q;
-            float2 e = make_float2(0.f, 0.f);
-            if (in) e = lookup3_c2(table + w.level_off[l], w.geo[l], u, vv, ww, 0);
-            c8[2 * q] = e.x; c8[2 * q + 1] = e.y;
-        }
-        store_chunk(t, row, c, c8);
+    char *hi = reinterpret_cast<char *>(t.a[0]) + row * 16, *lo = reinterpret_cast<char *>(t.a[1]) + row * 16;
+#pragma unroll 2
+    for (int l = 0; l < 16; l++) {
+        float2 e = make_float2(0.f, 0.f);
+        if (in) e = lookup3_c2(table + w.level_off[l], w.geo[l], u, vv, ww, 0);
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(e.x, h0, l0); split_bf16(e.y, h1, l1);
+        const int off = (l >> 2) * 2048 + (l & 3) * 4;
+        *reinterpret_cast<__nv_bfloat162 *>(hi + off) = __halves2bfloat162(h0, h1);
+        *reinterpret_cast<__nv_bfloat162 *>(lo + off) = __halves2bfloat162(l0, l1);
     }
 }
 

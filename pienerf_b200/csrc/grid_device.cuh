@@ -26,6 +26,7 @@ struct LevelGeom {
     uint32_t size;        // entries in this level (offsets[l+1]-offsets[l])
     uint32_t stride1;     // resolution (+1 unless align_corners)
     bool dense3;          // D=3: all three axes index linearly (no hashing, no early stop)
+    uint32_t mask;        // size-1 when size is a power of two (every hashed level of the reference config), else 0
 };
 
 __device__ __forceinline__ LevelGeom level_geom(uint32_t level, float S, uint32_t H, const int *__restrict__ offsets,
@@ -36,6 +37,7 @@ __device__ __forceinline__ LevelGeom level_geom(uint32_t level, float S, uint32_
     g.size = (uint32_t)(offsets[level + 1] - offsets[level]);
     g.stride1 = align_corners ? g.resolution : g.resolution + 1;
     g.dense3 = (uint64_t)g.stride1 * g.stride1 * g.stride1 <= (uint64_t)g.size;
+    g.mask = (g.size & (g.size - 1)) == 0 ? g.size - 1 : 0;
     return g;
 }
 
@@ -56,7 +58,7 @@ __device__ __forceinline__ uint32_t vertex_index(const uint32_t (&v)[D], const L
         for (uint32_t d = 0; d < D; d++) h ^= v[d] * grid_primes(d);
         index = h;
     }
-    return index % g.size;
+    return g.mask ? (index & g.mask) : (index % g.size);  // same value; avoids a runtime-divisor modulo
 }
 
 // Trilinear lookup of one level for D=3, C=2, fp32 table, linear interpolation: the hot instantiation.

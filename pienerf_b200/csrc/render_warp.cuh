@@ -64,45 +64,53 @@ __device__ __forceinline__ int nearest_sorted(const IpPack &P, const pn::BendCfg
 #pragma unroll
     for (int i = 0; i < KMAX; i++) { bd[i] = dmax; br[i] = 0x7fffffff; ks[i] = -1; }
     const int lo = max(g0 - 1, 0), hi = min(g0 + 1, c.res[0] - 1);
-    for (int dz = -1; dz <= 1; dz++) {
-        const int a2 = g2 + dz;
-        if (a2 < 0 || a2 >= c.res[2]) continue;
+    const int nb = hi - lo + 1, own = g0 - lo;                             // nb in 1..3 cells, own in 0..1
+    // conservative lower bounds on the distance to the neighbouring rows of cells (an IP lies inside its cell up to
+    // rounding of the cell assignment, hence the margin): a row whose bound already exceeds the current K-th best
+    // cannot change the result, ties included (strict >), so skipping it is exact.
+    const float eps = 1e-5f;
+    const float yl = fmaxf(y - (c.bbmin[1] + g1 * c.hgs) - eps, 0.f), yh = fmaxf((c.bbmin[1] + (g1 + 1) * c.hgs) - y - eps, 0.f);
+    const float zl = fmaxf(z - (c.bbmin[2] + g2 * c.hgs) - eps, 0.f), zh = fmaxf((c.bbmin[2] + (g2 + 1) * c.hgs) - z - eps, 0.f);
 #pragma unroll 1
-        for (int dy = -1; dy <= 1; dy++) {
-            const int a1 = g1 + dy;
-            if (a1 < 0 || a1 >= c.res[1]) continue;
-            if (own_cell_only && (dz != 0 || dy != 0)) continue;
-            const int row = (a2 * c.res[1] + a1) * c.res[0];
-            // cells lo..hi of a row are contiguous in the cell-sorted array: one range, <= 4 boundaries
-            int b[4];
+    for (int it = 0; it < 9; it++) {
+        // own row first so the bounds tighten early; the visiting order does not affect the result (rank keys)
+        const int dz = (it == 0) ? 0 : ((it <= 2) ? 0 : (it <= 5 ? -1 : 1));
+        const int dy = (it == 0) ? 0 : ((it == 1) ? -1 : (it == 2 ? 1 : ((it - 3) % 3) - 1));
+        if (own_cell_only && it != 0) break;
+        const int a1 = g1 + dy, a2 = g2 + dz;
+        if (a1 < 0 || a1 >= c.res[1] || a2 < 0 || a2 >= c.res[2]) continue;
+        const float gy = dy < 0 ? yl : (dy > 0 ? yh : 0.f), gz = dz < 0 ? zl : (dz > 0 ? zh : 0.f);
+        if (gy * gy + gz * gz > bd[KMAX - 1]) continue;
+        const int row = (a2 * c.res[1] + a1) * c.res[0];
+        // cells lo..hi of a row are contiguous in the cell-sorted array: one range, <= 4 boundaries
+        int b[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = (lo + j <= hi + 1) ? __ldg(P.cell_start + row + lo + j) : 0x7fffffff;
-            const int nb = hi - lo + 1, own = g0 - lo;                     // nb in 1..3 cells, own in 0..1
-            int first = b[0], last = nb == 3 ? b[3] : (nb == 2 ? b[2] : b[1]);
-            if (own_cell_only) { first = own == 0 ? b[0] : b[1]; last = own == 0 ? b[1] : b[2]; }
-            for (int k = first; k < last; k++) {
-                const float4 q = __ldg(P.pos + k);
-                const float d = (q.x - x) * (q.x - x) + (q.y - y) * (q.y - y) + (q.z - z) * (q.z - z);
-                const int cell = lo + (k >= b[1]) + (k >= b[2]);      // which of the <=3 cells this entry is in
-                const int cbeg = cell == lo ? b[0] : (cell == lo + 1 ? b[1] : b[2]);
-                const int r = ((int)rank[(dz + 1) * 9 + (dy + 1) * 3 + (cell - g0 + 1)] << 8) + (k - cbeg);
-                if (KMAX == 1) {
-                    if (key_less(d, r, bd[0], br[0])) { bd[0] = d; br[0] = r; ks[0] = k; }
-                } else if (KMAX == 2) {
-                    if (key_less(d, r, bd[KMAX - 1], br[KMAX - 1])) {
-                        if (key_less(d, r, bd[0], br[0])) { bd[KMAX - 1] = bd[0]; br[KMAX - 1] = br[0]; ks[KMAX - 1] = ks[0]; bd[0] = d; br[0] = r; ks[0] = k; }
-                        else { bd[KMAX - 1] = d; br[KMAX - 1] = r; ks[KMAX - 1] = k; }
-                    }
-                } else {
-                    if (key_less(d, r, bd[KMAX - 1], br[KMAX - 1])) {
-                        if (key_less(d, r, bd[1 % KMAX], br[1 % KMAX])) {
-                            bd[KMAX - 1] = bd[1 % KMAX]; br[KMAX - 1] = br[1 % KMAX]; ks[KMAX - 1] = ks[1 % KMAX];
-                            if (key_less(d, r, bd[0], br[0])) {
-                                bd[1 % KMAX] = bd[0]; br[1 % KMAX] = br[0]; ks[1 % KMAX] = ks[0];
-                                bd[0] = d; br[0] = r; ks[0] = k;
-                            } else { bd[1 % KMAX] = d; br[1 % KMAX] = r; ks[1 % KMAX] = k; }
-                        } else { bd[KMAX - 1] = d; br[KMAX - 1] = r; ks[KMAX - 1] = k; }
-                    }
+        for (int j = 0; j < 4; j++) b[j] = (j <= nb) ? __ldg(P.cell_start + row + lo + j) : 0x7fffffff;
+        int first = b[0], last = nb == 3 ? b[3] : (nb == 2 ? b[2] : b[1]);
+        if (own_cell_only) { first = own == 0 ? b[0] : b[1]; last = own == 0 ? b[1] : b[2]; }
+        for (int k = first; k < last; k++) {
+            const float4 q = __ldg(P.pos + k);
+            const float d = (q.x - x) * (q.x - x) + (q.y - y) * (q.y - y) + (q.z - z) * (q.z - z);
+            if (d > bd[KMAX - 1]) continue;                                // the common case: not among the K best
+            const int cell = lo + (k >= b[1]) + (k >= b[2]);              // which of the <=3 cells this entry is in
+            const int cbeg = cell == lo ? b[0] : (cell == lo + 1 ? b[1] : b[2]);
+            const int r = ((int)rank[(dz + 1) * 9 + (dy + 1) * 3 + (cell - g0 + 1)] << 8) + (k - cbeg);
+            if (KMAX == 1) {
+                if (key_less(d, r, bd[0], br[0])) { bd[0] = d; br[0] = r; ks[0] = k; }
+            } else if (KMAX == 2) {
+                if (key_less(d, r, bd[KMAX - 1], br[KMAX - 1])) {
+                    if (key_less(d, r, bd[0], br[0])) { bd[KMAX - 1] = bd[0]; br[KMAX - 1] = br[0]; ks[KMAX - 1] = ks[0]; bd[0] = d; br[0] = r; ks[0] = k; }
+                    else { bd[KMAX - 1] = d; br[KMAX - 1] = r; ks[KMAX - 1] = k; }
+                }
+            } else {
+                if (key_less(d, r, bd[KMAX - 1], br[KMAX - 1])) {
+                    if (key_less(d, r, bd[1 % KMAX], br[1 % KMAX])) {
+                        bd[KMAX - 1] = bd[1 % KMAX]; br[KMAX - 1] = br[1 % KMAX]; ks[KMAX - 1] = ks[1 % KMAX];
+                        if (key_less(d, r, bd[0], br[0])) {
+                            bd[1 % KMAX] = bd[0]; br[1 % KMAX] = br[0]; ks[1 % KMAX] = ks[0];
+                            bd[0] = d; br[0] = r; ks[0] = k;
+                        } else { bd[1 % KMAX] = d; br[1 % KMAX] = r; ks[1 % KMAX] = k; }
+                    } else { bd[KMAX - 1] = d; br[KMAX - 1] = r; ks[KMAX - 1] = k; }
                 }
             }
         }
@@ -208,6 +216,15 @@ struct __align__(128) RenderTcSmem {
     int nq[kTcGroups][4];       // samples each warp of a group contributes to the current tile
 };
 
+// what rund_cuda leaves for a finished ray (renderer.py:896-901); one shared copy of the code (instruction-fetch budget)
+static __device__ __noinline__ void finalize_ray(const RenderArgs &A, int ray, float near, float far, float ws, float dep, float cr,
+                                                 float cg, float cb) {
+    A.image[3 * ray] = cr + (1 - ws) * A.bg; A.image[3 * ray + 1] = cg + (1 - ws) * A.bg; A.image[3 * ray + 2] = cb + (1 - ws) * A.bg;
+    A.depth0[ray] = dep;
+    A.depth[ray] = fmaxf(dep - near, 0.f) / (far - near);
+    A.wsum[ray] = ws;
+}
+
 // TC = false: fp32 SIMT field (128 threads, 3 CTAs / SM).  TC = true: MLP on tcgen05 (field_tc.cuh), 384 threads.
 template <int KMAX, bool TC>
 __global__ void __launch_bounds__(TC ? kTcGroups * 128 : 128, TC ? 1 : 3) render_warp_kernel(const RenderArgs A, const IpPack P) {
@@ -271,14 +288,8 @@ __global__ void __launch_bounds__(TC ? kTcGroups * 128 : 128, TC ? 1 : 3) render
     long long kept = 0, evaluated = 0;
 
     auto finalize = [&](int tag) {
-        if (lane == 0) {
-            const int ray = W.ring_ray[tag & (kRing - 1)];
-            const float near = W.ring_near[tag & (kRing - 1)], far = W.ring_far[tag & (kRing - 1)];
-            A.image[3 * ray] = cr + (1 - ws) * A.bg; A.image[3 * ray + 1] = cg + (1 - ws) * A.bg; A.image[3 * ray + 2] = cb + (1 - ws) * A.bg;
-            A.depth0[ray] = dep;
-            A.depth[ray] = fmaxf(dep - near, 0.f) / (far - near);
-            A.wsum[ray] = ws;
-        }
+        if (lane == 0)
+            finalize_ray(A, W.ring_ray[tag & (kRing - 1)], W.ring_near[tag & (kRing - 1)], W.ring_far[tag & (kRing - 1)], ws, dep, cr, cg, cb);
     };
 
     while (true) {
