@@ -84,60 +84,23 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from pienerf_b200 import _lib
-    from pienerf_b200.dist import FrameGather, broadcast_ip_state, pack_ip_state, tile_partition, unpack_ip_state
-    from pienerf_b200.frame import FrameDriver, build_scene
-    from pienerf_b200 import raymarching
+    from pienerf_b200.frame import DistFrameDriver, build_scene
 
     model, sim, opt, pose, intr, body, field = build_scene(args.config, device=dev, density_scale=args.density_scale)
-    drv = FrameDriver(model, sim, opt, fused=True)
+    drv = DistFrameDriver(model, sim, opt)
     W, H = opt.W, opt.H
     N = W * H
-    parts = tile_partition(H, W, world)
-    my = torch.from_numpy(parts[rank]).to(dev)
-    gather = FrameGather(parts, 5, dev)                                      # rgb + depth + depth_0 per pixel
-    ipbuf = torch.zeros(sim.n_ip, 39, dtype=torch.float32, device=dev)
-    local_out = torch.empty(len(parts[rank]), 5, dtype=torch.float32, device=dev)
-    host_frame = torch.empty(N, 5, dtype=torch.float32).pin_memory() if rank == 0 else None
     host_pose = torch.from_numpy(pose).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
-    rays_full = raymarching.get_rays(host_pose[None], intr, H, W)
-    rays_o = rays_full["rays_o"][:, my].contiguous(); rays_d = rays_full["rays_d"][:, my].contiguous()
+    calib = None
+    if world > 1 and not args.equal_tiles:
+        calib = drv.calibrate(host_pose, intr)                                # rank 0 also runs the simulator: fewer tiles
     launches = {"n": 0}
 
     def frame(e2e, prof=None):
-        """One GUI frame.  e2e=True adds the host<->device traffic of the public API (pose in, frame out)."""
-        nonlocal rays_o, rays_d
-        if e2e:
-            # Trainer.test_gui regenerates the rays from the host pose every frame (trainer.py:541-543)
-            full = raymarching.get_rays(host_pose[None], intr, H, W)
-            launches["n"] += 1
-            if world > 1:
-                rays_o = full["rays_o"][:, my].contiguous(); rays_d = full["rays_d"][:, my].contiguous()
-                launches["n"] += 2
-            else:
-                rays_o, rays_d = full["rays_o"], full["rays_d"]
-        if rank == 0:                                                         # trainer.py:303-308: state BEFORE the step
-            pos, F, dF = sim.get_IP_info()
-            sim.stepforward()
-            launches["n"] += 1 + (2 + 3 * sim.iters + 1)
-            if world > 1:
-                pack_ip_state(pos, F, dF, ipbuf)
-        if world > 1:
-            broadcast_ip_state(ipbuf)
-            pos, F, dF = unpack_ip_state(ipbuf)
-        model.p_def, model.IP_F, model.IP_dF = pos, F, dF
-        if prof is not None:
-            _lib.lib.pn_set_profile_events(_lib.vp(prof[0].cuda_event), _lib.vp(prof[1].cuda_event))
-        out = model.render_deformed(rays_o, rays_d, **opt)
-        launches["n"] += 9
-        if prof is not None:
-            _lib.lib.pn_set_profile_events(_lib.vp(0), _lib.vp(0))
-        if world > 1 or e2e:
-            local_out[:, 0:3] = out["image"][0]; local_out[:, 3] = out["depth"][0]; local_out[:, 4] = out["depth_0"][0]
-            fb = gather(local_out)
-            if e2e and rank == 0:
-                host_frame.copy_(fb, non_blocking=True)                       # trainer.py:589-593 .cpu().numpy() of the frame
+        """One GUI frame through the public multi-GPU frame API.  e2e=True adds the host<->device traffic: rays are
+        regenerated from the host pose and the gathered frame is copied to pinned host memory."""
+        out, _ = drv.frame(host_pose, intr, to_host=e2e, regenerate_rays=e2e, profile_events=prof)
         return out
 
     def sync_all():
@@ -162,7 +125,7 @@ def run_ours(args):
             ev[i][1].record()
             samples0.append(out["stats"].clone())
         if e2e:
-            torch.cuda.current_stream().synchronize()
+            drv.wait_host()                                                   # every frame has landed in pinned host memory
         sync_all()
         wall = time.perf_counter() - t0
         ms = [a.elapsed_time(b) for a, b in ev]
@@ -177,10 +140,11 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         frame(False); frame(True)
-    launches["n"] = 0
+    drv.wait_host()
+    drv.launches = 0
     sampler = ClockSampler(local) if rank == 0 else None
     total_ms, wall, kms, samples = timed(args.steps, e2e=False, with_prof=True)
-    n_launch = launches["n"]
+    n_launch = drv.launches
     e2e_ms, e2e_wall, _, _ = timed(args.steps, e2e=True)
     clocks = sampler.stop() if sampler else None
 
@@ -235,12 +199,12 @@ def run_ours(args):
         "data": "synthetic", "impl": "ours",
         "config": {"workload": f"{args.config}: {sim.n_ip}-IP Q-GMLS body ({sim.n_k} kernels, sim_iters {sim.iters}) + {W}x{H} deformed render, "
                                f"random-init 16-level hash grid + 64-wide MLP, density_scale {args.density_scale}, num_seek_IP {opt.num_seek_IP}",
-                   "rays": N, "n_ip": sim.n_ip, "kept_samples_per_frame": samp, "parallelism": f"ray tiles x{world}, sim on rank 0",
+                   "rays": N, "n_ip": sim.n_ip, "kept_samples_per_frame": samp, "parallelism": f"16x16 ray tiles over {world} GPU(s), simulator on rank 0" + (f", sim-aware tile weights {[round(x, 4) for x in calib['weights']]}" if calib else ""),
                    "l2": "flushed between timed frames (256 MiB fill)"},
         "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 64 + 16, "d2h_bytes_per_step": N * 5 * 4,
-                "wall_fps": K / e2e_wall, "api": "FrameDriver-equivalent: host pose -> get_rays -> sim step -> render_deformed -> pinned host frame"},
+                "wall_fps": K / e2e_wall, "api": "pienerf_b200.frame.DistFrameDriver.frame(): host pose -> pn_get_rays -> sim step -> (bcast) -> pn_render_deformed -> (gather) -> async copy to pinned host frame (double buffered)"},
         "gpu_launches": n_launch,
-        "roofline": {"kernel": "render_persistent (march+warp+hash encode+MLP+composite)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+        "roofline": {"kernel": "render_warp_kernel<3,true> (lattice march + inverse warp + hash encode + tcgen05 MLP + composite)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                      "frac": achieved / hbm, "traffic": None, "peak_source": src, "kernel_ms": kernel_ms,
                      "algorithmic_bytes": f"{ALGO_BYTES_PER_SAMPLE_FUSED} B/sample x {samp:.0f} kept samples", "share_of_step": kernel_ms / (total_ms / K)},
         "clocks": clocks, "wall_fps": K / wall,
@@ -370,6 +334,7 @@ def main():
     ap.add_argument("--config", default="chair")
     ap.add_argument("--density-scale", type=float, default=1.0, dest="density_scale")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--equal-tiles", action="store_true", help="N>1: equal tile shares instead of sim-aware weights")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--cpu-stride", type=int, default=16)
     args = ap.parse_args()

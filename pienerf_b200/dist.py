@@ -6,16 +6,43 @@ import torch
 import torch.distributed as dist
 
 
-def tile_partition(H, W, world_size, tile=16):
-    """Round-robin assignment of tile x tile pixel blocks to ranks (contiguous bands would not balance: the
-    object covers a minority of the pixels).  Returns a list of int64 pixel-index arrays (row-major), one per
-    rank, every pixel exactly once."""
+def tile_partition(H, W, world_size, tile=16, weights=None):
+    """Assignment of tile x tile pixel blocks to ranks, interleaved along diagonals so neighbouring tiles in x AND
+    y land on different ranks (contiguous bands would not balance: the object covers a minority of the pixels).
+    `weights` (len world_size, sum 1) gives each rank's share of the tiles — rank 0 also runs the simulator, so it
+    gets a smaller share (see DistFrameDriver.calibrate).  Deterministic: every rank computes the same partition.
+    Returns a list of int64 pixel-index arrays (row-major), one per rank, every pixel exactly once."""
     ty, tx = (H + tile - 1) // tile, (W + tile - 1) // tile
-    tid = (np.arange(H)[:, None] // tile) * tx + (np.arange(W)[None, :] // tile)
-    # diagonal interleave so neighbouring tiles in x AND y land on different ranks
-    owner = ((np.arange(H)[:, None] // tile) + (np.arange(W)[None, :] // tile)) % world_size if world_size > 1 else np.zeros((H, W), np.int64)
-    del tid, ty
-    flat = owner.reshape(-1)
+    if world_size == 1:
+        return [np.arange(H * W, dtype=np.int64)]
+    ys, xs = np.divmod(np.arange(ty * tx), tx)
+    order = np.lexsort((ys, (ys + xs)))                      # walk tiles diagonal by diagonal
+    if weights is None:
+        owner_of_seq = np.arange(ty * tx) % world_size
+    else:
+        w = np.asarray(weights, dtype=np.float64)
+        w = w / w.sum()
+        owner_of_seq = np.empty(ty * tx, dtype=np.int64)
+        if world_size > 2 and np.allclose(w[1:], w[1]):
+            # rank 0 takes evenly spaced tiles of the diagonal walk, the others keep a plain round robin over the rest
+            # (preserves the diagonal interleave, which balances much better than a generic weighted scheme)
+            n0 = int(round(w[0] * ty * tx))
+            take0 = np.zeros(ty * tx, dtype=bool)
+            if n0 > 0:
+                take0[np.unique(np.floor((np.arange(n0) + 0.5) * (ty * tx) / n0).astype(np.int64))] = True
+            owner_of_seq[take0] = 0
+            owner_of_seq[~take0] = 1 + np.arange(int((~take0).sum())) % (world_size - 1)
+        else:
+            credit = np.zeros(world_size)
+            for i in range(ty * tx):                         # largest-remaining-credit weighted round robin
+                credit += w
+                r = int(np.argmax(credit))
+                owner_of_seq[i] = r
+                credit[r] -= 1.0
+    tile_owner = np.empty(ty * tx, dtype=np.int64)
+    tile_owner[order] = owner_of_seq
+    pix_tile = (np.arange(H)[:, None] // tile) * tx + (np.arange(W)[None, :] // tile)
+    flat = tile_owner[pix_tile].reshape(-1)
     return [np.nonzero(flat == r)[0].astype(np.int64) for r in range(world_size)]
 
 

@@ -72,6 +72,141 @@ class FrameDriver:
         return {"image": image, "depth": depth, "depth_0": depth_0}
 
 
+class DistFrameDriver:
+    """The frame loop on N GPUs of one node (one process per GPU; N = 1 works without a process group).
+
+    Per frame: rank 0 reads the IP state and advances the simulator (state BEFORE the step is
+    rendered, trainer.py:303-308), ONE broadcast of the packed [n_ip,39] fp32 IP state, every rank renders its
+    interleaved tiles with the fused kernel, ONE gather of [pixels,5] rows (rgb, depth, depth_0) to rank 0, and an
+    asynchronous copy of the frame into one of two pinned host buffers (the host consumes frame k while the GPUs
+    work on k+1; `wait_host()` blocks until a given frame has landed).
+    """
+
+    def __init__(self, model, sim, opt, tile=16, weights=None):
+        import torch.distributed as dist
+        from .dist import FrameGather, tile_partition
+        self.model, self.sim, self.opt, self.tile = model, sim, opt, tile
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.dev = next(model.parameters()).device
+        IP_pos, IP_F, IP_dF = sim.get_IP_info()
+        model.p_ori = IP_pos
+        model.p_def, model.IP_F, model.IP_dF = IP_pos, IP_F, IP_dF
+        model.IP_dx = sim.dx * 1.05
+        self.W, self.H = opt.W, opt.H
+        self.ipbuf = torch.zeros(sim.n_ip, 39, dtype=torch.float32, device=self.dev)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.host = [torch.empty(self.W * self.H, 5, dtype=torch.float32).pin_memory() for _ in range(2)] if self.rank == 0 else None
+        self.copy_done = [None, None]
+        self.frame_id = 0
+        self.launches = 0
+        self.set_partition(weights)
+
+    def set_partition(self, weights=None):
+        from .dist import FrameGather, tile_partition
+        self.parts = tile_partition(self.H, self.W, self.world, self.tile, weights)
+        self.my = torch.from_numpy(self.parts[self.rank]).to(self.dev)
+        self.gather = FrameGather(self.parts, 5, self.dev)
+        self.local = torch.empty(len(self.parts[self.rank]), 5, dtype=torch.float32, device=self.dev)
+        self._rays = None
+
+    def rays(self, pose_host, intrinsics):
+        full = raymarching.get_rays(pose_host[None] if pose_host.dim() == 2 else pose_host, intrinsics, self.H, self.W)
+        self.launches += 1
+        if self.world == 1:
+            return full["rays_o"], full["rays_d"]
+        self.launches += 2
+        return full["rays_o"][:, self.my].contiguous(), full["rays_d"][:, self.my].contiguous()
+
+    @torch.no_grad()
+    def frame(self, pose_host, intrinsics, to_host=True, regenerate_rays=True, profile_events=None, paused=False):
+        """One GUI frame.  Returns (render outputs of this rank, index of the pinned host buffer or None)."""
+        import torch.distributed as dist
+        from . import _lib
+        from .dist import broadcast_ip_state, pack_ip_state, unpack_ip_state
+        if regenerate_rays or self._rays is None:                    # trainer.py:541-543: rays from the host pose every frame
+            self._rays = self.rays(pose_host, intrinsics)
+        rays_o, rays_d = self._rays
+        if not paused:
+            if self.rank == 0:
+                pos, F, dF = self.sim.get_IP_info()                      # state BEFORE the step (trainer.py:303-306)
+                self.launches += 1
+                if self.world > 1:
+                    pack_ip_state(pos, F, dF, self.ipbuf)
+                    self.launches += 3
+            if self.world > 1:
+                broadcast_ip_state(self.ipbuf)                           # the other ranks start rendering at once ...
+                pos, F, dF = unpack_ip_state(self.ipbuf)
+                self.launches += 3
+            if self.rank == 0:
+                self.sim.stepforward()                                   # ... while rank 0 advances the simulator (trainer.py:308)
+                self.launches += 2 + 3 * self.sim.iters + 1
+            self.model.p_def, self.model.IP_F, self.model.IP_dF = pos, F, dF
+        if profile_events is not None:
+            _lib.lib.pn_set_profile_events(_lib.vp(profile_events[0].cuda_event), _lib.vp(profile_events[1].cuda_event))
+        out = self.model.render_deformed(rays_o, rays_d, **self.opt)
+        self.launches += 10
+        if profile_events is not None:
+            _lib.lib.pn_set_profile_events(_lib.vp(0), _lib.vp(0))
+        slot = None
+        if self.world > 1 or to_host:
+            slot = self.frame_id & 1
+            if self.rank == 0 and self.copy_done[slot] is not None:
+                torch.cuda.current_stream().wait_event(self.copy_done[slot])   # frame buffer reuse hazard (k-2 copy finished?)
+            self.local[:, 0:3] = out["image"][0]; self.local[:, 3] = out["depth"][0]; self.local[:, 4] = out["depth_0"][0]
+            self.launches += 3
+            fb = self.gather(self.local)
+            if to_host and self.rank == 0:
+                ready = torch.cuda.Event(); ready.record()
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(ready)
+                    self.host[slot].copy_(fb, non_blocking=True)             # trainer.py:589-593 .cpu().numpy() of the frame
+                    done = torch.cuda.Event(); done.record()
+                self.copy_done[slot] = done
+                # the next gather may only overwrite `fb` after this copy has read it
+                self._fb_guard = done
+        self.frame_id += 1
+        return out, slot
+
+    def wait_host(self, slot=None):
+        """Block until the async frame copies (all, or the given slot) have landed; returns the pinned buffer(s)."""
+        if self.rank != 0:
+            return None
+        for i, ev in enumerate(self.copy_done):
+            if ev is not None and (slot is None or i == slot):
+                ev.synchronize()
+        return self.host if slot is None else self.host[slot]
+
+    @torch.no_grad()
+    def calibrate(self, pose_host, intrinsics, frames=3):
+        """Sim-aware tile weights: rank 0 also runs the simulator (S ms), so it takes a share f0 of the tiles with
+        f0*R + S = (1-f0)*R/(N-1), R = whole-frame render time.  Measured here with CUDA events, agreed by broadcast."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return None
+        tr, tsim = [], []
+        for _ in range(frames):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            if self.rank == 0:
+                e[0].record(); self.sim.get_IP_info(); self.sim.stepforward(); e[1].record()
+            rays_o, rays_d = self.rays(pose_host, intrinsics)
+            e[2].record(); self.model.render_deformed(rays_o, rays_d, **self.opt); e[3].record()
+            torch.cuda.synchronize()
+            tr.append(e[2].elapsed_time(e[3]))
+            if self.rank == 0:
+                tsim.append(e[0].elapsed_time(e[1]))
+        t = torch.tensor([min(tr), min(tsim) if tsim else 0.0], dtype=torch.float64, device=self.dev)
+        allr = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(allr, t)
+        R = float(sum(x[0] for x in allr))                                    # whole frame = sum of the equal shares
+        S = float(allr[0][1]) + 0.05                                          # + pack / bookkeeping on rank 0
+        n = self.world
+        f0 = max(0.0, min(1.0 / n, (R / (n - 1) - S) / (R * n / (n - 1))))
+        w = [f0] + [(1.0 - f0) / (n - 1)] * (n - 1)
+        self.set_partition(w)
+        return {"render_ms": R, "sim_ms": S, "weights": w}
+
+
 def build_scene(config, device="cuda", seed=0, density_scale=1.0, solver="inverse"):
     """Synthetic stand-in for `main_gui.py:20-56`: model + simulator + options for a named config."""
     from .network import NeRFNetwork
