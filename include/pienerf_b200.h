@@ -151,25 +151,26 @@ int pn_qgmls_collect_gravity(double dx, const int *topo, const double *Nx, const
                              const double *rho, int n_ip, double *rhs, void *stream);
 /* simulator/cuda_utils.py:83-151 calc_elastic + collect_rhs_IP fused; rhs [n,3] is overwritten.
  * adjacency = the kernel->(ip,corner) CSR of solver.py:279-313 (adj_bgn [n_k+1], adj [tot] = ip*8+corner);
- * deterministic gather instead of fp64 atomics.  ip_stress [n_ip,9] scratch. */
+ * deterministic gather instead of fp64 atomics.  adj_slices = ceil(max entries per kernel / 128);
+ * ip_stress [n_ip,9] and partial [n_k, adj_slices, 30] are scratch. */
 int pn_qgmls_build_rhs(double dx, const int *topo, const double *mu, const double *lam, const double *dNx,
-                       const double *dof, int n_ip, int n_k, const int *adj_bgn, const int *adj, double *ip_stress,
-                       double *rhs, void *stream);
+                       const double *dof, int n_ip, int n_k, const int *adj_bgn, const int *adj, int adj_slices,
+                       double *ip_stress, double *partial, double *rhs, void *stream);
 /* y[n,3] = Mat[n,n] x[n,3]: the compact form of `(Mat (x) I3) @ v` (solver.py:576,600). */
 int pn_qgmls_matvec3(const double *mat, const double *x, int n, double *y, void *stream);
 /* simulator/solver.py:574-576,595-602 stepforward (iters local-global iterations) as one call. */
 typedef struct {
     int n_ip, n_k, iters; double dt, dx;
     const int *topo; const double *mu, *lam, *dNx;   /* IP_kernel [n_ip,8], IP_mu/lam [n_ip], IP_dNx [n_ip,8,3,10] */
-    const int *adj_bgn, *adj;                        /* kernel -> (ip*8+corner) CSR */
+    const int *adj_bgn, *adj; int adj_slices;        /* kernel -> (ip*8+corner) CSR; ceil(max entries per kernel / 128) */
     const double *Ainv, *M;                          /* [n,n] compact: global_matrix / mass_matrix_invt2 without (x)I3 */
     const double *A; const unsigned char *active;    /* PCG only: assembled system [n,n] (no +1e-3) and active kernels [n_k] */
     int pcg_iters;
     const double *dof_rest, *dof_f, *rhs_rest, *rhs_gravity;   /* [n,3] */
     double *dof, *dof_vel;                           /* in/out [n,3] */
-    double *scratch;                                 /* >= pn_qgmls_step_scratch_doubles(n_ip, n_k) doubles */
+    double *scratch;                                 /* >= pn_qgmls_step_scratch_doubles(n_ip, n_k, adj_slices) doubles */
 } pn_qgmls_step_t;
-uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k);
+uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k, int adj_slices);
 int pn_qgmls_step(const pn_qgmls_step_t *step_host, int solver /*0 dense inverse, 1 PCG on A*/, void *stream);
 /* simulator/solver.py:402-424 get_IP_info + cuda_utils.py:206-233 update_F_kernel: emits the fp32
  * renderer layouts directly: pos [n,3], F [n,9] (F[b][a] at a*3+b), dF [n,27] (c*9+r*3+j). */

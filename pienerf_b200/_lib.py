@@ -35,7 +35,7 @@ class DeformT(C.Structure):
 
 class QgmlsStepT(C.Structure):
     _fields_ = [("n_ip", i32), ("n_k", i32), ("iters", i32), ("dt", f64), ("dx", f64),
-                ("topo", vp), ("mu", vp), ("lam", vp), ("dNx", vp), ("adj_bgn", vp), ("adj", vp),
+                ("topo", vp), ("mu", vp), ("lam", vp), ("dNx", vp), ("adj_bgn", vp), ("adj", vp), ("adj_slices", i32),
                 ("Ainv", vp), ("M", vp), ("A", vp), ("active", vp), ("pcg_iters", i32),
                 ("dof_rest", vp), ("dof_f", vp), ("rhs_rest", vp), ("rhs_gravity", vp),
                 ("dof", vp), ("dof_vel", vp), ("scratch", vp)]
@@ -74,9 +74,9 @@ _PROTOS = {
     "pn_qgmls_build_ip_global": (i32, [f64, f64, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]),
     "pn_qgmls_build_pin_global": (i32, [f64, vp, i32, vp, vp, i32, vp, vp]),
     "pn_qgmls_collect_gravity": (i32, [f64, vp, vp, vp, vp, i32, vp, vp]),
-    "pn_qgmls_build_rhs": (i32, [f64, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
+    "pn_qgmls_build_rhs": (i32, [f64, vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp]),
     "pn_qgmls_matvec3": (i32, [vp, vp, i32, vp, vp]),
-    "pn_qgmls_step_scratch_doubles": (u64, [i32, i32]),
+    "pn_qgmls_step_scratch_doubles": (u64, [i32, i32, i32]),
     "pn_qgmls_step": (i32, [C.POINTER(QgmlsStepT), i32, vp]),
     "pn_qgmls_ip_info": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "pn_qgmls_update_pos": (i32, [vp, vp, vp, i32, vp, vp]),

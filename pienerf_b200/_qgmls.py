@@ -50,18 +50,19 @@ def collect_gravity(dx, topo, Nx, gravity, rho, rhs):
                                        dptr(rho, "rho", f64), topo.shape[0], dptr(rhs, "rhs", f64), stream_ptr()))
 
 
-def build_rhs(dx, topo, mu, lam, dNx, dof, n_k, adj_bgn, adj, ip_stress, rhs):
+def build_rhs(dx, topo, mu, lam, dNx, dof, n_k, adj_bgn, adj, adj_slices, ip_stress, partial, rhs):
     check(lib.pn_qgmls_build_rhs(float(dx), dptr(topo, "topo", i32), dptr(mu, "mu", f64), dptr(lam, "lam", f64), dptr(dNx, "dNx", f64),
                                  dptr(dof, "dof", f64), topo.shape[0], int(n_k), dptr(adj_bgn, "adj_bgn", i32), dptr(adj, "adj", i32),
-                                 dptr(ip_stress, "ip_stress", f64), dptr(rhs, "rhs", f64), stream_ptr()))
+                                 int(adj_slices), dptr(ip_stress, "ip_stress", f64), dptr(partial, "partial", f64), dptr(rhs, "rhs", f64),
+                                 stream_ptr()))
 
 
 def matvec3(mat, x, y):
     check(lib.pn_qgmls_matvec3(dptr(mat, "mat", f64), dptr(x, "x", f64), mat.shape[0], dptr(y, "y", f64), stream_ptr()))
 
 
-def step_scratch_doubles(n_ip, n_k):
-    return int(lib.pn_qgmls_step_scratch_doubles(int(n_ip), int(n_k)))
+def step_scratch_doubles(n_ip, n_k, adj_slices):
+    return int(lib.pn_qgmls_step_scratch_doubles(int(n_ip), int(n_k), int(adj_slices)))
 
 
 def step(desc, solver=0):

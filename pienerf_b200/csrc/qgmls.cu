@@ -311,28 +311,34 @@ __device__ __forceinline__ void volume_project(const double *sig, double *out) {
     out[0] = sig[0] + D0; out[1] = sig[1] + D1; out[2] = sig[2] + D2;
 }
 
-// calc_elastic (cuda_utils.py:83-121): one warp per IP.  stress[v] = dx^3 (mu R + lam V)  (row-major 3x3)
+// calc_elastic (cuda_utils.py:83-121): 8 lanes per IP (one per kernel corner), 4 IPs per warp.  Each lane folds its
+// corner's 10 DOF vectors against the corner's contiguous [3][10] gradient block, F is reduced over the 8 lanes with
+// shuffles, and the 4 group leaders run the 3x3 SVD + projections side by side.
+// stress[v] = dx^3 (mu R + lam V)  (row-major 3x3)
 __global__ void __launch_bounds__(128) ip_stress_kernel(double dx3, const int *__restrict__ topo, const double *__restrict__ mu,
                                                         const double *__restrict__ lam, const double *__restrict__ dNx,
                                                         const double *__restrict__ dof, int n_ip,
                                                         double *__restrict__ stress) {
-    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (v >= n_ip) return;
-    const double *dN = dNx + (size_t)v * 240;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = t >> 3, i = t & 7;
+    const bool live = v < n_ip;
     double F[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int e = lane; e < 80; e += 32) {  // e = i*10 + x
-        const int i = e / 10, x = e % 10;
-        const double *d = dof + 3 * (size_t)(topo[8 * v + i] * 10 + x);
-        const double g0 = dN[(i * 3 + 0) * 10 + x], g1 = dN[(i * 3 + 1) * 10 + x], g2 = dN[(i * 3 + 2) * 10 + x];
-        const double d0 = d[0], d1 = d[1], d2 = d[2];
-        F[0] += d0 * g0; F[1] += d0 * g1; F[2] += d0 * g2;
-        F[3] += d1 * g0; F[4] += d1 * g1; F[5] += d1 * g2;
-        F[6] += d2 * g0; F[7] += d2 * g1; F[8] += d2 * g2;
+    if (live) {
+        const double *dN = dNx + (size_t)v * 240 + i * 30;   // [c][x]
+        const double *d = dof + 3 * (size_t)(topo[8 * v + i] * 10);
+#pragma unroll
+        for (int x = 0; x < 10; x++) {
+            const double g0 = dN[x], g1 = dN[10 + x], g2 = dN[20 + x];
+            const double d0 = d[3 * x], d1 = d[3 * x + 1], d2 = d[3 * x + 2];
+            F[0] += d0 * g0; F[1] += d0 * g1; F[2] += d0 * g2;
+            F[3] += d1 * g0; F[4] += d1 * g1; F[5] += d1 * g2;
+            F[6] += d2 * g0; F[7] += d2 * g1; F[8] += d2 * g2;
+        }
     }
 #pragma unroll
     for (int k = 0; k < 9; k++)
-        for (int o = 16; o > 0; o >>= 1) F[k] += __shfl_xor_sync(kFull, F[k], o);
-    if (lane == 0) {
+        for (int o = 4; o > 0; o >>= 1) F[k] += __shfl_xor_sync(kFull, F[k], o);
+    if (live && i == 0) {
         double U[9], sg[3], V[9], sp[3];
         svd3x3(F, U, sg, V);
         volume_project(sg, sp);
@@ -346,22 +352,22 @@ __global__ void __launch_bounds__(128) ip_stress_kernel(double dx3, const int *_
     }
 }
 
-// collect_rhs_IP as a gather (cuda_utils.py:124-151 semantics, :153-188 structure): one CTA per kernel k.
-// Each thread walks the kernel's (ip,corner) adjacency with stride blockDim, reads the IP's 3x3 stress once and
-// the corner's contiguous 30-double gradient block, and accumulates all 10 slots x 3 components; a fixed-order
-// shuffle + shared-memory tree makes the result bit-reproducible (no fp64 atomics).
-// out[row] = (base_add[row] + sum) - base_sub[row] when the optional bases are given (`momentum + rhs - rhs_rest`).
-__global__ void __launch_bounds__(128) rhs_gather_kernel(const int *__restrict__ adj_bgn, const int *__restrict__ adj,
-                                                         const double *__restrict__ stress, const double *__restrict__ dNx,
-                                                         int n_k, const double *__restrict__ base_add,
-                                                         const double *__restrict__ base_sub, double *__restrict__ out) {
+// collect_rhs_IP as a gather (cuda_utils.py:124-151 semantics, :153-188 structure), two deterministic passes:
+//  1. rhs_partial_kernel: CTA (k, s) takes the s-th 128-entry slice of kernel k's (ip,corner) adjacency, one entry per
+//     thread: reads the IP's 3x3 stress and the corner's contiguous [3][10] gradient block, forms all 10 slots x 3
+//     components, and reduces them over the CTA with a fixed shuffle + shared-memory tree -> partial[k][s][30];
+//  2. rhs_final_kernel: sums the slices in order and applies `momentum + rhs - rhs_rest` (solver.py:599).
+// No fp64 atomics anywhere: steps are bit-reproducible.
+__global__ void __launch_bounds__(128) rhs_partial_kernel(const int *__restrict__ adj_bgn, const int *__restrict__ adj,
+                                                          const double *__restrict__ stress, const double *__restrict__ dNx,
+                                                          int slices, double *__restrict__ partial) {
     __shared__ double part[4][30];
-    const int k = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (k >= n_k) return;
+    const int k = blockIdx.x, sl = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int e = adj_bgn[k] + sl * 128 + threadIdx.x;
     double acc[30];
 #pragma unroll
     for (int i = 0; i < 30; i++) acc[i] = 0.0;
-    for (int e = adj_bgn[k] + threadIdx.x; e < adj_bgn[k + 1]; e += blockDim.x) {
+    if (e < adj_bgn[k + 1]) {
         const int code = adj[e], v = code >> 3, i = code & 7;
         const double *S = stress + (size_t)v * 9;
         const double *dN = dNx + (size_t)v * 240 + i * 30;   // [c][x], 30 contiguous doubles
@@ -369,9 +375,9 @@ __global__ void __launch_bounds__(128) rhs_gather_kernel(const int *__restrict__
 #pragma unroll
         for (int x = 0; x < 10; x++) {
             const double g0 = dN[x], g1 = dN[10 + x], g2 = dN[20 + x];
-            acc[3 * x] += s0 * g0 + s1 * g1 + s2 * g2;
-            acc[3 * x + 1] += s3 * g0 + s4 * g1 + s5 * g2;
-            acc[3 * x + 2] += s6 * g0 + s7 * g1 + s8 * g2;
+            acc[3 * x] = s0 * g0 + s1 * g1 + s2 * g2;
+            acc[3 * x + 1] = s3 * g0 + s4 * g1 + s5 * g2;
+            acc[3 * x + 2] = s6 * g0 + s7 * g1 + s8 * g2;
         }
     }
 #pragma unroll
@@ -380,11 +386,20 @@ __global__ void __launch_bounds__(128) rhs_gather_kernel(const int *__restrict__
         if (lane == 0) part[wid][i] = acc[i];
     }
     __syncthreads();
-    if (threadIdx.x < 30) {
-        const int row3 = k * 30 + threadIdx.x;               // (k*10 + x)*3 + r
-        const double sum = ((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x];
-        out[row3] = base_add ? (base_add[row3] + sum) - base_sub[row3] : sum;   // solver.py:599 order
-    }
+    if (threadIdx.x < 30)
+        partial[((size_t)k * slices + sl) * 30 + threadIdx.x] =
+            ((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) rhs_final_kernel(const double *__restrict__ partial, int n_k, int slices,
+                                                        const double *__restrict__ base_add, const double *__restrict__ base_sub,
+                                                        double *__restrict__ out) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;    // (k*10 + x)*3 + r
+    if (id >= n_k * 30) return;
+    const int k = id / 30, i = id % 30;
+    double sum = 0.0;
+    for (int s = 0; s < slices; s++) sum += partial[((size_t)k * slices + s) * 30 + i];
+    out[id] = base_add ? (base_add[id] + sum) - base_sub[id] : sum;
 }
 
 // ---------------------------------------------------------------- global step
@@ -665,12 +680,14 @@ extern "C" int pn_qgmls_collect_gravity(double dx, const int *topo, const double
 }
 
 extern "C" int pn_qgmls_build_rhs(double dx, const int *topo, const double *mu, const double *lam, const double *dNx,
-                                  const double *dof, int n_ip, int n_k, const int *adj_bgn, const int *adj,
-                                  double *ip_stress, double *rhs, void *stream) {
-    PN_REQUIRE(topo && mu && lam && dNx && dof && adj_bgn && adj && ip_stress && rhs, "null pointer");
+                                  const double *dof, int n_ip, int n_k, const int *adj_bgn, const int *adj, int slices,
+                                  double *ip_stress, double *partial, double *rhs, void *stream) {
+    PN_REQUIRE(topo && mu && lam && dNx && dof && adj_bgn && adj && ip_stress && partial && rhs, "null pointer");
+    PN_REQUIRE(slices >= 1, "adjacency slices must be >= 1");
     cudaStream_t st = PN_STREAM(stream);
-    ip_stress_kernel<<<div_up(n_ip * 32, 128), 128, 0, st>>>(dx * dx * dx, topo, mu, lam, dNx, dof, n_ip, ip_stress);
-    rhs_gather_kernel<<<n_k, 128, 0, st>>>(adj_bgn, adj, ip_stress, dNx, n_k, nullptr, nullptr, rhs);
+    ip_stress_kernel<<<div_up(n_ip * 8, 128), 128, 0, st>>>(dx * dx * dx, topo, mu, lam, dNx, dof, n_ip, ip_stress);
+    rhs_partial_kernel<<<dim3(n_k, slices), 128, 0, st>>>(adj_bgn, adj, ip_stress, dNx, slices, partial);
+    rhs_final_kernel<<<div_up(n_k * 30, 256), 256, 0, st>>>(partial, n_k, slices, nullptr, nullptr, rhs);
     PN_LAUNCH_CHECK("build_rhs");
     return PN_OK;
 }
@@ -683,14 +700,15 @@ extern "C" int pn_qgmls_matvec3(const double *mat, const double *x, int n, doubl
     return PN_OK;
 }
 
-extern "C" uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k) {
-    return 9ull * n_ip + 9ull * 30 * n_k + 16;
+extern "C" uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k, int adj_slices) {
+    return 9ull * n_ip + 9ull * 30 * n_k + 16 + 30ull * n_k * (adj_slices > 0 ? adj_slices : 1);
 }
 
 extern "C" int pn_qgmls_step(const pn_qgmls_step_t *s, int solver, void *stream) {
     PN_REQUIRE(s && s->topo && s->mu && s->lam && s->dNx && s->adj_bgn && s->adj && s->M && s->dof_rest && s->dof_f &&
                    s->rhs_rest && s->rhs_gravity && s->dof && s->dof_vel && s->scratch, "null pointer");
     PN_REQUIRE(solver == 0 || solver == 1, "solver must be 0 (dense inverse) or 1 (PCG)");
+    PN_REQUIRE(s->adj_slices >= 1, "adj_slices must be >= 1");
     PN_REQUIRE(solver == 1 ? (s->A && s->active) : (s->Ainv != nullptr), "missing system matrix for the chosen solver");
     cudaStream_t st = PN_STREAM(stream);
     const int n = 10 * s->n_k, n3 = 3 * n;
@@ -698,14 +716,16 @@ extern "C" int pn_qgmls_step(const pn_qgmls_step_t *s, int solver, void *stream)
     double *tilde = stress + 9 * (size_t)s->n_ip;
     double *last = tilde + n3, *mom = last + n3, *rhs = mom + n3, *x = rhs + n3;
     double *pcg = x + n3;  // r, z, p, Ap (4*n3) + 9 scalars, only touched by the PCG path
+    double *partial = pcg + 4 * (size_t)n3 + 16;
     const double dx3 = s->dx * s->dx * s->dx;
     const int eb = div_up(n3, 256);
     axpy_tilde_kernel<<<eb, 256, 0, st>>>(s->dof, s->dof_vel, s->dt, n3, tilde, last);
     // momentum = M/dt^2 @ dof_tilde + dof_f + rhs_gravity  (solver.py:576)
     matvec3_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(s->M, tilde, n, s->dof_f, s->rhs_gravity, nullptr, mom);
     for (int it = 0; it < s->iters; it++) {
-        ip_stress_kernel<<<div_up(s->n_ip * 32, 128), 128, 0, st>>>(dx3, s->topo, s->mu, s->lam, s->dNx, s->dof, s->n_ip, stress);
-        rhs_gather_kernel<<<s->n_k, 128, 0, st>>>(s->adj_bgn, s->adj, stress, s->dNx, s->n_k, mom, s->rhs_rest, rhs);
+        ip_stress_kernel<<<div_up(s->n_ip * 8, 128), 128, 0, st>>>(dx3, s->topo, s->mu, s->lam, s->dNx, s->dof, s->n_ip, stress);
+        rhs_partial_kernel<<<dim3(s->n_k, s->adj_slices), 128, 0, st>>>(s->adj_bgn, s->adj, stress, s->dNx, s->adj_slices, partial);
+        rhs_final_kernel<<<div_up(n3, 256), 256, 0, st>>>(partial, s->n_k, s->adj_slices, mom, s->rhs_rest, rhs);
         if (solver == 0) {
             // dof = dof_rest + Ainv rhs  (solver.py:600-601)
             matvec3_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(s->Ainv, rhs, n, s->dof_rest, nullptr, nullptr, s->dof);

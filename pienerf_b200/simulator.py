@@ -137,8 +137,10 @@ class Simulator:
         self.buffer = order.to(torch.int32).contiguous()        # code = ip*8 + corner
         self.tot = int(self.buffer.numel())
 
-        self._scratch = torch.empty(_qgmls.step_scratch_doubles(n_ip, n_k), dtype=torchfloat, device=dev)
+        self.adj_slices = max(1, (int(self.kernel_cnt.max()) + 127) // 128)
+        self._scratch = torch.empty(_qgmls.step_scratch_doubles(n_ip, n_k, self.adj_slices), dtype=torchfloat, device=dev)
         self._ip_stress = torch.empty(n_ip, 9, dtype=torchfloat, device=dev)
+        self._partial = torch.empty(n_k, self.adj_slices, 30, dtype=torchfloat, device=dev)
         # rhs_rest = build_rhs() + M/dt^2 @ dof (solver.py:314)
         tmp = torch.empty_like(self.dof)
         _qgmls.matvec3(self.mass_matrix_invt2, self.dof, tmp)
@@ -178,7 +180,7 @@ class Simulator:
         """solver.py:541-571 -> [n,3]."""
         rhs = torch.empty_like(self.dof)
         _qgmls.build_rhs(self.dx, self.IP_kernel, self.IP_mu, self.IP_lam, self.IP_dNx, self.dof, self.n_k, self.kernel_bg,
-                         self.buffer, self._ip_stress, rhs)
+                         self.buffer, self.adj_slices, self._ip_stress, self._partial, rhs)
         return rhs
 
     def _desc(self):
@@ -186,7 +188,7 @@ class Simulator:
             d = QgmlsStepT()
             d.n_ip, d.n_k, d.iters, d.dt, d.dx = self.n_ip, self.n_k, int(self.iters), float(self.dt), float(self.dx)
             d.topo, d.mu, d.lam, d.dNx = dptr(self.IP_kernel), dptr(self.IP_mu), dptr(self.IP_lam), dptr(self.IP_dNx)
-            d.adj_bgn, d.adj = dptr(self.kernel_bg), dptr(self.buffer)
+            d.adj_bgn, d.adj, d.adj_slices = dptr(self.kernel_bg), dptr(self.buffer), int(self.adj_slices)
             d.Ainv, d.M, d.A, d.active = dptr(self.global_matrix), dptr(self.mass_matrix_invt2), dptr(self.system_matrix), dptr(self._active_u8)
             d.pcg_iters = int(self.pcg_iters)
             d.dof_rest, d.rhs_rest, d.rhs_gravity = dptr(self.dof_rest), dptr(self.rhs_rest), dptr(self.rhs_gravity)
