@@ -21,7 +21,13 @@ oracle/_build/libsim_oracle.so: oracle/sim_oracle.c
 	@mkdir -p oracle/_build
 	gcc -O2 -fopenmp -shared -fPIC -o $@ $< -lm
 
+# developer A/B builds: make variant TAG=x EXTRA="-DPN_FOO=1"  ->  pienerf_b200/lib/libpienerf_b200_x.so (load with PN_LIB=...)
+variant:
+	@mkdir -p build_$(TAG) pienerf_b200/lib
+	@for f in $(SRC); do b=$$(basename $$f .cu); echo "[$(TAG)] $$b"; $(NVCC) $(NVFLAGS) $(EXTRA) -c $$f -o build_$(TAG)/$$b.o 2> build_$(TAG)/$$b.ptxas.log || { cat build_$(TAG)/$$b.ptxas.log; exit 1; }; done
+	$(NVCC) -shared $(ARCH) -o pienerf_b200/lib/libpienerf_b200_$(TAG).so build_$(TAG)/*.o -lcudart
+
 clean:
 	rm -rf build $(LIB) oracle/_build
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean variant

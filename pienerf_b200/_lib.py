@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpienerf_b200.so")
+# PN_LIB: developer override used to A/B kernel variants built with `make variant TAG=... EXTRA=-D...` (same C-ABI)
+LIB_PATH = os.environ.get("PN_LIB") or os.path.join(_HERE, "lib", "libpienerf_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

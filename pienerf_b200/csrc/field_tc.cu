@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(kGroups * 128, 1) field_forward_tc_kernel(cons
                                                                             float *__restrict__ sigmas, float *__restrict__ rgbs) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FieldTcSmem &S = *reinterpret_cast<FieldTcSmem *>(smem_raw);
-    const int group = threadIdx.x >> 7, row = threadIdx.x & 127;
+    const int group = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0), row = threadIdx.x & 127;  // provably warp-uniform
     pn::tc::TileSmem &T = S.tile[group];
     pn::tc::weights_fill(S.w, f);
     if (row == 0) pn::tc::mbar_init(&T.bar, 1);

@@ -54,6 +54,12 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {    // same warp that allocated
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// one lane of a converged warp (the compiler then keeps MMA descriptors in uniform registers: no per-thread waterfall)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -148,13 +154,21 @@ __device__ __forceinline__ void weights_fill(Weights &w, const pn_field_t &f) {
     }
 }
 
+// bf16 hi/lo split of two values at once: hi = {rn(a), rn(b)}, lo = {rn(a - hi_a), rn(b - hi_b)} (a in the low half =
+// the lower k index).  One packed convert per word instead of one per value; bit-identical to split_bf16.
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+}
+
 // store 8 consecutive k-values (one 16-byte chunk) of this thread's row into the hi and lo activation images
 __device__ __forceinline__ void store_chunk(TileSmem &t, int row, int chunk, const float (&v)[8]) {
-    __align__(16) __nv_bfloat16 h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) split_bf16(v[i], h[i], l[i]);
-    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(t.a[0]) + chunk * 2048 + row * 16) = *reinterpret_cast<const uint4 *>(h);
-    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(t.a[1]) + chunk * 2048 + row * 16) = *reinterpret_cast<const uint4 *>(l);
+    uint4 h, l;
+    split_pair(v[0], v[1], h.x, l.x); split_pair(v[2], v[3], h.y, l.y);
+    split_pair(v[4], v[5], h.z, l.z); split_pair(v[6], v[7], h.w, l.w);
+    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(t.a[0]) + chunk * 2048 + row * 16) = h;
+    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(t.a[1]) + chunk * 2048 + row * 16) = l;
 }
 
 // D[128,N] (TMEM columns tmem_d..) = A[128,K] W[N,K]^T with the 3-term bf16 split.  Called by ONE thread of the group.
@@ -201,14 +215,14 @@ static __device__ __noinline__ void epilogue_relu64(TileSmem &t, int row, uint32
 __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int group, int row, const float (&sh)[16], uint32_t &phase,
                                          float &sigma, float &r, float &g, float &b) {
     const uint32_t tm = t.tmem + ((uint32_t)(row & ~31) << 16);  // this warp's 32 TMEM lanes
-    const bool leader = (row == 0);
+    const bool warp0 = (row >> 5) == 0;  // warp-uniform: the group's first warp issues the MMAs through one elected lane
     float v[16], c8[8];
 
     // ---- sigma_net[0]: [128,32] x [64,32]^T -> cols 0..63
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    if (leader) { tc_fence_after(); issue_layer<64, 32>(t, w.w1[0], w.w1[1], t.tmem); umma_commit(&t.bar); }
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<64, 32>(t, w.w1[0], w.w1[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
     epilogue_relu64(t, row, tm);
@@ -216,7 +230,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    if (leader) { tc_fence_after(); issue_layer<16, 64>(t, w.w2[0], w.w2[1], t.tmem + 64); umma_commit(&t.bar); }
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<16, 64>(t, w.w2[0], w.w2[1], t.tmem + 64); umma_commit(&t.bar); } __syncwarp(); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
     tmem_ld16(tm + 64, v);
@@ -239,7 +253,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    if (leader) { tc_fence_after(); issue_layer<64, 32>(t, w.w3[0], w.w3[1], t.tmem); umma_commit(&t.bar); }
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<64, 32>(t, w.w3[0], w.w3[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
     epilogue_relu64(t, row, tm);
@@ -247,7 +261,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    if (leader) { tc_fence_after(); issue_layer<64, 64>(t, w.w4[0], w.w4[1], t.tmem + 64); umma_commit(&t.bar); }
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<64, 64>(t, w.w4[0], w.w4[1], t.tmem + 64); umma_commit(&t.bar); } __syncwarp(); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
     epilogue_relu64(t, row, tm + 64);
@@ -255,7 +269,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    if (leader) { tc_fence_after(); issue_layer<16, 64>(t, w.w5[0], w.w5[1], t.tmem); umma_commit(&t.bar); }
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<16, 64>(t, w.w5[0], w.w5[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
     tmem_ld16(tm, v);
@@ -277,11 +291,11 @@ __device__ __forceinline__ void encode_to_tile(TileSmem &t, const Weights &w, co
     for (int l = 0; l < 16; l++) {
         float2 e = make_float2(0.f, 0.f);
         if (in) e = lookup3_c2(table + w.level_off[l], w.geo[l], u, vv, ww, 0);
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(e.x, h0, l0); split_bf16(e.y, h1, l1);
+        uint32_t hw, lw;
+        split_pair(e.x, e.y, hw, lw);
         const int off = (l >> 2) * 2048 + (l & 3) * 4;
-        *reinterpret_cast<__nv_bfloat162 *>(hi + off) = __halves2bfloat162(h0, h1);
-        *reinterpret_cast<__nv_bfloat162 *>(lo + off) = __halves2bfloat162(l0, l1);
+        *reinterpret_cast<uint32_t *>(hi + off) = hw;
+        *reinterpret_cast<uint32_t *>(lo + off) = lw;
     }
 }
 

@@ -61,8 +61,34 @@ __device__ __forceinline__ uint32_t vertex_index(const uint32_t (&v)[D], const L
     return g.mask ? (index & g.mask) : (index % g.size);  // same value; avoids a runtime-divisor modulo
 }
 
+// Generic-index fallback of lookup3_c2 (tiled grids, hashed levels whose size is not a power of two): rare, so it is
+// kept out of line (scalar arguments only: nothing of the hot paths is forced through local memory) to spare the
+// instruction cache of the fused kernels.  Same weights and corner order as the inline paths.
+static __device__ __noinline__ float2 lookup3_c2_generic(const float2 *__restrict__ tab, uint32_t size, uint32_t stride1,
+                                                         uint32_t gridtype, uint32_t gx, uint32_t gy, uint32_t gz, float px,
+                                                         float py, float pz) {
+    LevelGeom g;
+    g.size = size; g.stride1 = stride1; g.mask = 0; g.scale = 0.f; g.resolution = 0; g.dense3 = false;
+    float2 r = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int c = 0; c < 8; c++) {
+        const uint32_t vv[3] = {gx + (c & 1), gy + ((c >> 1) & 1), gz + ((c >> 2) & 1)};
+        const float2 v = __ldg(tab + vertex_index<3>(vv, g, gridtype));
+        float w = (c & 1) ? px : 1.0f - px;
+        w *= (c & 2) ? py : 1.0f - py;
+        w *= (c & 4) ? pz : 1.0f - pz;
+        r.x += w * v.x;
+        r.y += w * v.y;
+    }
+    return r;
+}
+
 // Trilinear lookup of one level for D=3, C=2, fp32 table, linear interpolation: the hot instantiation.
 // x01 in [0,1] (caller handles the out-of-range -> zeros rule).  `tab` points at the level's first entry.
+// Three warp-uniform index paths (the level decides): dense (linear index, provably < size), hashed with a
+// power-of-two table (every hashed level of the reference config: y*P1 and z*P2 are hoisted out of the corner
+// loop, (v+1)*P == v*P + P mod 2^32, and `& mask` replaces the runtime-divisor modulo), and the generic fallback.
+// Same vertices, same weights ((wx*wy)*wz) and the same corner order of the sum as gridencoder.cu:137-197.
 __device__ __forceinline__ float2 lookup3_c2(const float2 *__restrict__ tab, const LevelGeom &g, float x, float y,
                                              float z, uint32_t gridtype = 0) {
     float px = x * g.scale + 0.5f, py = y * g.scale + 0.5f, pz = z * g.scale + 0.5f;
@@ -72,28 +98,29 @@ __device__ __forceinline__ float2 lookup3_c2(const float2 *__restrict__ tab, con
     float2 v[8];
     if (g.dense3) {
         const uint32_t s1 = g.stride1, s2 = g.stride1 * g.stride1;
-        const uint32_t base = gx + gy * s1 + gz * s2;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            uint32_t idx = base + (c & 1) + ((c >> 1) & 1) * s1 + ((c >> 2) & 1) * s2;
-            v[c] = __ldg(tab + idx);  // idx < stride1^3 <= size
-        }
+        const float2 *b00 = tab + (gx + gy * s1 + gz * s2);  // idx < stride1^3 <= size
+        const float2 *b10 = b00 + s1, *b01 = b00 + s2, *b11 = b01 + s1;
+        v[0] = __ldg(b00); v[1] = __ldg(b00 + 1); v[2] = __ldg(b10); v[3] = __ldg(b10 + 1);
+        v[4] = __ldg(b01); v[5] = __ldg(b01 + 1); v[6] = __ldg(b11); v[7] = __ldg(b11 + 1);
+    } else if (gridtype == 0 && g.mask) {
+        const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u;
+        const uint32_t hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
+        const uint32_t x1 = gx + 1, m = g.mask;
+        v[0] = __ldg(tab + ((gx ^ hy0 ^ hz0) & m)); v[1] = __ldg(tab + ((x1 ^ hy0 ^ hz0) & m));
+        v[2] = __ldg(tab + ((gx ^ hy1 ^ hz0) & m)); v[3] = __ldg(tab + ((x1 ^ hy1 ^ hz0) & m));
+        v[4] = __ldg(tab + ((gx ^ hy0 ^ hz1) & m)); v[5] = __ldg(tab + ((x1 ^ hy0 ^ hz1) & m));
+        v[6] = __ldg(tab + ((gx ^ hy1 ^ hz1) & m)); v[7] = __ldg(tab + ((x1 ^ hy1 ^ hz1) & m));
     } else {
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const uint32_t vv[3] = {gx + (c & 1), gy + ((c >> 1) & 1), gz + ((c >> 2) & 1)};
-            v[c] = __ldg(tab + vertex_index<3>(vv, g, gridtype));
-        }
+        return lookup3_c2_generic(tab, g.size, g.stride1, gridtype, gx, gy, gz, px, py, pz);
     }
+    const float qx = 1.0f - px, qy = 1.0f - py, qz = 1.0f - pz;
+    const float w00 = qx * qy, w10 = px * qy, w01 = qx * py, w11 = px * py;  // (1*wx)*wy, 1*wx exact
+    const float w[8] = {w00 * qz, w10 * qz, w01 * qz, w11 * qz, w00 * pz, w10 * pz, w01 * pz, w11 * pz};
     float2 r = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-        float w = 1.0f;
-        w *= (c & 1) ? px : 1.0f - px;
-        w *= (c & 2) ? py : 1.0f - py;
-        w *= (c & 4) ? pz : 1.0f - pz;
-        r.x += w * v[c].x;
-        r.y += w * v[c].y;
+        r.x += w[c] * v[c].x;
+        r.y += w[c] * v[c].y;
     }
     return r;
 }

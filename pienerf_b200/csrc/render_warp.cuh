@@ -200,12 +200,12 @@ __device__ __forceinline__ bool bend_sample_packed(const IpPack &P, const pn::Be
 constexpr int kQueue = 64;   // per-warp sample FIFO (power of two)
 constexpr int kRing = 128;   // in-flight ray descriptors per warp (> kQueue + 2)
 
-struct WarpShared {
-    float q[kQueue][8];     // x y z dirx diry dirz dt t_after
-    int qtag[kQueue];
+struct __align__(16) WarpShared {
+    float q[kQueue][8];     // x y z dirx diry dirz dt -
+    int2 qmeta[kQueue];     // (ray tag, bitcast t_after): what the compositor needs, one 64-bit load
+    float4 st[32];          // (alpha, r, g, b) of the current tile
     int ring_ray[kRing];    // per in-flight ray (tag % kRing): pixel id, near, far
     float ring_near[kRing], ring_far[kRing];
-    float st_alpha[32], st_r[32], st_g[32], st_b[32];
 };
 
 constexpr int kTcGroups = 3;   // 128-sample tile groups per CTA in tensor-core mode (384 threads, 1 CTA / SM)
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(TC ? kTcGroups * 128 : 128, TC ? 1 : 3) render
     pn::FieldSmem &fs = fbs.w;
     float *scratch = fbs.scratch + threadIdx.x;
     RenderTcSmem &TS = *reinterpret_cast<RenderTcSmem *>(smem_raw);
-    const int group = threadIdx.x >> 7, row = threadIdx.x & 127;
+    const int group = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0), row = threadIdx.x & 127;  // provably warp-uniform
     WarpShared *wsh_all = reinterpret_cast<WarpShared *>(smem_raw + (((TC ? sizeof(RenderTcSmem) : sizeof(pn::FieldBlockSmem)) + 127) & ~size_t(127)));
     __shared__ unsigned char rankA[27], rankB[27];
     uint32_t phase = 0;
@@ -360,8 +360,9 @@ __global__ void __launch_bounds__(TC ? kTcGroups * 128 : 128, TC ? 1 : 3) render
             if ((take >> lane) & 1u) {
                 const int s = (qhead + qcount + __popc(take & lt_mask)) & (kQueue - 1);
                 float *e = W.q[s];
-                e[0] = x; e[1] = y; e[2] = z; e[3] = dx; e[4] = dy; e[5] = dz; e[6] = dt; e[7] = t_after;
-                W.qtag[s] = m_tag;
+                *reinterpret_cast<float4 *>(e) = make_float4(x, y, z, dx);
+                *reinterpret_cast<float4 *>(e + 4) = make_float4(dy, dz, dt, 0.f);
+                W.qmeta[s] = make_int2(m_tag, __float_as_int(t_after));
             }
             qcount += ntake; m_emitted += ntake;
             const bool capped = m_emitted >= (int)A.max_samples;
@@ -415,13 +416,13 @@ __global__ void __launch_bounds__(TC ? kTcGroups * 128 : 128, TC ? 1 : 3) render
                 alpha = 1.0f - __expf(-sigma * e[6]);
             }
         }
-        W.st_alpha[lane] = alpha; W.st_r[lane] = r; W.st_g[lane] = g; W.st_b[lane] = b;
+        W.st[lane] = make_float4(alpha, r, g, b);
         __syncwarp();
         evaluated += n;
         // ------------------------------------------------------------------ composite, in FIFO order (raymarching.cu:862-913)
         for (int j = 0; j < n; j++) {
-            const int s = (qhead + j) & (kQueue - 1);
-            const int tag = W.qtag[s];
+            const int2 meta = W.qmeta[(qhead + j) & (kQueue - 1)];
+            const int tag = meta.x;
             if (tag != c_tag) {
                 if (c_tag >= 0 && !c_done) finalize(c_tag);
                 c_tag = tag; c_done = false;
@@ -429,15 +430,15 @@ __global__ void __launch_bounds__(TC ? kTcGroups * 128 : 128, TC ? 1 : 3) render
                 tdepth = W.ring_near[tag & (kRing - 1)]; last_t = tdepth;
             }
             if (c_done) continue;                                          // samples marched past an early termination
-            const float a = W.st_alpha[j];
+            const float4 sa = W.st[j];
             const float T = 1 - ws;
-            const float w = a * T;
+            const float w = sa.x * T;
             ws += w;
-            const float ta = W.q[s][7];
+            const float ta = __int_as_float(meta.y);
             tdepth += ta - last_t;
             last_t = ta;
             dep += w * tdepth;
-            cr += w * W.st_r[j]; cg += w * W.st_g[j]; cb += w * W.st_b[j];
+            cr += w * sa.y; cg += w * sa.z; cb += w * sa.w;
             kept++;
             if (T < A.T_thresh) {
                 finalize(c_tag);

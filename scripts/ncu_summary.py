@@ -3,7 +3,7 @@ import csv
 import subprocess
 import sys
 
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__t_sector_hit_rate.pct", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active",
@@ -21,6 +21,7 @@ for rep in sys.argv[1:]:
             if k in hdr:
                 i = hdr.index(k)
                 print(f"  {k:75s} {r[i]:>18s} {units[i]}")
-        st = {h: r[i] for i, h in enumerate(hdr) if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct")}
-        top = sorted(((float(v or 0), h.replace("smsp__average_warp_latency_issue_stalled_", "").replace("smsp__average_warps_issue_stalled_", "").replace("_per_warp_active.pct", "")) for h, v in st.items()), reverse=True)[:6]
-        print("  top stall reasons (% of warp-active):", ", ".join(f"{n} {v:.0f}" for v, n in top))
+        st = [(float(r[i].replace(",", "") or 0), h.replace("smsp__pcsamp_warps_issue_stalled_", "")) for i, h in enumerate(hdr)
+              if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued")]
+        tot = sum(v for v, _ in st) or 1.0
+        print("  stall reasons (% of pc samples):", ", ".join(f"{n} {100 * v / tot:.0f}" for v, n in sorted(st, reverse=True)[:7]))
