@@ -110,11 +110,13 @@ typedef struct {
 int pn_field_forward(const pn_field_t *field_host, const float *xyzs, const float *dirs, uint32_t M, float *sigmas,
                      float *rgbs, int mode, void *stream);
 
-/* nerf/renderer.py:755-907 rund_cuda as a device-resident frame: near/far, IP bbox + grid, then a
- * persistent per-ray march->inverse-warp->encode->MLP->composite kernel (no host sync).  Outputs
- * image [N,3], depth [N], depth_0 [N], weights_sum [N] as rund_cuda returns them.  ray_ids: optional
- * [N] i32 list of pixel indices this rank renders (NULL = 0..N-1 of rays_o/rays_d).
- * stats (optional, device int64[4]): [0] kept samples, [1] rays that hit the aabb. */
+/* nerf/renderer.py:755-907 rund_cuda as a device-resident frame (enqueue-only, no host sync): near/far, IP bbox +
+ * grid, then the render itself.  mode 3 (product path) = wavefront: per pass a march kernel (lattice march +
+ * inverse warp, samples appended to a compact list), the field kernel (hash-grid gather + tcgen05 MLP over 128-row
+ * tiles) and a per-ray compositor; modes 0-2 = single fused persistent kernels (0: tcgen05 MLP, 1: fp32 SIMT MLP,
+ * 2: one lane per ray).  Outputs image [N,3], depth [N], depth_0 [N], weights_sum [N] as rund_cuda returns them.
+ * stats (optional, device int64[4]): [0] composited samples, [1] rays that hit the aabb, [2] field evaluations,
+ * [3] rows the field kernel processed (mode 3; samples + slab padding). */
 typedef struct {
     const float *p_def, *p_ori, *F_IP, *dF_IP; int n_vtx; float IP_dx;
     const uint8_t *density_bitfield; float bound; uint32_t cascade; uint32_t grid_size;
@@ -127,6 +129,9 @@ int pn_render_deformed(const pn_field_t *field_host, const pn_deform_t *deform_h
 /* Optional profiling hook: two cudaEvent_t (as void*) that pn_render_deformed records on its stream right
  * around the persistent render kernel (NULL, NULL disables).  Used by bench.py for the roofline line. */
 int pn_set_profile_events(void *start_event, void *stop_event);
+/* Same for mode 3: events[2k], events[2k+1] (cudaEvent_t) bracket the k-th field-kernel launch of a frame, k < n/2;
+ * the pair of pn_set_profile_events then brackets all passes.  (NULL, 0) disables.  The array must stay alive. */
+int pn_set_profile_event_list(void **events, int n);
 /* bytes of scratch pn_render_deformed needs for N rays, n_vtx IPs, scene bound and IP-grid cell size hgs */
 uint64_t pn_render_workspace_bytes(uint32_t N, int n_vtx, float bound, float hgs);
 

@@ -348,8 +348,19 @@ __global__ void __launch_bounds__(128, 3) field_forward_kernel(const pn_field_t 
 }
 
 struct WorkspaceLayout {
-    size_t geom, queue, nears, fars, active, pig_cnt, pig_bgn, pig_fill, pig_idx, ip_pos, ip_rec, total;
+    size_t geom, queue, nears, fars, active, pig_cnt, pig_bgn, pig_fill, pig_idx, ip_pos, ip_rec;
+    size_t ctl, alive0, alive1, rs_march, rs_comp, link, xyzdt, meta, out, slab_next, counters;   // wavefront mode
+    int cap;
+    size_t total;
 };
+
+// rows of the per-pass sample list: 24 per ray (a chair frame keeps ~11 per ray over all passes), whole slabs
+int wave_capacity(uint32_t N) {
+    long long c = 24ll * (long long)N;
+    if (c < (1ll << 20)) c = 1ll << 20;
+    if (c > (32ll << 20)) c = 32ll << 20;
+    return (int)(c / 256 * 256);
+}
 
 WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
     WorkspaceLayout w;
@@ -366,6 +377,13 @@ WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
     w.pig_idx = take(sizeof(int) * (size_t)n_vtx);
     w.ip_pos = take(sizeof(float4) * (size_t)n_vtx);
     w.ip_rec = take(sizeof(float) * 16 * (size_t)n_vtx);
+    w.cap = wave_capacity(N);
+    w.ctl = take(16 * 16);
+    w.counters = take(64);
+    w.alive0 = take(sizeof(int) * N); w.alive1 = take(sizeof(int) * N);
+    w.rs_march = take(16 * (size_t)N); w.rs_comp = take(32 * (size_t)N); w.link = take(8 * (size_t)N);
+    w.xyzdt = take(16 * (size_t)w.cap); w.meta = take(8 * (size_t)w.cap); w.out = take(16 * (size_t)w.cap);
+    w.slab_next = take(sizeof(int) * (size_t)(w.cap / 256));
     w.total = o;
     return w;
 }
@@ -386,7 +404,7 @@ int set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
-#include "render_warp.cuh"
+#include "render_wave.cuh"
 
 int pn_field_forward_tc(const pn_field_t *f, const float *xyzs, const float *dirs, uint32_t M, float *sigmas, float *rgbs,
                         cudaStream_t st);
@@ -450,6 +468,13 @@ extern "C" int pn_field_forward(const pn_field_t *f, const float *xyzs, const fl
 }
 
 static cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+static cudaEvent_t *g_prof_list = nullptr;   // wavefront mode: events [2k], [2k+1] bracket the k-th field-kernel launch of a frame
+static int g_prof_n = 0;
+extern "C" int pn_set_profile_event_list(void **events, int n) {
+    g_prof_list = (cudaEvent_t *)events;
+    g_prof_n = events ? n : 0;
+    return PN_OK;
+}
 extern "C" int pn_set_profile_events(void *start, void *stop) {
     g_prof_start = (cudaEvent_t)start;
     g_prof_stop = (cudaEvent_t)stop;
@@ -465,7 +490,7 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
                                   void *workspace, uint64_t workspace_bytes, long long *stats, int mode, void *stream) {
     PN_REQUIRE(f && d && rays_o && rays_d && image && depth && depth_0 && weights_sum && workspace, "null pointer");
     PN_REQUIRE(f->L == pn::kLevels, "fused field expects the 16-level C=2 D=3 grid of nerf/network.py");
-    PN_REQUIRE(mode >= 0 && mode <= 2, "render mode: 0 = warp-cooperative + tcgen05 MLP (default), 1 = warp-cooperative fp32 SIMT, 2 = one lane per ray");
+    PN_REQUIRE(mode >= 0 && mode <= 3, "render mode: 0 = fused warp-cooperative + tcgen05 MLP, 1 = same with the fp32 SIMT MLP, 2 = one lane per ray, 3 = wavefront (march / field / composite kernels)");
     PN_REQUIRE(d->n_vtx > 0 && d->num_seek_IP >= 1 && d->num_seek_IP <= 3, "need IPs and num_seek_IP in 1..3");
     PN_REQUIRE(d->cascade >= 1 && d->cascade <= 8 && d->grid_size == 128, "cascade/grid_size out of range");
     if (N == 0) return PN_OK;
@@ -503,6 +528,48 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
     A.density_scale = d->density_scale; A.T_thresh = d->T_thresh; A.bg = d->bg_color; A.max_samples = d->max_steps;
 
     const uint32_t blocks = (uint32_t)pn_sm_count_cached() * 3u;
+    if (mode == 3) {
+        float4 *ip_pos = (float4 *)(base + w.ip_pos);
+        float *ip_rec = (float *)(base + w.ip_rec);
+        ip_pack_kernel<<<div_up(d->n_vtx, 256), 256, 0, st>>>(d->p_def, d->p_ori, d->F_IP, idx, d->n_vtx, geom->res, max_cells, bgn, ip_pos, ip_rec);
+        PN_LAUNCH_CHECK("ip_pack_kernel");
+        IpPack P{ip_pos, ip_rec, bgn};
+        WaveArgs Wv{};
+        Wv.ctl = (PassCtl *)(base + w.ctl); Wv.counters = (long long *)(base + w.counters);
+        Wv.alive[0] = (int *)(base + w.alive0); Wv.alive[1] = (int *)(base + w.alive1);
+        Wv.rs_march = (float4 *)(base + w.rs_march); Wv.rs_comp = (float4 *)(base + w.rs_comp); Wv.link = (int2 *)(base + w.link);
+        Wv.xyzdt = (float4 *)(base + w.xyzdt); Wv.meta = (int2 *)(base + w.meta); Wv.out = (float4 *)(base + w.out);
+        Wv.slab_next = (int *)(base + w.slab_next); Wv.cap = w.cap;
+        PN_CUDA(cudaMemsetAsync(base + w.ctl, 0, 16 * 16 + 256, st));       // ctl + counters (adjacent, 256-byte aligned blocks)
+        const size_t smem = sizeof(WaveFieldSmem) + 128;
+        if (int rc = set_smem(wave_field_kernel, smem)) return rc;
+        const uint32_t sms = (uint32_t)pn_sm_count_cached();
+        // pass caps 64, 128, ... until the per-ray cap is covered; one spare pass absorbs the <32-sample overshoot per pass
+        int n_pass = 0, covered = 0;
+        for (int cap_p = 64; covered < (int)d->max_steps && n_pass < kMaxPass - 1; cap_p *= 2) { covered += cap_p; n_pass++; }
+        n_pass++;
+        int cap_p = 64, fk = 0;
+        if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
+        for (int p = 0; p < n_pass; p++, cap_p *= 2) {
+            switch (d->num_seek_IP) {
+                case 1: wave_march_kernel<1><<<sms * 2, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
+                case 2: wave_march_kernel<2><<<sms * 2, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
+                default: wave_march_kernel<3><<<sms * 2, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
+            }
+            if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk], st));
+            wave_field_kernel<<<sms, kWaveGroups * 128, smem, st>>>(A, Wv, p);
+            if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk + 1], st));
+            fk++;
+            wave_composite_kernel<<<div_up(N, 256u), 256, 0, st>>>(A, Wv, p, p == n_pass - 1);
+        }
+        PN_LAUNCH_CHECK("wavefront passes");
+        if (g_prof_stop) PN_CUDA(cudaEventRecord(g_prof_stop, st));
+        if (stats) {
+            wave_stats_kernel<<<1, 1, 0, st>>>(queue, Wv, n_pass, stats);
+            PN_LAUNCH_CHECK("wave_stats_kernel");
+        }
+        return PN_OK;
+    }
     if (mode == 0 || mode == 1) {
         float4 *ip_pos = (float4 *)(base + w.ip_pos);
         float *ip_rec = (float *)(base + w.ip_rec);

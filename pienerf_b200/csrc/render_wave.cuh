@@ -1,0 +1,295 @@
+// Wavefront deformed-space renderer (render mode 3).  Included by render_fused.cu.
+//
+// The frame is rendered in a few device-resident passes; every pass is three launches on one stream, no host sync:
+//   wave_march_kernel      one warp = one ray at a time, 32 lanes = 32 consecutive lattice points (same exact
+//                          lattice/ballot replay as render_warp.cuh), inverse warp through the quadratic GMLS field,
+//                          occupancy test; kept samples are appended to a compact global sample list (slabs of 256
+//                          rows handed out by one atomic each) — up to `pass_cap` samples per ray per pass;
+//   wave_field_kernel      THE hash-lookup + MLP pass: 128-row tiles of the sample list, 16-level hash-grid gather
+//                          straight into the bf16 hi/lo activation tile in shared memory, 5-layer MLP on tcgen05
+//                          with TMEM accumulators (field_tc.cuh), writes (alpha, r, g, b) per sample;
+//   wave_composite_kernel  one thread = one ray: the reference's sequential front-to-back recurrence over the ray's
+//                          samples of this pass (raymarching.cu:862-913), early termination, survivors are compacted
+//                          into the next pass's ray list.
+// pass_cap doubles every pass (64, 128, ...), so a saturating ray wastes at most ~64 field evaluations (the reference's
+// wavefront loop has the same property with n_step <= 8 per iteration) while fog rays need only a handful of passes.
+// Why three kernels instead of one fused one: marching (divergent neighbour search, ~100 registers), the field
+// (gather-bound, 16-20 warps per SM of tensor-core tiles) and compositing (a scalar recurrence) want different
+// occupancies; fused they ran at 12 warps / SM and 34 % issue utilisation.  The extra global traffic is 84 B / sample
+// (~0.6 GB per chair frame, < 0.1 ms of HBM time).
+#pragma once
+#include "render_warp.cuh"
+
+namespace {
+
+constexpr int kSlab = 256;       // sample rows per slab (two field tiles)
+constexpr int kMaxPass = 8;
+#ifndef PN_WAVE_GROUPS
+#define PN_WAVE_GROUPS 4         // 128-row tile groups per field CTA
+#endif
+constexpr int kWaveGroups = PN_WAVE_GROUPS;
+
+struct PassCtl { int n_alive; int next; int n_reserved; int pad; };
+
+struct WaveArgs {
+    PassCtl *ctl;          // [kMaxPass + 1], zeroed per frame
+    int *alive[2];         // ray lists written by the compositor for the next pass
+    float4 *rs_march;      // [N] t_next, skip_until, bitcast emitted, finished flag
+    float4 *rs_comp;       // [2N] ws dep cr cg | cb tdepth last_t -
+    int2 *link;            // [N] first sample row of this pass, number of samples
+    float4 *xyzdt;         // [cap] rest-space position + dt
+    int2 *meta;            // [cap] (ray or -1 for a padding row, bitcast t_after)
+    float4 *out;           // [cap] alpha r g b
+    int *slab_next;        // [cap / kSlab] row at which a warp's sample stream continues after this slab
+    long long *counters;   // [0] composited samples, [1] emitted samples
+    int cap;               // rows available per pass
+};
+
+// --------------------------------------------------------------------------------------------- march
+template <int KMAX>
+__global__ void __launch_bounds__(256, 2) wave_march_kernel(const RenderArgs A, const IpPack P, const WaveArgs Wv, int pass, int pass_cap) {
+    __shared__ unsigned char rankA[27], rankB[27];
+    if (threadIdx.x < 27) {
+        const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
+        int ra = 0, rb = 0;
+        for (int q = 0; q < 26; q++) {
+            if (pn::kNeigh[q][0] == dx && pn::kNeigh[q][1] == dy && pn::kNeigh[q][2] == dz) ra = q + 1;
+            if (pn::kNeigh[q][0] == dz && pn::kNeigh[q][1] == dy && pn::kNeigh[q][2] == dx) rb = q + 1;
+        }
+        rankA[threadIdx.x] = (unsigned char)ra; rankB[threadIdx.x] = (unsigned char)rb;
+    }
+    pn::BendCfg bc = A.bend;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { bc.bbmin[i] = A.geom->bbmin[i]; bc.bbmax[i] = A.geom->bbmax[i]; bc.hi[i] = A.geom->hi[i]; bc.res[i] = A.geom->res[i]; }
+    __syncthreads();
+    const pn::MarchCfg m = A.march;
+    PassCtl *ctl = Wv.ctl + pass;
+    const int n_alive = pass == 0 ? A.queue->n_active : ctl->n_alive;
+    const int *alive = pass == 0 ? A.active : Wv.alive[(pass - 1) & 1];
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    int cur = 0, end = 0;                                              // this warp's write cursor inside its current slab
+    long long emitted_total = 0;
+
+    while (true) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&ctl->next, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= n_alive) break;
+        const int ray = alive[slot];
+        const float ox = A.rays_o[3 * ray], oy = A.rays_o[3 * ray + 1], oz = A.rays_o[3 * ray + 2];
+        const float dx = A.rays_d[3 * ray], dy = A.rays_d[3 * ray + 1], dz = A.rays_d[3 * ray + 2];
+        const float rdx = 1 / dx, rdy = 1 / dy, rdz = 1 / dz;
+        const float near = A.nears[ray], far = A.fars[ray];
+        float t_next = near, skip_until = 0.f;
+        int emitted = 0;
+        if (pass > 0) {
+            const float4 s = Wv.rs_march[ray];
+            t_next = s.x; skip_until = s.y; emitted = __float_as_int(s.z);
+        }
+        int pass_emitted = 0, first_idx = -1;
+        bool finished = false;
+        while (true) {
+            // lane i evaluates lattice point t_i = f^i(t_next)
+            float t = t_next;
+            for (int i = 0; i < lane; i++) t += pn::step_size(m, t);
+            const float dt = pn::step_size(m, t);
+            const float t_after = t + dt;
+            const bool valid = t < far;
+            const bool need = valid && t >= skip_until;
+            float x = 0, y = 0, z = 0, tt = 0;
+            bool emit = false;
+            if (need) {
+                pn::deformed_sample(bc, ox, oy, oz, dx, dy, dz, t, x, y, z);
+                const bool found = bend_sample_packed<KMAX>(P, bc, rankA, rankB, x, y, z);
+                const bool occ = pn::occupancy_and_exit(m, x, y, z, t, dt, dx, dy, dz, rdx, rdy, rdz, tt);
+                emit = occ && found;
+            }
+            const uint32_t valid_m = __ballot_sync(0xffffffffu, valid);
+            const uint32_t need_m = __ballot_sync(0xffffffffu, need);
+            const uint32_t emit_m = __ballot_sync(0xffffffffu, emit);
+            // replay the reference's visit order over this chunk (raymarching.cu:1385-1432)
+            uint32_t take = 0;
+            float carry = skip_until;
+            int i = need_m ? __ffs(need_m) - 1 : (valid_m == 0xffffffffu ? 32 : __popc(valid_m));
+            while (i < 32 && ((valid_m >> i) & 1u)) {
+                if ((emit_m >> i) & 1u) {
+                    const uint32_t inv = ~(emit_m >> i);
+                    const int run = inv ? __ffs(inv) - 1 : 32;
+                    take |= ((run >= 32 ? 0xffffffffu : ((1u << run) - 1u)) << i);
+                    i += run;
+                    carry = 0.f;
+                } else {
+                    const float tti = __shfl_sync(0xffffffffu, tt, i);
+                    const uint32_t ge = __ballot_sync(0xffffffffu, valid && t >= tti) & ~((2u << i) - 1u);
+                    const uint32_t inval = ~valid_m & ~((2u << i) - 1u);
+                    if (ge) { i = __ffs(ge) - 1; carry = 0.f; }
+                    else if (inval) { i = __ffs(inval) - 1; }
+                    else { i = 32; carry = tti; }
+                }
+            }
+            const bool ray_left = i < 32;
+            int ntake = __popc(take);
+            if (emitted + ntake > (int)A.max_samples) {                   // per-ray sample cap
+                int keep = (int)A.max_samples - emitted;
+                uint32_t tk = take, out = 0;
+                while (keep-- > 0 && tk) { const uint32_t lowest = tk & (0u - tk); out |= lowest; tk ^= lowest; }
+                take = out; ntake = __popc(take);
+            }
+            // rows for the kept samples of this chunk
+            const int room = end - cur;
+            int nb = 0;
+            if (ntake > room) {
+                if (lane == 0) nb = atomicAdd(&ctl->n_reserved, kSlab);
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+                if (nb + kSlab > Wv.cap) break;                             // sample list full: this chunk is redone next pass
+                if (lane == 0 && end > 0) Wv.slab_next[(end - 1) / kSlab] = nb;
+            }
+            const int rank = __popc(take & lt_mask);
+            const int idx = rank < room ? cur + rank : nb + (rank - room);
+            if ((take >> lane) & 1u) {
+                Wv.xyzdt[idx] = make_float4(x, y, z, dt);
+                Wv.meta[idx] = make_int2(ray, __float_as_int(t_after));
+            }
+            if (ntake > 0 && first_idx < 0) first_idx = room > 0 ? cur : nb;
+            if (ntake > room) { cur = nb + (ntake - room); end = nb + kSlab; }
+            else cur += ntake;
+            emitted += ntake; pass_emitted += ntake;
+            if (ray_left || emitted >= (int)A.max_samples) { finished = true; break; }
+            t_next = __shfl_sync(0xffffffffu, t_after, 31);
+            skip_until = carry;
+            if (pass_emitted >= pass_cap) break;
+        }
+        if (lane == 0) {
+            Wv.rs_march[ray] = make_float4(t_next, skip_until, __int_as_float(emitted), finished ? 1.f : 0.f);
+            Wv.link[ray] = make_int2(first_idx, pass_emitted);
+        }
+        emitted_total += pass_emitted;
+    }
+    for (int i = cur + lane; i < end; i += 32) Wv.meta[i] = make_int2(-1, 0);   // padding rows of the last slab
+    if (lane == 0 && emitted_total) atomicAdd((unsigned long long *)&Wv.counters[1], (unsigned long long)emitted_total);
+}
+
+// --------------------------------------------------------------------------------------------- field
+struct __align__(128) WaveFieldSmem {
+    pn::tc::Weights w;
+    pn::tc::TileSmem tile[kWaveGroups];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWaveGroups * 128, 1) wave_field_kernel(const RenderArgs A, const WaveArgs Wv, int pass) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    WaveFieldSmem &S = *reinterpret_cast<WaveFieldSmem *>(smem_raw);
+    const int group = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0), row = threadIdx.x & 127;
+    const int n_rows = min(Wv.ctl[pass].n_reserved, Wv.cap);
+    if (n_rows == 0) return;
+    pn::tc::TileSmem &T = S.tile[group];
+    pn::tc::weights_fill(S.w, A.field);
+    if (row == 0) pn::tc::mbar_init(&T.bar, 1);
+    pn::tc::fence_barrier_init();
+    if (threadIdx.x < 32) pn::tc::tmem_alloc(&S.tmem_base, 512);
+    pn::tc::fence_async_smem();
+    pn::tc::tc_fence_before();
+    __syncthreads();
+    pn::tc::tc_fence_after();
+    if (row == 0) T.tmem = S.tmem_base + group * pn::tc::kTmemCols;
+    pn::tc::group_sync(group);
+    const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
+    uint32_t phase = 0;
+    const int n_tiles = n_rows / 128;                                   // slabs are whole tiles
+    for (int tile = blockIdx.x * kWaveGroups + group; tile < n_tiles; tile += gridDim.x * kWaveGroups) {
+        const int i = tile * 128 + row;
+        const int2 mt = Wv.meta[i];
+        const bool valid = mt.x >= 0;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        float dx = 0, dy = 0, dz = 1;
+        if (valid) {
+            s = Wv.xyzdt[i];
+            dx = __ldg(A.rays_d + 3 * mt.x); dy = __ldg(A.rays_d + 3 * mt.x + 1); dz = __ldg(A.rays_d + 3 * mt.x + 2);
+        }
+        float sh[16];
+        pn::sh_eval<4>(dx, dy, dz, sh);
+        pn::tc::encode_to_tile(T, S.w, table, A.field.bound, row, valid, s.x, s.y, s.z);
+        float sigma, r, g, b;
+        pn::tc::mlp_tile(T, S.w, group, row, sh, phase, sigma, r, g, b);
+        if (valid) {
+            sigma = A.density_scale * sigma;
+            Wv.out[i] = make_float4(1.0f - __expf(-sigma * s.w), r, g, b);
+        }
+    }
+    pn::tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) pn::tc::tmem_dealloc(S.tmem_base, 512);
+}
+
+// --------------------------------------------------------------------------------------------- composite
+__global__ void __launch_bounds__(256) wave_composite_kernel(const RenderArgs A, const WaveArgs Wv, int pass, int last_pass) {
+    const int n_alive = pass == 0 ? A.queue->n_active : Wv.ctl[pass].n_alive;
+    const int *alive = pass == 0 ? A.active : Wv.alive[(pass - 1) & 1];
+    int *alive_out = Wv.alive[pass & 1];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool survive = false;
+    int ray = -1;
+    long long kept = 0;
+    if (i < n_alive) {
+        ray = alive[i];
+        const int2 lk = Wv.link[ray];
+        const bool finished = Wv.rs_march[ray].w != 0.f;
+        const float near = A.nears[ray], far = A.fars[ray];
+        float ws = 0, dep = 0, cr = 0, cg = 0, cb = 0, tdepth = near, last_t = near;
+        if (pass > 0) {
+            const float4 a = Wv.rs_comp[2 * ray], b = Wv.rs_comp[2 * ray + 1];
+            ws = a.x; dep = a.y; cr = a.z; cg = a.w; cb = b.x; tdepth = b.y; last_t = b.z;
+        }
+        bool terminated = false;
+        int idx = lk.x;
+        for (int s = 0; s < lk.y; s++) {
+            if (s > 0) {
+                idx++;
+                if ((idx & (kSlab - 1)) == 0) idx = Wv.slab_next[idx / kSlab - 1];
+            }
+            const float4 o = Wv.out[idx];
+            const float ta = __int_as_float(Wv.meta[idx].y);
+            const float T = 1 - ws;                                         // raymarching.cu:890-906
+            const float w = o.x * T;
+            ws += w;
+            tdepth += ta - last_t;
+            last_t = ta;
+            dep += w * tdepth;
+            cr += w * o.y; cg += w * o.z; cb += w * o.w;
+            kept++;
+            if (T < A.T_thresh) { terminated = true; break; }
+        }
+        if (terminated || finished || last_pass) {
+            A.image[3 * ray] = cr + (1 - ws) * A.bg; A.image[3 * ray + 1] = cg + (1 - ws) * A.bg; A.image[3 * ray + 2] = cb + (1 - ws) * A.bg;
+            A.depth0[ray] = dep;
+            A.depth[ray] = fmaxf(dep - near, 0.f) / (far - near);
+            A.wsum[ray] = ws;
+        } else {
+            survive = true;
+            Wv.rs_comp[2 * ray] = make_float4(ws, dep, cr, cg);
+            Wv.rs_comp[2 * ray + 1] = make_float4(cb, tdepth, last_t, 0.f);
+        }
+    }
+    const uint32_t sm = __ballot_sync(0xffffffffu, survive);
+    const int lane = threadIdx.x & 31;
+    if (sm) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&Wv.ctl[pass + 1].n_alive, __popc(sm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (survive) alive_out[base + __popc(sm & ((1u << lane) - 1))] = ray;
+    }
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+    if (lane == 0 && kept) atomicAdd((unsigned long long *)&Wv.counters[0], (unsigned long long)kept);
+}
+
+__global__ void wave_stats_kernel(const FrameQueue *q, const WaveArgs Wv, int n_pass, long long *stats) {
+    stats[0] = Wv.counters[0];   // composited samples
+    stats[1] = q->n_active;      // rays that hit the IP box
+    stats[2] = Wv.counters[1];   // field evaluations (>= stats[0]: samples marched past an early termination)
+    long long rows = 0;
+    for (int p = 0; p < n_pass; p++) rows += min(Wv.ctl[p].n_reserved, Wv.cap);
+    stats[3] = rows;             // rows the field kernel processed (samples + slab padding)
+}
+
+}  // namespace

@@ -22,6 +22,11 @@ from .gridencoder import GridEncoder
 from .shencoder import SHEncoder
 
 
+import os
+
+DEFAULT_RENDER_MODE = int(os.environ.get("PN_RENDER_MODE", "3"))   # 3 wavefront (product path), 0 fused tcgen05 kernel (see pn_render_deformed)
+
+
 class NeRFNetwork(nn.Module):
     def __init__(self, encoding="hashgrid", encoding_dir="sphere_harmonics", num_layers=2, hidden_dim=64, geo_feat_dim=15,
                  num_layers_color=3, hidden_dim_color=64, bound=1, cuda_ray=True, density_scale=1, min_near=0.2,
@@ -206,9 +211,11 @@ class NeRFNetwork(nn.Module):
     # ------------------------------------------------------------------ fused frame (product path)
     @torch.no_grad()
     def render_deformed(self, rays_o, rays_d, staged=False, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024, T_thresh=1e-2,
-                        mode=0, out=None, **kwargs):
+                        mode=None, out=None, **kwargs):
         """renderer.py:587-599 -> rund_cuda semantics in one device-resident call.  Returns the same dict.
         mode 0: warp-cooperative march + tcgen05 MLP (default); 1: same with the fp32 SIMT MLP; 2: one lane per ray."""
+        if mode is None:
+            mode = DEFAULT_RENDER_MODE
         if perturb:
             raise NotImplementedError("perturb is only used with spp>1 accumulation, which the sim GUI never does (gui.py:620-622)")
         prefix = rays_o.shape[:-1]

@@ -44,10 +44,11 @@ def test_frame_vs_oracle(amp, K):
     fused = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in fused.items()}                       # mode 0: tcgen05 MLP
     simt = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in model.render_deformed(ro_, rd_, mode=1, **kw, **opt).items()}
     lane = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in model.render_deformed(ro_, rd_, mode=2, **kw, **opt).items()}
+    wave = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in model.render_deformed(ro_, rd_, mode=3, **kw, **opt).items()}
     torch.cuda.synchronize()
     hit = want["weights_sum"] > 0
     assert hit.sum() > 100 and want["n_samples"] > 1000
-    for name, got in (("loop", loop), ("fused-tc", fused), ("fused-simt", simt), ("fused-lane", lane)):
+    for name, got in (("loop", loop), ("fused-tc", fused), ("fused-simt", simt), ("fused-lane", lane), ("wavefront", wave)):
         img = got["image"][0].cpu().numpy(); ws = got["weights_sum"].cpu().numpy(); d0 = got["depth_0"][0].cpu().numpy()
         # knife-edge occupancy flips (fp32 FMA contraction) can move a handful of silhouette pixels
         assert _bad_fraction(img, want["image"], 1e-3) <= 0.01, (name, _bad_fraction(img, want["image"], 1e-3))
@@ -60,6 +61,10 @@ def test_frame_vs_oracle(amp, K):
     a = loop["image"][0].cpu().numpy(); b = simt["image"][0].cpu().numpy(); c = fused["image"][0].cpu().numpy()
     assert _bad_fraction(a, b, 1e-4) <= 0.002
     assert _bad_fraction(b, c, 2e-4) <= 0.002                                       # bf16x3 tensor-core MLP vs fp32 SIMT MLP
+    # wavefront and fused kernels: same per-ray sample sequence, same tensor-core MLP, same compositing order
+    for k in ("image", "depth", "depth_0", "weights_sum"):
+        assert torch.equal(torch.nan_to_num(wave[k], nan=-7.0), torch.nan_to_num(fused[k], nan=-7.0)), k   # depth is NaN for a miss, as in the reference
+    assert int(wave["stats"][0]) == int(fused["stats"][0]) and int(wave["stats"][1]) == int(fused["stats"][1])
     assert abs(int(simt["stats"][0]) - loop["n_samples"]) <= 0.002 * loop["n_samples"] + 2
     assert abs(loop["n_samples"] - want["n_samples"]) <= 0.01 * want["n_samples"]
 
@@ -98,7 +103,8 @@ def test_cut_and_dt_gamma_config():
     model.density_bitfield.copy_(_gpu(bits))
     model.p_ori, model.p_def, model.IP_F, model.IP_dF, model.IP_dx = _gpu(p_ori), _gpu(p_def), _gpu(F), _gpu(dF), 0.0525
     opt = dict(max_iter_num=1, hash_grid_size=0.06, bound=2.0, cut=True, cut_bounds=cb, num_seek_IP=1)
-    for fn in (model.rund_cuda, model.render_deformed):
+    import functools
+    for fn in (model.rund_cuda, functools.partial(model.render_deformed, mode=0), functools.partial(model.render_deformed, mode=3)):
         got = fn(_gpu(rays_o)[None], _gpu(rays_d)[None], **kw, **opt)["image"][0].cpu().numpy()
         assert _bad_fraction(got, want["image"], 1e-3) <= 0.02 and psnr(got, want["image"]) > 40
 
