@@ -280,22 +280,27 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
 }
 
 // Encode one sample and store its 32 features (k = 2*level, 2*level+1; chunks 0..3) for sigma_net[0].  Zero row for
-// invalid samples.  One level per rolled iteration (small code), each level writes its bf16x2 hi and lo words directly.
+// invalid samples.  Four levels (= one 16-byte k-chunk of the hi and of the lo image) per rolled iteration: 32 gathers
+// in flight per thread, and one conflict-free 128-bit store per image instead of four 4-byte stores at a 16-byte
+// stride (which serialised 4-way on the shared-memory banks).
 __device__ __forceinline__ void encode_to_tile(TileSmem &t, const Weights &w, const float2 *__restrict__ table, float bound, int row,
                                                bool valid, float x, float y, float z) {
     const float inv = 1.0f / (2 * bound);
     const float u = (x + bound) * inv, vv = (y + bound) * inv, ww = (z + bound) * inv;
     const bool in = valid && !(u < 0 || u > 1 || vv < 0 || vv > 1 || ww < 0 || ww > 1);
     char *hi = reinterpret_cast<char *>(t.a[0]) + row * 16, *lo = reinterpret_cast<char *>(t.a[1]) + row * 16;
-#pragma unroll 2
-    for (int l = 0; l < 16; l++) {
-        float2 e = make_float2(0.f, 0.f);
-        if (in) e = lookup3_c2(table + w.level_off[l], w.geo[l], u, vv, ww, 0);
-        uint32_t hw, lw;
-        split_pair(e.x, e.y, hw, lw);
-        const int off = (l >> 2) * 2048 + (l & 3) * 4;
-        *reinterpret_cast<uint32_t *>(hi + off) = hw;
-        *reinterpret_cast<uint32_t *>(lo + off) = lw;
+#pragma unroll 1
+    for (int c4 = 0; c4 < 4; c4++) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int l = 4 * c4 + j;
+            float2 e = make_float2(0.f, 0.f);
+            if (in) e = lookup3_c2(table + w.level_off[l], w.geo[l], u, vv, ww, 0);
+            split_pair(e.x, e.y, hw[j], lw[j]);
+        }
+        *reinterpret_cast<uint4 *>(hi + c4 * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4 *>(lo + c4 * 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
 }
 

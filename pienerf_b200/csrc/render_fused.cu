@@ -383,7 +383,7 @@ WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
     w.alive0 = take(sizeof(int) * N); w.alive1 = take(sizeof(int) * N);
     w.rs_march = take(16 * (size_t)N); w.rs_comp = take(32 * (size_t)N); w.link = take(8 * (size_t)N);
     w.xyzdt = take(16 * (size_t)w.cap); w.meta = take(8 * (size_t)w.cap); w.out = take(16 * (size_t)w.cap);
-    w.slab_next = take(sizeof(int) * (size_t)(w.cap / 256));
+    w.slab_next = take(sizeof(int) * (size_t)(w.cap / 128));
     w.total = o;
     return w;
 }

@@ -22,7 +22,10 @@
 
 namespace {
 
-constexpr int kSlab = 256;       // sample rows per slab (two field tiles)
+#ifndef PN_WAVE_SLAB
+#define PN_WAVE_SLAB 128
+#endif
+constexpr int kSlab = PN_WAVE_SLAB;   // sample rows per slab (a whole number of 128-row field tiles)
 constexpr int kMaxPass = 8;
 #ifndef PN_WAVE_GROUPS
 #define PN_WAVE_GROUPS 4         // 128-row tile groups per field CTA
