@@ -95,7 +95,8 @@ def run_ours(args):
     calib = None
     if world > 1 and not args.equal_tiles:
         calib = drv.calibrate(host_pose, intr)                                # rank 0 also runs the simulator: fewer tiles
-    launches = {"n": 0}
+    from pienerf_b200 import _lib
+    n_pass = int(_lib.lib.pn_render_pass_count(int(opt.max_steps)))
 
     def frame(e2e, prof=None):
         """One GUI frame through the public multi-GPU frame API.  e2e=True adds the host<->device traffic: rays are
@@ -111,10 +112,14 @@ def run_ours(args):
 
     def timed(K, e2e, with_prof=False):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        pv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)] if with_prof else None
+        # per frame: (start, stop) around all render passes + one event pair per field-kernel launch (one per pass)
+        pv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+               [torch.cuda.Event(enable_timing=True) for _ in range(2 * n_pass)]) for _ in range(K)] if with_prof else None
         if pv:
-            for a, b in pv:
+            for a, b, lst in pv:
                 a.record(); b.record()                                        # instantiate the handles
+                for e in lst:
+                    e.record()
         samples0 = []
         sync_all()
         t0 = time.perf_counter()
@@ -134,8 +139,12 @@ def run_ours(args):
             t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total_ms = float(t.item())
-        kms = [a.elapsed_time(b) for a, b in pv] if pv else None
-        samples = [int(s[0]) for s in samples0]
+        kms = None
+        if pv:
+            kms = {"render": [a.elapsed_time(b) for a, b, _ in pv],
+                   "field": [sum(lst[2 * k].elapsed_time(lst[2 * k + 1]) for k in range(n_pass)) for _, _, lst in pv],
+                   "field_launch": [lst[0].elapsed_time(lst[1]) for _, _, lst in pv]}
+        samples = [[int(v) for v in s[:4]] for s in samples0]
         return total_ms, wall, kms, samples
 
     for _ in range(max(args.warmup, 3)):
@@ -192,23 +201,27 @@ def run_ours(args):
 
     K = args.steps
     fps = K / (total_ms * 1e-3)
-    kernel_ms = float(np.mean(kms))
-    samp = float(np.mean(samples))
-    achieved = samp * ALGO_BYTES_PER_SAMPLE_FUSED / (kernel_ms * 1e-3) / 1e9
+    render_ms = float(np.mean(kms["render"])); field_ms = float(np.mean(kms["field"])); field0_ms = float(np.mean(kms["field_launch"]))
+    st = np.mean(np.asarray(samples, dtype=np.float64), axis=0)           # composited, rays hit, field evaluations, field rows
+    samp, evaluated, rows = float(st[0]), float(st[2]), float(st[3])
+    achieved = evaluated * ALGO_BYTES_PER_SAMPLE_FUSED / (field_ms * 1e-3) / 1e9
     line = {
         "metric": "simulated+rendered frames/s at 800x800", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 render / f64 sim",
         "data": "synthetic", "impl": "ours",
         "config": {"workload": f"{args.config}: {sim.n_ip}-IP Q-GMLS body ({sim.n_k} kernels, sim_iters {sim.iters}) + {W}x{H} deformed render, "
                                f"random-init 16-level hash grid + 64-wide MLP, density_scale {args.density_scale}, num_seek_IP {opt.num_seek_IP}",
-                   "rays": N, "n_ip": sim.n_ip, "kept_samples_per_frame": samp, "parallelism": f"16x16 ray tiles over {world} GPU(s), simulator on rank 0" + (f", sim-aware tile weights {[round(x, 4) for x in calib['weights']]}" if calib else ""),
+                   "rays": N, "n_ip": sim.n_ip, "kept_samples_per_frame": samp, "field_evaluations_per_frame": evaluated,
+                   "parallelism": f"16x16 ray tiles over {world} GPU(s), simulator on rank 0" + (f", sim-aware tile weights {[round(x, 4) for x in calib['weights']]}" if calib else ""),
                    "l2": "flushed between timed frames (256 MiB fill)"},
         "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 64 + 16, "d2h_bytes_per_step": N * 5 * 4,
                 "wall_fps": K / e2e_wall, "api": "pienerf_b200.frame.DistFrameDriver.frame(): host pose -> pn_get_rays -> sim step -> (bcast) -> pn_render_deformed -> (gather) -> async copy to pinned host frame (double buffered)"},
         "gpu_launches": n_launch,
-        "roofline": {"kernel": "render_warp_kernel<3,true> (lattice march + inverse warp + hash encode + tcgen05 MLP + composite)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                     "frac": achieved / hbm, "traffic": None, "peak_source": src, "kernel_ms": kernel_ms,
-                     "algorithmic_bytes": f"{ALGO_BYTES_PER_SAMPLE_FUSED} B/sample x {samp:.0f} kept samples", "share_of_step": kernel_ms / (total_ms / K)},
+        "roofline": {"kernel": "wave_field_kernel (16-level hash-grid gather + tcgen05 MLP over 128-row sample tiles; one launch per wavefront pass)",
+                     "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": src,
+                     "kernel_ms_per_frame": field_ms, "launches_per_frame": n_pass, "first_pass_launch_ms": field0_ms,
+                     "algorithmic_bytes": f"{ALGO_BYTES_PER_SAMPLE_FUSED} B/sample x {evaluated:.0f} field evaluations per frame (summed over the frame's launches; rows incl. slab padding: {rows:.0f})",
+                     "share_of_step": field_ms / (total_ms / K), "render_passes_ms_per_frame": render_ms},
         "clocks": clocks, "wall_fps": K / wall,
     }
     line.update(extra)

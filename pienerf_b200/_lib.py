@@ -71,6 +71,7 @@ _PROTOS = {
     "pn_render_workspace_bytes": (u64, [u32, i32, f32, f32]),
     "pn_set_profile_events": (i32, [vp, vp]),
     "pn_set_profile_event_list": (i32, [vp, i32]),
+    "pn_render_pass_count": (i32, [u32]),
     "pn_qgmls_shape_functions": (i32, [f64, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     "pn_qgmls_collect_param": (i32, [vp, vp, vp, vp, i32, i32, f64, vp, vp, vp, vp]),
     "pn_qgmls_build_ip_global": (i32, [f64, f64, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]),

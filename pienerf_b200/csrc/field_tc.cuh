@@ -107,7 +107,7 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 
 // ---- shared-memory images
 // Weight matrix [N,K] (nn.Linear [out,in]) as B operand: element (n,k) of part p at  p*N*K*2 + (k/8)*(N*16) + n*16 + (k%8)*2.
-struct Weights {
+struct __align__(128) Weights {
     __nv_bfloat16 w1[2][64 * 32];   // sigma_net[0]   N=64 K=32   [hi|lo]
     __nv_bfloat16 w2[2][16 * 64];   // sigma_net[1]   N=16 K=64
     __nv_bfloat16 w3[2][64 * 32];   // color_net[0]   N=64 K=32 (input 31 zero-padded)
@@ -115,9 +115,10 @@ struct Weights {
     __nv_bfloat16 w5[2][16 * 64];   // color_net[2]   N=16 (3 used) K=64
     LevelGeom geo[16];
     uint32_t level_off[16];
+    uint32_t fast;                  // every level is dense or a power-of-two hash table (encode_rows_ilp applies)
 };
 // Activations of one tile group: [128 rows, 64 k] bf16, hi and lo images, chunk-major: (r,k) at (k/8)*2048 + r*16 + (k%8)*2
-struct TileSmem {
+struct __align__(128) TileSmem {
     __nv_bfloat16 a[2][kTile * 64];
     uint64_t bar;
     uint32_t tmem;
@@ -152,6 +153,14 @@ __device__ __forceinline__ void weights_fill(Weights &w, const pn_field_t &f) {
         w.geo[threadIdx.x] = level_geom(threadIdx.x, f.S, f.H, f.offsets, false);
         w.level_off[threadIdx.x] = (uint32_t)f.offsets[threadIdx.x];
     }
+    if (threadIdx.x == 0) {
+        uint32_t fast = 1;
+        for (int l = 0; l < 16; l++) {
+            const LevelGeom g = level_geom(l, f.S, f.H, f.offsets, false);
+            if (!g.dense3 && !g.mask) fast = 0;
+        }
+        w.fast = fast;
+    }
 }
 
 // bf16 hi/lo split of two values at once: hi = {rn(a), rn(b)}, lo = {rn(a - hi_a), rn(b - hi_b)} (a in the low half =
@@ -174,9 +183,10 @@ __device__ __forceinline__ void store_chunk(TileSmem &t, int row, int chunk, con
 // D[128,N] (TMEM columns tmem_d..) = A[128,K] W[N,K]^T with the 3-term bf16 split.  Called by ONE thread of the group.
 // Rolled loops with incremental descriptors: this runs on a single thread, code size matters more than issue rate.
 template <int N, int K>
-__device__ __forceinline__ void issue_layer(const TileSmem &t, const __nv_bfloat16 *w_hi, const __nv_bfloat16 *w_lo, uint32_t tmem_d) {
+__device__ __forceinline__ void issue_layer(const void *a_hi_img, const void *a_lo_img, const __nv_bfloat16 *w_hi, const __nv_bfloat16 *w_lo,
+                                            uint32_t tmem_d) {
     constexpr uint32_t idesc = instr_desc_bf16(N);
-    const uint64_t a_hi = smem_desc(smem_u32(t.a[0]), 2048, 128), a_lo = smem_desc(smem_u32(t.a[1]), 2048, 128);
+    const uint64_t a_hi = smem_desc(smem_u32(a_hi_img), 2048, 128), a_lo = smem_desc(smem_u32(a_lo_img), 2048, 128);
     const uint64_t b_hi = smem_desc(smem_u32(w_hi), N * 16, 128), b_lo = smem_desc(smem_u32(w_lo), N * 16, 128);
     uint32_t acc = 0;
 #pragma unroll 1
@@ -212,8 +222,11 @@ static __device__ __noinline__ void epilogue_relu64(TileSmem &t, int row, uint32
 // Full MLP for one tile.  Preconditions: this thread's 32 encoded features are already stored (chunks 0..3 of t.a);
 // `sh` = SH(4) of the sample's ray direction.  `phase` is the group's running mbarrier parity (updated).
 // All 128 threads of the group must call this together.
+// `a0_hi/a0_lo`: the [128,32] bf16 hi/lo images sigma_net[0] reads (the tile's own t.a, or a stage of a producer ring);
+// `release` (optional): mbarrier that is arrived on once the layer-1 MMAs have finished reading those images.
 __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int group, int row, const float (&sh)[16], uint32_t &phase,
-                                         float &sigma, float &r, float &g, float &b) {
+                                         float &sigma, float &r, float &g, float &b, const void *a0_hi, const void *a0_lo,
+                                         uint64_t *release = nullptr) {
     const uint32_t tm = t.tmem + ((uint32_t)(row & ~31) << 16);  // this warp's 32 TMEM lanes
     const bool warp0 = (row >> 5) == 0;  // warp-uniform: the group's first warp issues the MMAs through one elected lane
     float v[16], c8[8];
@@ -222,7 +235,11 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<64, 32>(t, w.w1[0], w.w1[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
+    if (warp0) {
+        tc_fence_after();
+        if (elect_one()) { issue_layer<64, 32>(a0_hi, a0_lo, w.w1[0], w.w1[1], t.tmem); if (release) umma_commit(release); umma_commit(&t.bar); }
+        __syncwarp();
+    }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
     epilogue_relu64(t, row, tm);
@@ -230,7 +247,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<16, 64>(t, w.w2[0], w.w2[1], t.tmem + 64); umma_commit(&t.bar); } __syncwarp(); }
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<16, 64>(t.a[0], t.a[1], w.w2[0], w.w2[1], t.tmem + 64); umma_commit(&t.bar); } __syncwarp(); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
     tmem_ld16(tm + 64, v);
@@ -253,7 +270,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<64, 32>(t, w.w3[0], w.w3[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<64, 32>(t.a[0], t.a[1], w.w3[0], w.w3[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
     epilogue_relu64(t, row, tm);
@@ -261,7 +278,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<64, 64>(t, w.w4[0], w.w4[1], t.tmem + 64); umma_commit(&t.bar); } __syncwarp(); }
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<64, 64>(t.a[0], t.a[1], w.w4[0], w.w4[1], t.tmem + 64); umma_commit(&t.bar); } __syncwarp(); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
     epilogue_relu64(t, row, tm + 64);
@@ -269,7 +286,7 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<16, 64>(t, w.w5[0], w.w5[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer<16, 64>(t.a[0], t.a[1], w.w5[0], w.w5[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
     mbar_wait(&t.bar, phase); phase ^= 1;
     tc_fence_after();
     tmem_ld16(tm, v);
@@ -277,6 +294,208 @@ __device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int grou
     g = 1.0f / (1.0f + expf(-v[1]));
     b = 1.0f / (1.0f + expf(-v[2]));
     tc_fence_before();  // order these TMEM reads before the next tile's first MMA (which follows a group_sync)
+}
+
+__device__ __forceinline__ void mlp_tile(TileSmem &t, const Weights &w, int group, int row, const float (&sh)[16], uint32_t &phase,
+                                         float &sigma, float &r, float &g, float &b) {
+    mlp_tile(t, w, group, row, sh, phase, sigma, r, g, b, t.a[0], t.a[1], nullptr);
+}
+
+// ---- TS variant: activations stay in tensor memory.  A operand of layers 2..5 is read by tcgen05.mma straight from
+// TMEM (bf16 pairs packed along K: element (row, k) = lane `row`, 32-bit column k/2, half k%2), written there by the
+// epilogue threads with tcgen05.st.  Removes the activation round trip through shared memory (stores + tensor-core
+// operand reads), which shares the L1 data pipe with the hash-table gathers.
+// TMEM columns of one group: D [0,64) fp32 accumulator | A_hi [64,96) | A_lo [96,128).
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <int N, int K>
+__device__ __forceinline__ void issue_layer_ts(uint32_t a_hi_t, uint32_t a_lo_t, const __nv_bfloat16 *w_hi, const __nv_bfloat16 *w_lo, uint32_t tmem_d) {
+    constexpr uint32_t idesc = instr_desc_bf16(N);
+    const uint64_t b_hi = smem_desc(smem_u32(w_hi), N * 16, 128), b_lo = smem_desc(smem_u32(w_lo), N * 16, 128);
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int term = 0; term < 3; term++) {  // small terms first, hi*hi last (same order as issue_layer)
+        uint32_t at = term == 0 ? a_lo_t : a_hi_t;
+        uint64_t bd = term == 1 ? b_lo : b_hi;
+#pragma unroll 1
+        for (int ks = 0; ks < K / 16; ks++) {
+            umma_bf16_ts(tmem_d, at, bd, idesc, acc);
+            acc = 1;
+            at += 8;                        // 16 bf16 k-values = 8 columns
+            bd += (2 * N * 16) >> 4;
+        }
+    }
+}
+// 8 consecutive k-values of this thread's row -> 4 hi words and 4 lo words
+__device__ __forceinline__ void split8(const float (&v)[8], uint32_t *h, uint32_t *l) {
+    split_pair(v[0], v[1], h[0], l[0]); split_pair(v[2], v[3], h[1], l[1]);
+    split_pair(v[4], v[5], h[2], l[2]); split_pair(v[6], v[7], h[3], l[3]);
+}
+static __device__ __noinline__ void epilogue_relu64_ts(uint32_t tm) {   // D [0,64) -> relu -> A_hi/A_lo (this warp's lanes)
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        float v[16], c8[8];
+        uint32_t h[8], l[8];
+        tmem_ld16(tm + q * 16, v);
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) c8[i] = fmaxf(v[hh * 8 + i], 0.f);
+            split8(c8, h + 4 * hh, l + 4 * hh);
+        }
+        tmem_st8(tm + 64 + q * 8, h);
+        tmem_st8(tm + 96 + q * 8, l);
+    }
+}
+// Same contract as mlp_tile; layer 1 reads its A operand from shared memory (a0_hi/a0_lo), layers 2..5 from TMEM.
+__device__ __forceinline__ void mlp_tile_ts(TileSmem &t, const Weights &w, int group, int row, const float (&sh)[16], uint32_t &phase,
+                                            float &sigma, float &r, float &g, float &b, const void *a0_hi, const void *a0_lo,
+                                            uint64_t *release) {
+    const uint32_t tm = t.tmem + ((uint32_t)(row & ~31) << 16);  // this warp's 32 TMEM lanes
+    const bool warp0 = (row >> 5) == 0;
+    const uint32_t a_hi_t = t.tmem + 64, a_lo_t = t.tmem + 96;
+    float v[16], c8[8];
+    uint32_t h[8], l[8];
+    // ---- sigma_net[0]: A from the producer stage (smem) -> D
+    tc_fence_before();
+    group_sync(group);
+    if (warp0) {
+        tc_fence_after();
+        if (elect_one()) { issue_layer<64, 32>(a0_hi, a0_lo, w.w1[0], w.w1[1], t.tmem); if (release) umma_commit(release); umma_commit(&t.bar); }
+        __syncwarp();
+    }
+    mbar_wait(&t.bar, phase); phase ^= 1;
+    tc_fence_after();
+    epilogue_relu64_ts(tm);
+    // ---- sigma_net[1]: [128,64] x [16,64]^T -> D cols 0..15
+    tmem_wait_st();
+    tc_fence_before();
+    group_sync(group);
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer_ts<16, 64>(a_hi_t, a_lo_t, w.w2[0], w.w2[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
+    mbar_wait(&t.bar, phase); phase ^= 1;
+    tc_fence_after();
+    tmem_ld16(tm, v);
+    sigma = expf(v[0]);
+    // colour-net input row: SH(16) | geo(15) | 0  (K = 32 -> 16 columns per image)
+#pragma unroll
+    for (int i = 0; i < 8; i++) c8[i] = sh[i];
+    split8(c8, h, l);
+#pragma unroll
+    for (int i = 0; i < 8; i++) c8[i] = sh[8 + i];
+    split8(c8, h + 4, l + 4);
+    tmem_st8(tm + 64, h); tmem_st8(tm + 96, l);
+#pragma unroll
+    for (int i = 0; i < 8; i++) c8[i] = v[1 + i];
+    split8(c8, h, l);
+#pragma unroll
+    for (int i = 0; i < 7; i++) c8[i] = v[9 + i];
+    c8[7] = 0.f;
+    split8(c8, h + 4, l + 4);
+    tmem_st8(tm + 64 + 8, h); tmem_st8(tm + 96 + 8, l);
+    // ---- color_net[0]: K = 32
+    tmem_wait_st();
+    tc_fence_before();
+    group_sync(group);
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer_ts<64, 32>(a_hi_t, a_lo_t, w.w3[0], w.w3[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
+    mbar_wait(&t.bar, phase); phase ^= 1;
+    tc_fence_after();
+    epilogue_relu64_ts(tm);
+    // ---- color_net[1]: K = 64
+    tmem_wait_st();
+    tc_fence_before();
+    group_sync(group);
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer_ts<64, 64>(a_hi_t, a_lo_t, w.w4[0], w.w4[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
+    mbar_wait(&t.bar, phase); phase ^= 1;
+    tc_fence_after();
+    epilogue_relu64_ts(tm);
+    // ---- color_net[2]: N = 16 (3 used)
+    tmem_wait_st();
+    tc_fence_before();
+    group_sync(group);
+    if (warp0) { tc_fence_after(); if (elect_one()) { issue_layer_ts<16, 64>(a_hi_t, a_lo_t, w.w5[0], w.w5[1], t.tmem); umma_commit(&t.bar); } __syncwarp(); }
+    mbar_wait(&t.bar, phase); phase ^= 1;
+    tc_fence_after();
+    tmem_ld16(tm, v);
+    r = 1.0f / (1.0f + expf(-v[0]));
+    g = 1.0f / (1.0f + expf(-v[1]));
+    b = 1.0f / (1.0f + expf(-v[2]));
+    tc_fence_before();
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// High-ILP encoder for a producer warp: all 8 corner indices of FOUR levels are computed first (the dense / hashed
+// choice is a select, not a branch), then the 32 gathers are issued back to back, then interpolated, split and stored
+// as one 16-byte k-chunk of the hi and of the lo image at `hi_row`/`lo_row` (+ chunk * 2048).  Requires every level to
+// be dense or a power-of-two hash table (Weights::fast); same vertices, weights and summation order as lookup3_c2.
+__device__ __forceinline__ void encode_rows_ilp(char *hi_row, char *lo_row, const Weights &w, const float2 *__restrict__ table, float bound,
+                                                bool valid, float x, float y, float z) {
+    const float inv = 1.0f / (2 * bound);
+    const float u = (x + bound) * inv, vv = (y + bound) * inv, ww = (z + bound) * inv;
+    const bool in = valid && !(u < 0 || u > 1 || vv < 0 || vv > 1 || ww < 0 || ww > 1);
+#pragma unroll 1
+    for (int c4 = 0; c4 < 4; c4++) {
+        uint32_t idx[4][8];
+        float fr[4][3];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int l = 4 * c4 + j;
+            const LevelGeom g = w.geo[l];
+            const uint32_t off = w.level_off[l];   // entry offsets stay 32-bit (whole table < 2^32 entries): one IMAD.WIDE per gather
+            float px = u * g.scale + 0.5f, py = vv * g.scale + 0.5f, pz = ww * g.scale + 0.5f;
+            const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+            fr[j][0] = px - fx; fr[j][1] = py - fy; fr[j][2] = pz - fz;
+            const uint32_t gx = (uint32_t)fx, gy = (uint32_t)fy, gz = (uint32_t)fz;
+            const uint32_t s1 = g.stride1, s2 = g.stride1 * g.stride1;
+            const uint32_t dy0 = gy * s1, dz0 = gz * s2;
+            const uint32_t hy0 = gy * 2654435761u, hz0 = gz * 805459861u;
+            // per-axis terms: dense -> added, hashed -> xored; (v+1)*P == v*P + P mod 2^32
+            const uint32_t ty0 = g.dense3 ? dy0 : hy0, ty1 = g.dense3 ? dy0 + s1 : hy0 + 2654435761u;
+            const uint32_t tz0 = g.dense3 ? dz0 : hz0, tz1 = g.dense3 ? dz0 + s2 : hz0 + 805459861u;
+            const uint32_t m = g.dense3 ? 0xffffffffu : g.mask;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const uint32_t tx = gx + (c & 1), ty = (c & 2) ? ty1 : ty0, tz = (c & 4) ? tz1 : tz0;
+                const uint32_t id = g.dense3 ? (tx + ty + tz) : ((tx ^ ty ^ tz) & m);
+                idx[j][c] = in ? id + off : 0u;
+            }
+        }
+        float2 v[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int c = 0; c < 8; c++) v[j][c] = __ldg(table + idx[j][c]);
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float px = fr[j][0], py = fr[j][1], pz = fr[j][2];
+            const float qx = 1.0f - px, qy = 1.0f - py, qz = 1.0f - pz;
+            const float w00 = qx * qy, w10 = px * qy, w01 = qx * py, w11 = px * py;
+            const float wt[8] = {w00 * qz, w10 * qz, w01 * qz, w11 * qz, w00 * pz, w10 * pz, w01 * pz, w11 * pz};
+            float2 e = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 8; c++) { e.x += wt[c] * v[j][c].x; e.y += wt[c] * v[j][c].y; }
+            if (!in) e = make_float2(0.f, 0.f);
+            split_pair(e.x, e.y, hw[j], lw[j]);
+        }
+        *reinterpret_cast<uint4 *>(hi_row + c4 * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4 *>(lo_row + c4 * 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
 }
 
 // Encode one sample and store its 32 features (k = 2*level, 2*level+1; chunks 0..3) for sigma_net[0].  Zero row for

@@ -11,6 +11,7 @@
 //                            sigma/colour MLP -> composite, all in registers, weights in shared memory.
 // The per-ray sample sequence is exactly the reference's (the wavefront loop only batches it differently), so
 // images agree to MLP rounding; see DESIGN.md for the one documented deviation (per-ray cap = max_steps).
+#include <cstdlib>
 #include "field_device.cuh"
 #include "march_device.cuh"
 
@@ -481,6 +482,12 @@ extern "C" int pn_set_profile_events(void *start, void *stop) {
     return PN_OK;
 }
 
+extern "C" int pn_render_pass_count(uint32_t max_steps) {
+    int n_pass = 0, covered = 0;
+    for (int cap_p = 64; covered < (int)max_steps && n_pass < kMaxPass - 1; cap_p *= 2) { covered += cap_p; n_pass++; }
+    return n_pass + 1;
+}
+
 extern "C" uint64_t pn_render_workspace_bytes(uint32_t N, int n_vtx, float bound, float hgs) {
     return layout(N, n_vtx, max_cells_for(bound, hgs)).total;
 }
@@ -541,13 +548,13 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
         Wv.xyzdt = (float4 *)(base + w.xyzdt); Wv.meta = (int2 *)(base + w.meta); Wv.out = (float4 *)(base + w.out);
         Wv.slab_next = (int *)(base + w.slab_next); Wv.cap = w.cap;
         PN_CUDA(cudaMemsetAsync(base + w.ctl, 0, 16 * 16 + 256, st));       // ctl + counters (adjacent, 256-byte aligned blocks)
-        const size_t smem = sizeof(WaveFieldSmem) + 128;
-        if (int rc = set_smem(wave_field_kernel, smem)) return rc;
+        // PN_FIELD_KERNEL=1 selects the unspecialised field kernel (A/B only); default: producer/consumer warp roles
+        static const int field_ws = [] { const char *e = getenv("PN_FIELD_KERNEL"); return !(e && e[0] == '1'); }();
+        const size_t smem = (field_ws ? sizeof(WaveWsSmem) : sizeof(WaveFieldSmem)) + 128;
+        if (int rc = field_ws ? set_smem(wave_field_ws_kernel, smem) : set_smem(wave_field_kernel, smem)) return rc;
         const uint32_t sms = (uint32_t)pn_sm_count_cached();
         // pass caps 64, 128, ... until the per-ray cap is covered; one spare pass absorbs the <32-sample overshoot per pass
-        int n_pass = 0, covered = 0;
-        for (int cap_p = 64; covered < (int)d->max_steps && n_pass < kMaxPass - 1; cap_p *= 2) { covered += cap_p; n_pass++; }
-        n_pass++;
+        const int n_pass = pn_render_pass_count(d->max_steps);
         int cap_p = 64, fk = 0;
         if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
         for (int p = 0; p < n_pass; p++, cap_p *= 2) {
@@ -557,7 +564,8 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
                 default: wave_march_kernel<3><<<sms * 2, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
             }
             if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk], st));
-            wave_field_kernel<<<sms, kWaveGroups * 128, smem, st>>>(A, Wv, p);
+            if (field_ws) wave_field_ws_kernel<<<sms, (kWsProd + kWsCons) * 128, smem, st>>>(A, Wv, p);
+            else wave_field_kernel<<<sms, kWaveGroups * 128, smem, st>>>(A, Wv, p);
             if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk + 1], st));
             fk++;
             wave_composite_kernel<<<div_up(N, 256u), 256, 0, st>>>(A, Wv, p, p == n_pass - 1);

@@ -225,6 +225,124 @@ __global__ void __launch_bounds__(kWaveGroups * 128, 1) wave_field_kernel(const 
     if (threadIdx.x < 32) pn::tc::tmem_dealloc(S.tmem_base, 512);
 }
 
+// --------------------------------------------------------------------------------------------- field, warp-specialised
+// Same work as wave_field_kernel, split by role inside one persistent CTA per SM:
+//   producer groups (4 warps = 128 rows each): hash-grid gather only — 32 gathers in flight per thread
+//                   (encode_rows_ilp) — writing the [128,32] bf16 hi/lo input of sigma_net[0] into a ring of stages;
+//   consumer groups (4 warps each): the five tensor-core layers; layer 1 reads its A operand straight from the ring
+//                   stage and releases it with tcgen05.commit on the stage's `empty` mbarrier.
+// The gathers (L2 latency bound) no longer stop while a tile is in its MLP phases, and vice versa.
+#ifndef PN_WS_PROD
+#define PN_WS_PROD 2
+#endif
+#ifndef PN_WS_CONS
+#define PN_WS_CONS 2
+#endif
+#ifndef PN_WS_STAGES
+#define PN_WS_STAGES 4
+#endif
+constexpr int kWsProd = PN_WS_PROD, kWsCons = PN_WS_CONS, kWsStages = PN_WS_STAGES;
+
+struct __align__(128) WsStage { __nv_bfloat16 a[2][128 * 32]; };   // hi | lo, chunk-major: (k/8)*2048 + row*16 + (k%8)*2
+struct __align__(128) WaveWsSmem {
+    pn::tc::Weights w;
+    pn::tc::TileSmem tile[kWsCons];
+    WsStage stage[kWsStages];
+    uint64_t full[kWsStages], empty[kWsStages];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_kernel(const RenderArgs A, const WaveArgs Wv, int pass) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    WaveWsSmem &S = *reinterpret_cast<WaveWsSmem *>(smem_raw);
+    const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0), row = threadIdx.x & 127, lane = threadIdx.x & 31;
+    const int n_rows = min(Wv.ctl[pass].n_reserved, Wv.cap);
+    if (n_rows == 0) return;
+    pn::tc::weights_fill(S.w, A.field);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWsStages; s++) { pn::tc::mbar_init(&S.full[s], 4); pn::tc::mbar_init(&S.empty[s], 1); }
+        for (int g = 0; g < kWsCons; g++) pn::tc::mbar_init(&S.tile[g].bar, 1);
+    }
+    pn::tc::fence_barrier_init();
+    if (threadIdx.x < 32) pn::tc::tmem_alloc(&S.tmem_base, 256);
+    pn::tc::fence_async_smem();
+    pn::tc::tc_fence_before();
+    __syncthreads();
+    pn::tc::tc_fence_after();
+    const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
+    const int n_tiles = n_rows / 128;                                   // slabs are whole tiles
+    // the j-th tile of this CTA is tile blockIdx.x + j * gridDim.x and lives in stage j % kWsStages
+    if (wg >= kWsCons) {
+        // ---------------------------------------------------------------- producer
+        const int pg = wg - kWsCons;
+        for (int j = pg; blockIdx.x + j * (int)gridDim.x < n_tiles; j += kWsProd) {
+            const int tile = blockIdx.x + j * gridDim.x, st = j % kWsStages, use = j / kWsStages;
+            const int i = tile * 128 + row;
+            const int2 mt = Wv.meta[i];
+            const bool valid = mt.x >= 0;
+            float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) sm = Wv.xyzdt[i];
+            pn::tc::mbar_wait(&S.empty[st], (use & 1) ^ 1);               // stage free (a fresh barrier passes at once)
+            char *hi = reinterpret_cast<char *>(S.stage[st].a[0]) + row * 16, *lo = reinterpret_cast<char *>(S.stage[st].a[1]) + row * 16;
+            if (S.w.fast) {
+                pn::tc::encode_rows_ilp(hi, lo, S.w, table, A.field.bound, valid, sm.x, sm.y, sm.z);
+            } else {
+                // generic table shapes: per-level path (tiled grids, non power-of-two hash sizes)
+                const float inv = 1.0f / (2 * A.field.bound);
+                const float u = (sm.x + A.field.bound) * inv, vv = (sm.y + A.field.bound) * inv, ww = (sm.z + A.field.bound) * inv;
+                const bool in = valid && !(u < 0 || u > 1 || vv < 0 || vv > 1 || ww < 0 || ww > 1);
+#pragma unroll 1
+                for (int l = 0; l < 16; l++) {
+                    float2 e = make_float2(0.f, 0.f);
+                    if (in) e = pn::lookup3_c2(table + S.w.level_off[l], S.w.geo[l], u, vv, ww, 0);
+                    uint32_t hw, lw;
+                    pn::tc::split_pair(e.x, e.y, hw, lw);
+                    const int off = (l >> 2) * 2048 + (l & 3) * 4;
+                    *reinterpret_cast<uint32_t *>(hi + off) = hw;
+                    *reinterpret_cast<uint32_t *>(lo + off) = lw;
+                }
+            }
+            pn::tc::fence_async_smem();                                   // generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) pn::tc::mbar_arrive(&S.full[st]);
+        }
+    } else {
+        // ---------------------------------------------------------------- consumer
+        const int cg = wg;
+        pn::tc::TileSmem &T = S.tile[cg];
+        if (row == 0) T.tmem = S.tmem_base + cg * pn::tc::kTmemCols;
+        pn::tc::group_sync(cg);
+        uint32_t phase = 0;
+        for (int j = cg; blockIdx.x + j * (int)gridDim.x < n_tiles; j += kWsCons) {
+            const int tile = blockIdx.x + j * gridDim.x, st = j % kWsStages, use = j / kWsStages;
+            const int i = tile * 128 + row;
+            const int2 mt = Wv.meta[i];
+            const bool valid = mt.x >= 0;
+            float dt = 0.f, dx = 0, dy = 0, dz = 1;
+            if (valid) {
+                dt = Wv.xyzdt[i].w;
+                dx = __ldg(A.rays_d + 3 * mt.x); dy = __ldg(A.rays_d + 3 * mt.x + 1); dz = __ldg(A.rays_d + 3 * mt.x + 2);
+            }
+            float sh[16];
+            pn::sh_eval<4>(dx, dy, dz, sh);
+            pn::tc::mbar_wait(&S.full[st], use & 1);
+            float sigma, r, g, b;
+#ifdef PN_WS_SS
+            pn::tc::mlp_tile(T, S.w, cg, row, sh, phase, sigma, r, g, b, S.stage[st].a[0], S.stage[st].a[1], &S.empty[st]);
+#else
+            pn::tc::mlp_tile_ts(T, S.w, cg, row, sh, phase, sigma, r, g, b, S.stage[st].a[0], S.stage[st].a[1], &S.empty[st]);
+#endif
+            if (valid) {
+                sigma = A.density_scale * sigma;
+                Wv.out[i] = make_float4(1.0f - __expf(-sigma * dt), r, g, b);
+            }
+        }
+    }
+    pn::tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) pn::tc::tmem_dealloc(S.tmem_base, 256);
+}
+
 // --------------------------------------------------------------------------------------------- composite
 __global__ void __launch_bounds__(256) wave_composite_kernel(const RenderArgs A, const WaveArgs Wv, int pass, int last_pass) {
     const int n_alive = pass == 0 ? A.queue->n_active : Wv.ctl[pass].n_alive;

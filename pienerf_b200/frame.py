@@ -142,12 +142,16 @@ class DistFrameDriver:
                 self.sim.stepforward()                                   # ... while rank 0 advances the simulator (trainer.py:308)
                 self.launches += 2 + 3 * self.sim.iters + 1
             self.model.p_def, self.model.IP_F, self.model.IP_dF = pos, F, dF
-        if profile_events is not None:
+        if profile_events is not None:                               # (start, stop[, flat list of per-pass field-kernel events])
             _lib.lib.pn_set_profile_events(_lib.vp(profile_events[0].cuda_event), _lib.vp(profile_events[1].cuda_event))
+            if len(profile_events) > 2:
+                arr = (_lib.vp * len(profile_events[2]))(*[e.cuda_event for e in profile_events[2]])
+                _lib.lib.pn_set_profile_event_list(arr, len(profile_events[2]))
         out = self.model.render_deformed(rays_o, rays_d, **self.opt)
-        self.launches += 10
+        self.launches += self.model._render_launches
         if profile_events is not None:
             _lib.lib.pn_set_profile_events(_lib.vp(0), _lib.vp(0))
+            _lib.lib.pn_set_profile_event_list(None, 0)
         slot = None
         if self.world > 1 or to_host:
             slot = self.frame_id & 1
