@@ -361,7 +361,8 @@ static __device__ __noinline__ void epilogue_relu64_ts(uint32_t tm) {   // D [0,
     }
 }
 // Same contract as mlp_tile; layer 1 reads its A operand from shared memory (a0_hi/a0_lo), layers 2..5 from TMEM.
-__device__ __forceinline__ void mlp_tile_ts(TileSmem &t, const Weights &w, int group, int row, const float (&sh)[16], uint32_t &phase,
+template <class TileT>   // anything with .tmem (TMEM base column of the group) and .bar (the group's MMA-done mbarrier)
+__device__ __forceinline__ void mlp_tile_ts(TileT &t, const Weights &w, int group, int row, const float (&sh)[16], uint32_t &phase,
                                             float &sigma, float &r, float &g, float &b, const void *a0_hi, const void *a0_lo,
                                             uint64_t *release) {
     const uint32_t tm = t.tmem + ((uint32_t)(row & ~31) << 16);  // this warp's 32 TMEM lanes

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kWaveGroups * 128, 1) wave_field_kernel(const 
 //                   stage and releases it with tcgen05.commit on the stage's `empty` mbarrier.
 // The gathers (L2 latency bound) no longer stop while a tile is in its MLP phases, and vice versa.
 #ifndef PN_WS_PROD
-#define PN_WS_PROD 2
+#define PN_WS_PROD 3
 #endif
 #ifndef PN_WS_CONS
 #define PN_WS_CONS 2
@@ -244,9 +244,14 @@ __global__ void __launch_bounds__(kWaveGroups * 128, 1) wave_field_kernel(const 
 constexpr int kWsProd = PN_WS_PROD, kWsCons = PN_WS_CONS, kWsStages = PN_WS_STAGES;
 
 struct __align__(128) WsStage { __nv_bfloat16 a[2][128 * 32]; };   // hi | lo, chunk-major: (k/8)*2048 + row*16 + (k%8)*2
+#ifdef PN_WS_SS
+using WsTile = pn::tc::TileSmem;                                    // A/B build: activations through shared memory
+#else
+struct WsTile { uint64_t bar; uint32_t tmem; uint32_t pad; };       // activations live in TMEM: only the barrier + TMEM base
+#endif
 struct __align__(128) WaveWsSmem {
     pn::tc::Weights w;
-    pn::tc::TileSmem tile[kWsCons];
+    WsTile tile[kWsCons];
     WsStage stage[kWsStages];
     uint64_t full[kWsStages], empty[kWsStages];
     uint32_t tmem_base;
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
         for (int g = 0; g < kWsCons; g++) pn::tc::mbar_init(&S.tile[g].bar, 1);
     }
     pn::tc::fence_barrier_init();
-    if (threadIdx.x < 32) pn::tc::tmem_alloc(&S.tmem_base, 256);
+    if (threadIdx.x < 32) pn::tc::tmem_alloc(&S.tmem_base, kWsCons <= 2 ? 256 : 512);
     pn::tc::fence_async_smem();
     pn::tc::tc_fence_before();
     __syncthreads();
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
     } else {
         // ---------------------------------------------------------------- consumer
         const int cg = wg;
-        pn::tc::TileSmem &T = S.tile[cg];
+        WsTile &T = S.tile[cg];
         if (row == 0) T.tmem = S.tmem_base + cg * pn::tc::kTmemCols;
         pn::tc::group_sync(cg);
         uint32_t phase = 0;
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
     }
     pn::tc::tc_fence_before();
     __syncthreads();
-    if (threadIdx.x < 32) pn::tc::tmem_dealloc(S.tmem_base, 256);
+    if (threadIdx.x < 32) pn::tc::tmem_dealloc(S.tmem_base, kWsCons <= 2 ? 256 : 512);
 }
 
 // --------------------------------------------------------------------------------------------- composite
