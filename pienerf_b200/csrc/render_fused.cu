@@ -559,9 +559,9 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
         if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
         for (int p = 0; p < n_pass; p++, cap_p *= 2) {
             switch (d->num_seek_IP) {
-                case 1: wave_march_kernel<1><<<sms * 2, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
-                case 2: wave_march_kernel<2><<<sms * 2, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
-                default: wave_march_kernel<3><<<sms * 2, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
+                case 1: wave_march_kernel<1><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
+                case 2: wave_march_kernel<2><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
+                default: wave_march_kernel<3><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
             }
             if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk], st));
             if (field_ws) wave_field_ws_kernel<<<sms, (kWsProd + kWsCons) * 128, smem, st>>>(A, Wv, p);

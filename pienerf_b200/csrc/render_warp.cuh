@@ -121,6 +121,11 @@ __device__ __forceinline__ int nearest_sorted(const IpPack &P, const pn::BendCfg
     return found;
 }
 
+// (A flattened one-candidate-stream-per-lane formulation of this search was measured on B200: fewer warp
+//  instructions but a single dependent load per lane in flight — slower than the nested loops below, which the
+//  compiler unrolls by two.  Occupancy, not instruction count, is what the march kernel responds to.)
+#define PN_NEAREST nearest_sorted
+
 // bend_sample (march_device.cuh) over the packed, cell-sorted IP state.  Identical decisions and arithmetic.
 template <int KMAX>
 __device__ __forceinline__ bool bend_sample_packed(const IpPack &P, const pn::BendCfg &c, const unsigned char *rankA,
@@ -134,10 +139,10 @@ __device__ __forceinline__ bool bend_sample_packed(const IpPack &P, const pn::Be
     int n_ip;
     if (KMAX == 1) {
         // find_closest_IP: own cell; the neighbours only if the own cell holds nothing closer than 9999.9
-        n_ip = nearest_sorted<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, true, 9999.9f, ks);
-        if (n_ip == 0) n_ip = nearest_sorted<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, false, 9999.9f, ks);
+        n_ip = PN_NEAREST<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, true, 9999.9f, ks);
+        if (n_ip == 0) n_ip = PN_NEAREST<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, false, 9999.9f, ks);
     } else {
-        n_ip = nearest_sorted<KMAX>(P, c, rankA, x, y, z, g0, g1, g2, false, FLT_MAX, ks);
+        n_ip = PN_NEAREST<KMAX>(P, c, rankA, x, y, z, g0, g1, g2, false, FLT_MAX, ks);
     }
     if (n_ip <= 0) return false;
     for (int k = 0; k < n_ip; k++) {  // boundary filter with the shrinking loop bound (raymarching.cu:1246-1251)

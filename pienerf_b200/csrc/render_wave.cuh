@@ -49,8 +49,11 @@ struct WaveArgs {
 };
 
 // --------------------------------------------------------------------------------------------- march
+#ifndef PN_MARCH_MINB
+#define PN_MARCH_MINB 3   // 24 warps / SM at 80 registers (a few spills) beat 16 warps at 128: the search is latency-bound
+#endif
 template <int KMAX>
-__global__ void __launch_bounds__(256, 2) wave_march_kernel(const RenderArgs A, const IpPack P, const WaveArgs Wv, int pass, int pass_cap) {
+__global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const RenderArgs A, const IpPack P, const WaveArgs Wv, int pass, int pass_cap) {
     __shared__ unsigned char rankA[27], rankB[27];
     if (threadIdx.x < 27) {
         const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;

@@ -65,6 +65,9 @@ def test_frame_vs_oracle(amp, K):
     for k in ("image", "depth", "depth_0", "weights_sum"):
         assert torch.equal(torch.nan_to_num(wave[k], nan=-7.0), torch.nan_to_num(fused[k], nan=-7.0)), k   # depth is NaN for a miss, as in the reference
     assert int(wave["stats"][0]) == int(fused["stats"][0]) and int(wave["stats"][1]) == int(fused["stats"][1])
+    # mode 2 walks the IP grid in the reference's own order (march_device.cuh); the packed/flattened search of modes
+    # 0/1/3 must take exactly the same emit / skip decisions
+    assert int(lane["stats"][0]) == int(simt["stats"][0]) == int(wave["stats"][0])
     assert abs(int(simt["stats"][0]) - loop["n_samples"]) <= 0.002 * loop["n_samples"] + 2
     assert abs(loop["n_samples"] - want["n_samples"]) <= 0.01 * want["n_samples"]
 
