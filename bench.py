@@ -217,9 +217,10 @@ def run_ours(args):
         "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 64 + 16, "d2h_bytes_per_step": N * 5 * 4,
                 "wall_fps": K / e2e_wall, "api": "pienerf_b200.frame.DistFrameDriver.frame(): host pose -> pn_get_rays -> sim step -> (bcast) -> pn_render_deformed -> (gather) -> async copy to pinned host frame (double buffered)"},
         "gpu_launches": n_launch,
-        "roofline": {"kernel": "wave_field_kernel (16-level hash-grid gather + tcgen05 MLP over 128-row sample tiles; one launch per wavefront pass)",
-                     "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": src,
-                     "kernel_ms_per_frame": field_ms, "launches_per_frame": n_pass, "first_pass_launch_ms": field0_ms,
+        "roofline": {"kernel": "wave_field_ws_kernel (16-level hash-grid gather + tcgen05 MLP over 128-row sample tiles; one launch per wavefront pass)",
+                     "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "traffic": 164.5e6, "traffic_note": "dram__bytes_read+write of the first-pass launch (3.9 M rows, 4.1 GB algorithmic) in profiles/r1_ncu_summary.txt; the 46.7 MiB table is L2-resident",
+                     "peak_source": src, "kernel_ms_per_frame": field_ms, "launches_per_frame": n_pass, "first_pass_launch_ms": field0_ms,
                      "algorithmic_bytes": f"{ALGO_BYTES_PER_SAMPLE_FUSED} B/sample x {evaluated:.0f} field evaluations per frame (summed over the frame's launches; rows incl. slab padding: {rows:.0f})",
                      "share_of_step": field_ms / (total_ms / K), "render_passes_ms_per_frame": render_ms},
         "clocks": clocks, "wall_fps": K / wall,

@@ -27,15 +27,16 @@ if has launches; then
     python scripts/launch_shares.py "$OUT/launches.csv" 30 > "$OUT/launch_shares.txt" 2>&1; head -20 "$OUT/launch_shares.txt"
 fi
 if has ncu_frame; then
-    timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_warp_kernel -s 2 -c 1 -f -o "$OUT/frame" \
-        python scripts/profile_frame.py 4 1.0 0 > "$OUT/ncu_frame.log" 2>&1
+    # the three wavefront kernels of pass 0 (field = the roofline kernel), timed frames only
+    timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:wave_ -c 3 -f -o "$OUT/wave" \
+        python scripts/mode_compare.py 3 1.0 > "$OUT/ncu_wave.log" 2>&1
 fi
 if has ncu_grid; then
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:grid_forward_d3c2 -s 3 -c 2 -f -o "$OUT/grid" \
         python scripts/grid_bench.py > "$OUT/ncu_grid.log" 2>&1
 fi
 if has ncu_sim; then
-    timeout 900 ncu --set full --clock-control none --import-source on -k "regex:ip_stress_kernel|rhs_gather_kernel|matvec3_kernel|ip_info_kernel" -s 40 -c 8 -f -o "$OUT/sim" \
+    timeout 900 ncu --set full --clock-control none --import-source on -k "regex:ip_stress_kernel|rhs_partial_kernel|matvec3_kernel|ip_info_kernel" -s 40 -c 8 -f -o "$OUT/sim" \
         python scripts/profile_frame.py 4 1.0 0 > "$OUT/ncu_sim.log" 2>&1
 fi
 if has ncu_field; then
