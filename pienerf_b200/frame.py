@@ -82,7 +82,7 @@ class DistFrameDriver:
     work on k+1; `wait_host()` blocks until a given frame has landed).
     """
 
-    def __init__(self, model, sim, opt, tile=16, weights=None):
+    def __init__(self, model, sim, opt, tile=16, weights=None, overlap_sim=True):
         import torch.distributed as dist
         from .dist import FrameGather, tile_partition
         self.model, self.sim, self.opt, self.tile = model, sim, opt, tile
@@ -96,6 +96,8 @@ class DistFrameDriver:
         self.W, self.H = opt.W, opt.H
         self.ipbuf = torch.zeros(sim.n_ip, 39, dtype=torch.float32, device=self.dev)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.sim_stream = torch.cuda.Stream(device=self.dev, priority=-1)
+        self.overlap_sim = overlap_sim
         self.host = [torch.empty(self.W * self.H, 5, dtype=torch.float32).pin_memory() for _ in range(2)] if self.rank == 0 else None
         self.copy_done = [None, None]
         self.frame_id = 0
@@ -127,6 +129,7 @@ class DistFrameDriver:
         if regenerate_rays or self._rays is None:                    # trainer.py:541-543: rays from the host pose every frame
             self._rays = self.rays(pose_host, intrinsics)
         rays_o, rays_d = self._rays
+        step_done = None
         if not paused:
             if self.rank == 0:
                 pos, F, dF = self.sim.get_IP_info()                      # state BEFORE the step (trainer.py:303-306)
@@ -139,8 +142,19 @@ class DistFrameDriver:
                 pos, F, dF = unpack_ip_state(self.ipbuf)
                 self.launches += 3
             if self.rank == 0:
-                self.sim.stepforward()                                   # ... while rank 0 advances the simulator (trainer.py:308)
-                self.launches += 2 + 3 * self.sim.iters + 1
+                # ... while rank 0 advances the simulator (trainer.py:308).  The frame renders the state read BEFORE the
+                # step, so the step only has to be ordered after that read: it runs on a high-priority side stream,
+                # concurrently with this rank's render kernels, and the frame ends by waiting for it.
+                if self.overlap_sim:
+                    read_done = torch.cuda.Event(); read_done.record()
+                    with torch.cuda.stream(self.sim_stream):
+                        self.sim_stream.wait_event(read_done)
+                        self.sim.stepforward()
+                        step_done = torch.cuda.Event(); step_done.record()
+                else:
+                    self.sim.stepforward()
+                    step_done = None
+                self.launches += 2 + 4 * self.sim.iters + 1
             self.model.p_def, self.model.IP_F, self.model.IP_dF = pos, F, dF
         if profile_events is not None:                               # (start, stop[, flat list of per-pass field-kernel events])
             _lib.lib.pn_set_profile_events(_lib.vp(profile_events[0].cuda_event), _lib.vp(profile_events[1].cuda_event))
@@ -169,6 +183,8 @@ class DistFrameDriver:
                 self.copy_done[slot] = done
                 # the next gather may only overwrite `fb` after this copy has read it
                 self._fb_guard = done
+        if step_done is not None:
+            torch.cuda.current_stream().wait_event(step_done)           # frame k is complete only when step k is
         self.frame_id += 1
         return out, slot
 
