@@ -72,6 +72,40 @@ class FrameDriver:
         return {"image": image, "depth": depth, "depth_0": depth_0}
 
 
+def screen_to_world(x, y, depth_0, pose, intrinsics, average_depth=0.0):
+    """nerf/gui.py:647-657: unproject pixel (x, y) with the rendered `depth_0` [H,W] (0 = nothing hit -> average_depth)."""
+    fx, fy, cx, cy = [float(v) for v in intrinsics]
+    H, W = depth_0.shape
+    # the GUI indexes its [W,H]-reshaped buffer with (x, y); same pixel here as depth_0[row y, column x]
+    d = float(depth_0[min(max(int(y), 0), H - 1), min(max(int(x), 0), W - 1)])
+    if d == 0.0:
+        d = float(average_depth)
+    cam = np.array([(x - cx) / fx * d, (y - cy) / fy * d, d, 1.0])
+    return (np.asarray(pose, dtype=np.float64) @ cam)[:3], d
+
+
+def world_to_screen(pos, pose, intrinsics):
+    """nerf/gui.py:659-667."""
+    fx, fy, cx, cy = [float(v) for v in intrinsics]
+    P = np.eye(4); P[:np.asarray(pose).shape[0], :] = np.asarray(pose, dtype=np.float64)
+    xc, yc, zc = (np.linalg.inv(P) @ np.array([*pos, 1.0]))[:3]
+    return xc / zc * fx + cx, yc / zc * fy + cy, zc
+
+
+def drag_force(sim, sid, target, force_scale=1.0, limit=5e5):
+    """nerf/gui.py:561-577,584-586: the mouse-drag force on IP `sid` towards world point `target` (None clears it)."""
+    if sid is None:
+        sim.clear_force()
+        return None
+    p0 = sim.get_IP_info()[0][sid].double().cpu().numpy()
+    f = force_scale * 1e5 * (np.asarray(target, dtype=np.float64) - p0)
+    n = np.linalg.norm(f)
+    if n > limit:
+        f *= limit / n
+    sim.update_force(int(sid), f)
+    return f
+
+
 class DistFrameDriver:
     """The frame loop on N GPUs of one node (one process per GPU; N = 1 works without a process group).
 

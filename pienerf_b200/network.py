@@ -49,6 +49,10 @@ class NeRFNetwork(nn.Module):
         self.register_buffer("aabb_train", aabb)
         self.register_buffer("aabb_infer", aabb.clone())
         self.register_buffer("density_bitfield", torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
+        # density-grid maintenance state (renderer.py:95-106); the frame loop only reads the bitfield
+        self.register_buffer("density_grid", torch.zeros(self.cascade, self.grid_size ** 3))
+        self.mean_density = 0.0
+        self.iter_density = 0
         # nerf/network.py:30-71
         self.num_layers, self.hidden_dim, self.geo_feat_dim = num_layers, hidden_dim, geo_feat_dim
         self.encoder = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
@@ -99,6 +103,92 @@ class NeRFNetwork(nn.Module):
             if l != self.num_layers_color - 1:
                 h = F.relu(h, inplace=True)
         return sigma, torch.sigmoid(h)
+
+    # ------------------------------------------------------------------ nerf/network.py:129-146
+    @torch.no_grad()
+    def density(self, x):
+        """sigma and geometry features only (hash-grid kernel + the two sigma_net layers)."""
+        h = self.encoder(x, bound=self.bound)
+        for l in range(self.num_layers):
+            h = self.sigma_net[l](h)
+            if l != self.num_layers - 1:
+                h = F.relu(h, inplace=True)
+        return {"sigma": torch.exp(h[..., 0]), "geo_feat": h[..., 1:]}
+
+    # ------------------------------------------------------------------ nerf/renderer.py:396-401, 455-549 (SURVEY 8f.1)
+    def reset_extra_state(self):
+        self.density_grid.zero_()
+        self.mean_density = 0.0
+        self.iter_density = 0
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128, noise=True, generator=None):
+        """Density-grid maintenance: sample sigma at (jittered) cell centres of every cascade, EMA-max into
+        `density_grid`, re-threshold and pack the occupancy bitfield the march kernels read.  Full update for the
+        first 16 calls, then the reference's half-random / half-occupied partial update.  `noise=False` (cell centres,
+        no jitter) makes the result reproducible for the parity test; the reference always jitters."""
+        if not self.cuda_ray:
+            return
+        dev, H = self.density_bitfield.device, self.grid_size
+        tmp_grid = -torch.ones_like(self.density_grid)
+
+        def rand_like(t):
+            return torch.rand(t.shape, dtype=t.dtype, device=t.device, generator=generator)
+
+        def sample(cas, coords, indices):
+            xyzs = 2 * coords.float() / (H - 1) - 1
+            bound = min(2 ** cas, self.bound)
+            half_grid_size = bound / H
+            cas_xyzs = xyzs * (bound - half_grid_size)
+            if noise:
+                cas_xyzs = cas_xyzs + (rand_like(cas_xyzs) * 2 - 1) * half_grid_size
+            sig = self.density(cas_xyzs)["sigma"].reshape(-1) * self.density_scale
+            tmp_grid[cas, indices] = sig
+
+        if self.iter_density < 16:
+            ar = torch.arange(H, dtype=torch.int32, device=dev)
+            for xs in ar.split(S):
+                for ys in ar.split(S):
+                    for zs in ar.split(S):
+                        xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
+                        coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1).contiguous()
+                        indices = raymarching.morton3D(coords).long()
+                        for cas in range(self.cascade):
+                            sample(cas, coords, indices)
+        else:
+            N = H ** 3 // 4
+            for cas in range(self.cascade):
+                coords = torch.randint(0, H, (N, 3), device=dev, generator=generator, dtype=torch.int32)
+                indices = raymarching.morton3D(coords).long()
+                occ = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                if occ.numel() > 0:
+                    pick = torch.randint(0, occ.shape[0], [N], dtype=torch.long, device=dev, generator=generator)
+                    occ = occ[pick]
+                    occ_coords = raymarching.morton3D_invert(occ.int())
+                    indices = torch.cat([indices, occ], dim=0)
+                    coords = torch.cat([coords, occ_coords], dim=0)
+                sample(cas, coords, indices)
+        valid = (self.density_grid >= 0) & (tmp_grid >= 0)
+        self.density_grid[valid] = torch.maximum(self.density_grid[valid] * decay, tmp_grid[valid])
+        self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+        self.iter_density += 1
+        density_thresh = min(self.mean_density, self.density_thresh)
+        self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
+
+    # ------------------------------------------------------------------ nerf/trainer.py:799-818,853-906 (SURVEY 8f.2)
+    def load_checkpoint(self, path_or_state, strict=False):
+        """torch-ngp `.pth` checkpoint (or its `model` state dict): same key names as this module, so a real chair /
+        trex asset loads directly; extra keys (optimizer, ema, bg_net ...) are ignored unless strict."""
+        state = torch.load(path_or_state, map_location="cpu") if isinstance(path_or_state, (str, bytes)) or hasattr(path_or_state, "read") else path_or_state
+        if "model" in state and isinstance(state["model"], dict):
+            if "mean_density" in state:
+                self.mean_density = float(state["mean_density"])
+            state = state["model"]
+        own = self.state_dict()
+        if "encoder.embeddings" in state and tuple(state["encoder.embeddings"].shape) != tuple(own["encoder.embeddings"].shape):
+            raise ValueError(f"checkpoint hash table {tuple(state['encoder.embeddings'].shape)} does not match bound={self.bound} "
+                             f"({tuple(own['encoder.embeddings'].shape)}): construct NeRFNetwork with the checkpoint's bound")
+        return self.load_state_dict({k: v for k, v in state.items() if strict or k in own}, strict=strict)
 
     def _field_struct(self):
         f = FieldT()

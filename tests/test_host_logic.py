@@ -114,3 +114,19 @@ def test_broadcast_and_gather_world_size_2():
     for p in procs:
         p.join(60)
     assert res == [(0, True), (1, True)]
+
+
+def test_screen_world_roundtrip():
+    """nerf/gui.py:647-667 helpers (picking): unproject with a depth, project back to the same pixel."""
+    from pienerf_b200.frame import screen_to_world, world_to_screen
+    from pienerf_b200.synthetic import orbit_intrinsics, orbit_pose
+    pose = orbit_pose(radius=2.5); intr = orbit_intrinsics(64, 48, 50.0)
+    depth = np.zeros((48, 64), dtype=np.float32); depth[20, 30] = 2.25
+    p, d = screen_to_world(30, 20, depth, pose, intr, average_depth=9.0)
+    assert d == 2.25
+    x, y, z = world_to_screen(p, pose, intr)
+    assert abs(x - 30) < 1e-9 and abs(y - 20) < 1e-9 and abs(z - 2.25) < 1e-9
+    _, d = screen_to_world(0, 0, depth, pose, intr, average_depth=9.0)          # nothing hit -> the GUI's average depth
+    assert d == 9.0
+    _, d = screen_to_world(1000, -5, depth, pose, intr, average_depth=9.0)      # clamped like gui.py:649
+    assert d == 9.0
