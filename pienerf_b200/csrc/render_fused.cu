@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(128, 3) field_forward_kernel(const pn_field_t 
 }
 
 struct WorkspaceLayout {
-    size_t geom, queue, nears, fars, active, pig_cnt, pig_bgn, pig_fill, pig_idx, ip_pos, ip_rec;
+    size_t geom, queue, nears, fars, active, pig_cnt, pig_bgn, pig_fill, pig_idx, ip_pos, ip_rec, nb_cnt, nb_start, nb_fill, nb_list;
     size_t ctl, alive0, alive1, rs_march, rs_comp, link, xyzdt, meta, out, slab_next, counters;   // wavefront mode
     int cap;
     size_t total;
@@ -378,6 +378,8 @@ WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
     w.pig_idx = take(sizeof(int) * (size_t)n_vtx);
     w.ip_pos = take(sizeof(float4) * (size_t)n_vtx);
     w.ip_rec = take(sizeof(float) * 16 * (size_t)n_vtx);
+    w.nb_cnt = take(sizeof(int) * (size_t)max_cells); w.nb_start = take(sizeof(int) * ((size_t)max_cells + 1));
+    w.nb_fill = take(sizeof(int) * (size_t)max_cells); w.nb_list = take(sizeof(float4) * 27 * (size_t)n_vtx);
     w.cap = wave_capacity(N);
     w.ctl = take(16 * 16);
     w.counters = take(64);
@@ -539,8 +541,13 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
         float4 *ip_pos = (float4 *)(base + w.ip_pos);
         float *ip_rec = (float *)(base + w.ip_rec);
         ip_pack_kernel<<<div_up(d->n_vtx, 256), 256, 0, st>>>(d->p_def, d->p_ori, d->F_IP, idx, d->n_vtx, geom->res, max_cells, bgn, ip_pos, ip_rec);
-        PN_LAUNCH_CHECK("ip_pack_kernel");
-        IpPack P{ip_pos, ip_rec, bgn};
+        int *nb_cnt = (int *)(base + w.nb_cnt), *nb_start = (int *)(base + w.nb_start), *nb_fill = (int *)(base + w.nb_fill);
+        float4 *nb_list = (float4 *)(base + w.nb_list);
+        nb_count_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(cnt, geom->res, max_cells, nb_cnt);
+        ip_grid_scan<<<1, 1024, 0, st>>>(nb_cnt, geom->res, max_cells, nb_start, nb_fill);
+        nb_fill_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(bgn, ip_pos, geom->res, max_cells, d->num_seek_IP == 1, nb_start, nb_list);
+        PN_LAUNCH_CHECK("ip_pack / neighbourhood lists");
+        IpPack P{ip_pos, ip_rec, bgn, nb_start, nb_list};
         WaveArgs Wv{};
         Wv.ctl = (PassCtl *)(base + w.ctl); Wv.counters = (long long *)(base + w.counters);
         Wv.alive[0] = (int *)(base + w.alive0); Wv.alive[1] = (int *)(base + w.alive1);
@@ -582,8 +589,13 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
         float4 *ip_pos = (float4 *)(base + w.ip_pos);
         float *ip_rec = (float *)(base + w.ip_rec);
         ip_pack_kernel<<<div_up(d->n_vtx, 256), 256, 0, st>>>(d->p_def, d->p_ori, d->F_IP, idx, d->n_vtx, geom->res, max_cells, bgn, ip_pos, ip_rec);
-        PN_LAUNCH_CHECK("ip_pack_kernel");
-        IpPack P{ip_pos, ip_rec, bgn};
+        int *nb_cnt = (int *)(base + w.nb_cnt), *nb_start = (int *)(base + w.nb_start), *nb_fill = (int *)(base + w.nb_fill);
+        float4 *nb_list = (float4 *)(base + w.nb_list);
+        nb_count_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(cnt, geom->res, max_cells, nb_cnt);
+        ip_grid_scan<<<1, 1024, 0, st>>>(nb_cnt, geom->res, max_cells, nb_start, nb_fill);
+        nb_fill_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(bgn, ip_pos, geom->res, max_cells, d->num_seek_IP == 1, nb_start, nb_list);
+        PN_LAUNCH_CHECK("ip_pack / neighbourhood lists");
+        IpPack P{ip_pos, ip_rec, bgn, nb_start, nb_list};
         const bool tc = mode == 0;
         const size_t smem = tc ? (((sizeof(RenderTcSmem) + 127) & ~size_t(127)) + kTcGroups * 4 * sizeof(WarpShared) + 128)
                                : (((sizeof(pn::FieldBlockSmem) + 127) & ~size_t(127)) + 4 * sizeof(WarpShared) + 128);

@@ -21,7 +21,103 @@ struct IpPack {
     const float4 *pos;      // [n] (p_def.xyz, bitcast original ip) in cell order
     const float *rec;       // [n,16]: p_ori(0..2) p_def(3..5) Finv(6..14) for the max_iter_num == 1 fast path
     const int *cell_start;  // [n_grid+1]
+    const int *nb_start;    // [n_grid+1] CSR of the per-cell neighbourhood lists
+    const float4 *nb_list;  // [<= 27 n] (p_def.xyz, bitcast position k in the cell-sorted arrays)
 };
+
+// Per-frame neighbourhood lists: for every IP-grid cell, the IPs of its 27-cell neighbourhood in exactly the order in
+// which the reference's search visits them (own cell, then the 26 offsets of kNeigh — applied as (x,y,z) offsets by
+// find_closest_IPs and as (z,y,x) offsets by find_closest_IP, raymarching.cu:986-1118 — IPs of a cell in ascending
+// index).  A lattice point then scans ONE contiguous list with a strict-less insertion: the reference's tie-breaking
+// falls out of the order, no per-row cell_start lookups, no rank keys, no divergent row loop, loads are independent of
+// the loop state (unrolled, prefetchable).  Every IP appears in at most 27 lists: <= 27 n entries (0.9 MB for 2k IPs).
+__global__ void __launch_bounds__(256) nb_count_kernel(const int *__restrict__ cnt, const int *__restrict__ res, int n_grid_cap,
+                                                       int *__restrict__ nb_cnt) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r0 = res[0], r1 = res[1], r2 = res[2];
+    if (c >= min(r0 * r1 * r2, n_grid_cap)) return;
+    const int g0 = c % r0, g1 = (c / r0) % r1, g2 = c / (r0 * r1);
+    int n = 0;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                const int a0 = g0 + dx, a1 = g1 + dy, a2 = g2 + dz;
+                if (a0 >= 0 && a0 < r0 && a1 >= 0 && a1 < r1 && a2 >= 0 && a2 < r2) n += cnt[(a2 * r1 + a1) * r0 + a0];
+            }
+    nb_cnt[c] = n;
+}
+__global__ void __launch_bounds__(256) nb_fill_kernel(const int *__restrict__ cell_start, const float4 *__restrict__ pos,
+                                                      const int *__restrict__ res, int n_grid_cap, int zyx_order,
+                                                      int *__restrict__ nb_start, float4 *__restrict__ nb_list) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r0 = res[0], r1 = res[1], r2 = res[2];
+    const int n_grid = min(r0 * r1 * r2, n_grid_cap);
+    if (c >= n_grid) return;
+    const int g0 = c % r0, g1 = (c / r0) % r1, g2 = c / (r0 * r1);
+    int o = nb_start[c];
+    for (int q = -1; q < 26; q++) {
+        int d0 = 0, d1 = 0, d2 = 0;
+        if (q >= 0) {
+            if (zyx_order) { d2 = pn::kNeigh[q][0]; d1 = pn::kNeigh[q][1]; d0 = pn::kNeigh[q][2]; }
+            else { d0 = pn::kNeigh[q][0]; d1 = pn::kNeigh[q][1]; d2 = pn::kNeigh[q][2]; }
+        }
+        const int a0 = g0 + d0, a1 = g1 + d1, a2 = g2 + d2;
+        if (a0 < 0 || a0 >= r0 || a1 < 0 || a1 >= r1 || a2 < 0 || a2 >= r2) continue;
+        const int gid = (a2 * r1 + a1) * r0 + a0;
+        for (int k = cell_start[gid]; k < cell_start[gid + 1]; k++) {
+            const float4 p = pos[k];
+            nb_list[o++] = make_float4(p.x, p.y, p.z, __int_as_float(k));
+        }
+    }
+    if (c == n_grid - 1) nb_start[n_grid] = o;
+}
+
+// K nearest IPs of (x,y,z) among the 27 cells around cell (g0,g1,g2): one pass over the cell's neighbourhood list.
+// ks[] = positions in the cell-sorted arrays, nearest first; ties keep the earlier-visited IP (strict <), as the
+// reference's insertion does.  KMAX == 1 follows find_closest_IP: the own cell alone decides unless it is empty.
+template <int KMAX>
+__device__ __forceinline__ int nearest_list(const IpPack &P, const pn::BendCfg &c, float x, float y, float z, int g0, int g1, int g2,
+                                            int (&ks)[KMAX]) {
+    const int cell = (g2 * c.res[1] + g1) * c.res[0] + g0;
+    int s = __ldg(P.nb_start + cell);
+    const int e = __ldg(P.nb_start + cell + 1);
+    float bd[KMAX];
+#pragma unroll
+    for (int i = 0; i < KMAX; i++) { bd[i] = KMAX == 1 ? 9999.9f : FLT_MAX; ks[i] = -1; }
+    if (KMAX == 1) {
+        const int e_own = s + (__ldg(P.cell_start + cell + 1) - __ldg(P.cell_start + cell));
+        for (; s < e_own; s++) {
+            const float4 q = __ldg(P.nb_list + s);
+            const float d = (q.x - x) * (q.x - x) + (q.y - y) * (q.y - y) + (q.z - z) * (q.z - z);
+            if (d < bd[0]) { bd[0] = d; ks[0] = __float_as_int(q.w); }
+        }
+        if (ks[0] != -1) return 1;
+    }
+#pragma unroll 4
+    for (int k = s; k < e; k++) {
+        const float4 q = __ldg(P.nb_list + k);
+        const float d = (q.x - x) * (q.x - x) + (q.y - y) * (q.y - y) + (q.z - z) * (q.z - z);
+        if (d < bd[KMAX - 1]) {
+            const int id = __float_as_int(q.w);
+            if (KMAX == 1) {
+                bd[0] = d; ks[0] = id;
+            } else if (KMAX == 2) {
+                if (d < bd[0]) { bd[KMAX - 1] = bd[0]; ks[KMAX - 1] = ks[0]; bd[0] = d; ks[0] = id; }
+                else { bd[KMAX - 1] = d; ks[KMAX - 1] = id; }
+            } else {
+                if (d < bd[1 % KMAX]) {
+                    bd[KMAX - 1] = bd[1 % KMAX]; ks[KMAX - 1] = ks[1 % KMAX];
+                    if (d < bd[0]) { bd[1 % KMAX] = bd[0]; ks[1 % KMAX] = ks[0]; bd[0] = d; ks[0] = id; }
+                    else { bd[1 % KMAX] = d; ks[1 % KMAX] = id; }
+                } else { bd[KMAX - 1] = d; ks[KMAX - 1] = id; }
+            }
+        }
+    }
+    int found = 0;
+#pragma unroll
+    for (int i = 0; i < KMAX; i++) found += ks[i] != -1;
+    return found;
+}
 
 // Per-frame packing of the IP state in IP-grid cell order.  Finv uses the very arithmetic of the per-sample
 // inverse (pn::adjugate_inverse), so hoisting it out of the march loop changes no bit when max_iter_num == 1
@@ -121,10 +217,6 @@ __device__ __forceinline__ int nearest_sorted(const IpPack &P, const pn::BendCfg
     return found;
 }
 
-// (A flattened one-candidate-stream-per-lane formulation of this search was measured on B200: fewer warp
-//  instructions but a single dependent load per lane in flight — slower than the nested loops below, which the
-//  compiler unrolls by two.  Occupancy, not instruction count, is what the march kernel responds to.)
-#define PN_NEAREST nearest_sorted
 
 // bend_sample (march_device.cuh) over the packed, cell-sorted IP state.  Identical decisions and arithmetic.
 template <int KMAX>
@@ -136,14 +228,17 @@ __device__ __forceinline__ bool bend_sample_packed(const IpPack &P, const pn::Be
     int g2 = (int)floorf((z - c.bbmin[2]) / c.hgs);
     g0 = min(max(g0, 0), c.res[0] - 1); g1 = min(max(g1, 0), c.res[1] - 1); g2 = min(max(g2, 0), c.res[2] - 1);
     int ks[KMAX];
+#ifdef PN_SEARCH_SORTED   // A/B build: row-pruned search over cell_start (nearest_sorted)
     int n_ip;
     if (KMAX == 1) {
-        // find_closest_IP: own cell; the neighbours only if the own cell holds nothing closer than 9999.9
-        n_ip = PN_NEAREST<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, true, 9999.9f, ks);
-        if (n_ip == 0) n_ip = PN_NEAREST<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, false, 9999.9f, ks);
+        n_ip = nearest_sorted<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, true, 9999.9f, ks);
+        if (n_ip == 0) n_ip = nearest_sorted<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, false, 9999.9f, ks);
     } else {
-        n_ip = PN_NEAREST<KMAX>(P, c, rankA, x, y, z, g0, g1, g2, false, FLT_MAX, ks);
+        n_ip = nearest_sorted<KMAX>(P, c, rankA, x, y, z, g0, g1, g2, false, FLT_MAX, ks);
     }
+#else
+    int n_ip = nearest_list<KMAX>(P, c, x, y, z, g0, g1, g2, ks);
+#endif
     if (n_ip <= 0) return false;
     for (int k = 0; k < n_ip; k++) {  // boundary filter with the shrinking loop bound (raymarching.cu:1246-1251)
         const float4 q = __ldg(P.pos + ks[k < KMAX ? k : 0]);
