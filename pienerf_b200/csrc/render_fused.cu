@@ -575,7 +575,7 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
             else wave_field_kernel<<<sms, kWaveGroups * 128, smem, st>>>(A, Wv, p);
             if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk + 1], st));
             fk++;
-            wave_composite_kernel<<<div_up(N, 256u), 256, 0, st>>>(A, Wv, p, p == n_pass - 1);
+            wave_composite_kernel<<<min(div_up(N, 256u), sms * 8u), 256, 0, st>>>(A, Wv, p, p == n_pass - 1);
         }
         PN_LAUNCH_CHECK("wavefront passes");
         if (g_prof_stop) PN_CUDA(cudaEventRecord(g_prof_stop, st));

@@ -356,57 +356,70 @@ __global__ void __launch_bounds__(256) wave_composite_kernel(const RenderArgs A,
     const int n_alive = pass == 0 ? A.queue->n_active : Wv.ctl[pass].n_alive;
     const int *alive = pass == 0 ? A.active : Wv.alive[(pass - 1) & 1];
     int *alive_out = Wv.alive[pass & 1];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool survive = false;
-    int ray = -1;
-    long long kept = 0;
-    if (i < n_alive) {
-        ray = alive[i];
-        const int2 lk = Wv.link[ray];
-        const bool finished = Wv.rs_march[ray].w != 0.f;
-        const float near = A.nears[ray], far = A.fars[ray];
-        float ws = 0, dep = 0, cr = 0, cg = 0, cb = 0, tdepth = near, last_t = near;
-        if (pass > 0) {
-            const float4 a = Wv.rs_comp[2 * ray], b = Wv.rs_comp[2 * ray + 1];
-            ws = a.x; dep = a.y; cr = a.z; cg = a.w; cb = b.x; tdepth = b.y; last_t = b.z;
-        }
-        bool terminated = false;
-        int idx = lk.x;
-        for (int s = 0; s < lk.y; s++) {
-            if (s > 0) {
-                idx++;
-                if ((idx & (kSlab - 1)) == 0) idx = Wv.slab_next[idx / kSlab - 1];
-            }
-            const float4 o = Wv.out[idx];
-            const float ta = __int_as_float(Wv.meta[idx].y);
-            const float T = 1 - ws;                                         // raymarching.cu:890-906
-            const float w = o.x * T;
-            ws += w;
-            tdepth += ta - last_t;
-            last_t = ta;
-            dep += w * tdepth;
-            cr += w * o.y; cg += w * o.z; cb += w * o.w;
-            kept++;
-            if (T < A.T_thresh) { terminated = true; break; }
-        }
-        if (terminated || finished || last_pass) {
-            A.image[3 * ray] = cr + (1 - ws) * A.bg; A.image[3 * ray + 1] = cg + (1 - ws) * A.bg; A.image[3 * ray + 2] = cb + (1 - ws) * A.bg;
-            A.depth0[ray] = dep;
-            A.depth[ray] = fmaxf(dep - near, 0.f) / (far - near);
-            A.wsum[ray] = ws;
-        } else {
-            survive = true;
-            Wv.rs_comp[2 * ray] = make_float4(ws, dep, cr, cg);
-            Wv.rs_comp[2 * ray + 1] = make_float4(cb, tdepth, last_t, 0.f);
-        }
-    }
-    const uint32_t sm = __ballot_sync(0xffffffffu, survive);
     const int lane = threadIdx.x & 31;
-    if (sm) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&Wv.ctl[pass + 1].n_alive, __popc(sm));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (survive) alive_out[base + __popc(sm & ((1u << lane) - 1))] = ray;
+    long long kept = 0;
+    // grid-stride over the pass's rays, one warp-uniform trip count per warp (the survivor compaction votes)
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n_alive; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + lane;
+        bool survive = false;
+        int ray = -1;
+        if (i < n_alive) {
+            ray = alive[i];
+            const int2 lk = Wv.link[ray];
+            const bool finished = Wv.rs_march[ray].w != 0.f;
+            const float near = A.nears[ray], far = A.fars[ray];
+            float ws = 0, dep = 0, cr = 0, cg = 0, cb = 0, tdepth = near, last_t = near;
+            if (pass > 0) {
+                const float4 a = Wv.rs_comp[2 * ray], b = Wv.rs_comp[2 * ray + 1];
+                ws = a.x; dep = a.y; cr = a.z; cg = a.w; cb = b.x; tdepth = b.y; last_t = b.z;
+            }
+            bool terminated = false;
+            int idx = lk.x, rem = lk.y;
+            while (rem > 0 && !terminated) {
+                // rows of a ray are contiguous up to the end of a slab: 8 independent loads per step, then the recurrence
+                const int seg = min(rem, kSlab - (idx & (kSlab - 1)));
+                for (int s = 0; s < seg && !terminated; s += 8) {
+                    float4 o[8];
+                    float ta[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (s + j < seg) { o[j] = Wv.out[idx + s + j]; ta[j] = __int_as_float(Wv.meta[idx + s + j].y); }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (s + j < seg && !terminated) {
+                            const float T = 1 - ws;                             // raymarching.cu:890-906
+                            const float w = o[j].x * T;
+                            ws += w;
+                            tdepth += ta[j] - last_t;
+                            last_t = ta[j];
+                            dep += w * tdepth;
+                            cr += w * o[j].y; cg += w * o[j].z; cb += w * o[j].w;
+                            kept++;
+                            if (T < A.T_thresh) terminated = true;
+                        }
+                    }
+                }
+                rem -= seg; idx += seg;
+                if (rem > 0 && !terminated) idx = Wv.slab_next[idx / kSlab - 1];   // idx sits on a slab boundary here
+            }
+            if (terminated || finished || last_pass) {
+                A.image[3 * ray] = cr + (1 - ws) * A.bg; A.image[3 * ray + 1] = cg + (1 - ws) * A.bg; A.image[3 * ray + 2] = cb + (1 - ws) * A.bg;
+                A.depth0[ray] = dep;
+                A.depth[ray] = fmaxf(dep - near, 0.f) / (far - near);
+                A.wsum[ray] = ws;
+            } else {
+                survive = true;
+                Wv.rs_comp[2 * ray] = make_float4(ws, dep, cr, cg);
+                Wv.rs_comp[2 * ray + 1] = make_float4(cb, tdepth, last_t, 0.f);
+            }
+        }
+        const uint32_t sm = __ballot_sync(0xffffffffu, survive);
+        if (sm) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&Wv.ctl[pass + 1].n_alive, __popc(sm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (survive) alive_out[base + __popc(sm & ((1u << lane) - 1))] = ray;
+        }
     }
     for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
     if (lane == 0 && kept) atomicAdd((unsigned long long *)&Wv.counters[0], (unsigned long long)kept);
