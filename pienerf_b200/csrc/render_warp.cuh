@@ -93,23 +93,33 @@ __device__ __forceinline__ int nearest_list(const IpPack &P, const pn::BendCfg &
         }
         if (ks[0] != -1) return 1;
     }
-#pragma unroll 4
-    for (int k = s; k < e; k++) {
-        const float4 q = __ldg(P.nb_list + k);
-        const float d = (q.x - x) * (q.x - x) + (q.y - y) * (q.y - y) + (q.z - z) * (q.z - z);
-        if (d < bd[KMAX - 1]) {
-            const int id = __float_as_int(q.w);
-            if (KMAX == 1) {
-                bd[0] = d; ks[0] = id;
-            } else if (KMAX == 2) {
-                if (d < bd[0]) { bd[KMAX - 1] = bd[0]; ks[KMAX - 1] = ks[0]; bd[0] = d; ks[0] = id; }
-                else { bd[KMAX - 1] = d; ks[KMAX - 1] = id; }
-            } else {
-                if (d < bd[1 % KMAX]) {
-                    bd[KMAX - 1] = bd[1 % KMAX]; ks[KMAX - 1] = ks[1 % KMAX];
-                    if (d < bd[0]) { bd[1 % KMAX] = bd[0]; ks[1 % KMAX] = ks[0]; bd[0] = d; ks[0] = id; }
-                    else { bd[1 % KMAX] = d; ks[1 % KMAX] = id; }
-                } else { bd[KMAX - 1] = d; ks[KMAX - 1] = id; }
+#ifndef PN_LIST_BATCH
+#define PN_LIST_BATCH 8
+#endif
+    // PN_LIST_BATCH independent loads are issued before the first distance is needed (the list is L2-resident, the scan is
+    // latency-bound); indices past the end re-read the last entry and are masked out
+    for (int k = s; k < e; k += PN_LIST_BATCH) {
+        float4 qs[PN_LIST_BATCH];
+#pragma unroll
+        for (int j = 0; j < PN_LIST_BATCH; j++) qs[j] = __ldg(P.nb_list + min(k + j, e - 1));
+#pragma unroll
+        for (int j = 0; j < PN_LIST_BATCH; j++) {
+            const float4 q = qs[j];
+            const float d = (q.x - x) * (q.x - x) + (q.y - y) * (q.y - y) + (q.z - z) * (q.z - z);
+            if (k + j < e && d < bd[KMAX - 1]) {
+                const int id = __float_as_int(q.w);
+                if (KMAX == 1) {
+                    bd[0] = d; ks[0] = id;
+                } else if (KMAX == 2) {
+                    if (d < bd[0]) { bd[KMAX - 1] = bd[0]; ks[KMAX - 1] = ks[0]; bd[0] = d; ks[0] = id; }
+                    else { bd[KMAX - 1] = d; ks[KMAX - 1] = id; }
+                } else {
+                    if (d < bd[1 % KMAX]) {
+                        bd[KMAX - 1] = bd[1 % KMAX]; ks[KMAX - 1] = ks[1 % KMAX];
+                        if (d < bd[0]) { bd[1 % KMAX] = bd[0]; ks[1 % KMAX] = ks[0]; bd[0] = d; ks[0] = id; }
+                        else { bd[1 % KMAX] = d; ks[1 % KMAX] = id; }
+                    } else { bd[KMAX - 1] = d; ks[KMAX - 1] = id; }
+                }
             }
         }
     }
