@@ -112,7 +112,11 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    enqueue_s = [0.0]                                                        # host time spent enqueueing frames (all timed loops)
+    enqueue_n = [0]
+
     def timed(K, e2e, with_prof=False):
+        enqueue_n[0] += K
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         # per frame: (start, stop) around all render passes + one event pair per field-kernel launch (one per pass)
         pv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
@@ -128,7 +132,9 @@ def run_ours(args):
         for i in range(K):
             flush.fill_(float(i))                                             # evict L2 between timed frames (not timed)
             ev[i][0].record()
+            c0 = time.perf_counter()
             out = frame(e2e, pv[i] if pv else None)
+            enqueue_s[0] += time.perf_counter() - c0
             ev[i][1].record()
             samples0.append(out["stats"].clone())
         if e2e:
@@ -238,7 +244,7 @@ def run_ours(args):
                      "peak_source": src, "kernel_ms_per_frame": field_ms, "launches_per_frame": n_pass, "first_pass_launch_ms": field0_ms,
                      "algorithmic_bytes": f"{ALGO_BYTES_PER_SAMPLE_FUSED} B/sample x {evaluated:.0f} field evaluations per frame (summed over the frame's launches; rows incl. slab padding: {rows:.0f})",
                      "share_of_step": field_ms / (total_ms / K), "render_passes_ms_per_frame": render_ms},
-        "clocks": clocks, "wall_fps": K / wall,
+        "clocks": clocks, "wall_fps": K / wall, "host_enqueue_ms_per_frame": 1e3 * enqueue_s[0] / max(enqueue_n[0], 1),
     }
     line.update(extra)
     if world == 1 and not args.no_cpu_baseline:

@@ -64,6 +64,56 @@ def broadcast_ip_state(buf, src=0):
     return buf
 
 
+def ip_state_views(buf, n_ip):
+    """One flat fp32 buffer of 39 n floats = [pos n*3 | F n*9 | dF n*27]: the simulator writes its IP state straight into
+    these contiguous views and ONE broadcast of the flat buffer moves it — no pack / unpack copies."""
+    pos = buf[:3 * n_ip].view(n_ip, 3)
+    F = buf[3 * n_ip:12 * n_ip].view(n_ip, 9)
+    dF = buf[12 * n_ip:39 * n_ip].view(n_ip, 27)
+    return pos, F, dF
+
+
+class PlanarFrameGather:
+    """Copy-free variant of FrameGather.  Every rank renders straight into its send segment
+    [image n_max*3 | depth n_max | depth_0 n_max] (views handed to the renderer as `out=`), ONE gather moves the segments,
+    and rank 0 scatters them into the [H*W,5] frame with three index_copy_ calls over the concatenated pixel indices
+    (padding rows of the shorter segments land in a dummy row)."""
+
+    def __init__(self, parts, device):
+        self.parts, self.world = parts, len(parts)
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.n = len(parts[self.rank])
+        self.n_max = max(len(p) for p in parts)
+        self.n_pix = sum(len(p) for p in parts)
+        nm = self.n_max
+        self.send = torch.zeros(5 * nm, dtype=torch.float32, device=device)
+        self.out = {"image": self.send[:3 * nm].view(nm, 3)[:self.n], "depth": self.send[3 * nm:4 * nm][:self.n],
+                    "depth_0": self.send[4 * nm:5 * nm][:self.n], "weights_sum": torch.empty(self.n, dtype=torch.float32, device=device)}
+        if self.rank == 0 and self.world > 1:
+            self.recv = torch.zeros(self.world, 5 * nm, dtype=torch.float32, device=device)
+            self.recv_list = list(self.recv.unbind(0))
+            idx = np.full((self.world, nm), self.n_pix, dtype=np.int64)          # padding -> dummy row n_pix
+            for r, p in enumerate(parts):
+                idx[r, :len(p)] = p
+            self.index = torch.from_numpy(idx.reshape(-1)).to(device)
+            self.frame = {"image": torch.zeros(self.n_pix + 1, 3, dtype=torch.float32, device=device),
+                          "depth": torch.zeros(self.n_pix + 1, dtype=torch.float32, device=device),
+                          "depth_0": torch.zeros(self.n_pix + 1, dtype=torch.float32, device=device)}
+
+    def __call__(self):
+        """Returns {"image" [H*W,3], "depth" [H*W], "depth_0" [H*W]} on rank 0 (row-major pixels), None elsewhere."""
+        if self.world == 1:
+            return {k: self.out[k] for k in ("image", "depth", "depth_0")}      # the renderer's own outputs, no copy at all
+        dist.gather(self.send, self.recv_list if self.rank == 0 else None, dst=0)
+        if self.rank != 0:
+            return None
+        nm = self.n_max
+        self.frame["image"].index_copy_(0, self.index, self.recv[:, :3 * nm].reshape(-1, 3))
+        self.frame["depth"].index_copy_(0, self.index, self.recv[:, 3 * nm:4 * nm].reshape(-1))
+        self.frame["depth_0"].index_copy_(0, self.index, self.recv[:, 4 * nm:5 * nm].reshape(-1))
+        return {k: v[:self.n_pix] for k, v in self.frame.items()}
+
+
 class FrameGather:
     """Gathers per-rank [n_r, C] pixel rows into the full [H*W, C] framebuffer on rank 0."""
 

@@ -128,11 +128,15 @@ class DistFrameDriver:
         model.p_def, model.IP_F, model.IP_dF = IP_pos, IP_F, IP_dF
         model.IP_dx = sim.dx * 1.05
         self.W, self.H = opt.W, opt.H
-        self.ipbuf = torch.zeros(sim.n_ip, 39, dtype=torch.float32, device=self.dev)
+        from .dist import ip_state_views
+        self.ipbuf = torch.zeros(sim.n_ip * 39, dtype=torch.float32, device=self.dev)
+        self.ip_views = ip_state_views(self.ipbuf, sim.n_ip)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.sim_stream = torch.cuda.Stream(device=self.dev, priority=-1)
         self.overlap_sim = overlap_sim
-        self.host = [torch.empty(self.W * self.H, 5, dtype=torch.float32).pin_memory() for _ in range(2)] if self.rank == 0 else None
+        npx = self.W * self.H
+        self.host = [{"image": torch.empty(npx, 3, dtype=torch.float32).pin_memory(), "depth": torch.empty(npx, dtype=torch.float32).pin_memory(),
+                      "depth_0": torch.empty(npx, dtype=torch.float32).pin_memory()} for _ in range(2)] if self.rank == 0 else None
         self.copy_done = [None, None]
         self.frame_id = 0
         self.launches = 0
@@ -142,8 +146,8 @@ class DistFrameDriver:
         from .dist import FrameGather, tile_partition
         self.parts = tile_partition(self.H, self.W, self.world, self.tile, weights)
         self.my = torch.from_numpy(self.parts[self.rank]).to(self.dev)
-        self.gather = FrameGather(self.parts, 5, self.dev)
-        self.local = torch.empty(len(self.parts[self.rank]), 5, dtype=torch.float32, device=self.dev)
+        from .dist import PlanarFrameGather
+        self.gathers = [PlanarFrameGather(self.parts, self.dev) for _ in range(2)]   # double-buffered with the host frames
         self._rays = None
 
     def rays(self, pose_host, intrinsics):
@@ -159,22 +163,19 @@ class DistFrameDriver:
         """One GUI frame.  Returns (render outputs of this rank, index of the pinned host buffer or None)."""
         import torch.distributed as dist
         from . import _lib
-        from .dist import broadcast_ip_state, pack_ip_state, unpack_ip_state
+        from .dist import broadcast_ip_state
         if regenerate_rays or self._rays is None:                    # trainer.py:541-543: rays from the host pose every frame
             self._rays = self.rays(pose_host, intrinsics)
         rays_o, rays_d = self._rays
         step_done = None
         if not paused:
+            pos, F, dF = self.ip_views
             if self.rank == 0:
-                pos, F, dF = self.sim.get_IP_info()                      # state BEFORE the step (trainer.py:303-306)
+                self.sim.get_IP_info(out=self.ip_views)                  # state BEFORE the step (trainer.py:303-306)
                 self.launches += 1
-                if self.world > 1:
-                    pack_ip_state(pos, F, dF, self.ipbuf)
-                    self.launches += 3
             if self.world > 1:
                 broadcast_ip_state(self.ipbuf)                           # the other ranks start rendering at once ...
-                pos, F, dF = unpack_ip_state(self.ipbuf)
-                self.launches += 3
+                self.launches += 1
             if self.rank == 0:
                 # ... while rank 0 advances the simulator (trainer.py:308).  The frame renders the state read BEFORE the
                 # step, so the step only has to be ordered after that read: it runs on a high-priority side stream,
@@ -195,28 +196,28 @@ class DistFrameDriver:
             if len(profile_events) > 2:
                 arr = (_lib.vp * len(profile_events[2]))(*[e.cuda_event for e in profile_events[2]])
                 _lib.lib.pn_set_profile_event_list(arr, len(profile_events[2]))
-        out = self.model.render_deformed(rays_o, rays_d, **self.opt)
+        gather_frame = self.world > 1 or to_host
+        slot = self.frame_id & 1 if gather_frame else None
+        gat = self.gathers[slot] if gather_frame else None
+        if gather_frame and self.rank == 0 and self.copy_done[slot] is not None:
+            torch.cuda.current_stream().wait_event(self.copy_done[slot])    # frame k-2's host copy has read this slot's buffers
+        out = self.model.render_deformed(rays_o, rays_d, out=gat.out if gather_frame else None, **self.opt)
         self.launches += self.model._render_launches
         if profile_events is not None:
             _lib.lib.pn_set_profile_events(_lib.vp(0), _lib.vp(0))
             _lib.lib.pn_set_profile_event_list(None, 0)
-        slot = None
-        if self.world > 1 or to_host:
-            slot = self.frame_id & 1
-            if self.rank == 0 and self.copy_done[slot] is not None:
-                torch.cuda.current_stream().wait_event(self.copy_done[slot])   # frame buffer reuse hazard (k-2 copy finished?)
-            self.local[:, 0:3] = out["image"][0]; self.local[:, 3] = out["depth"][0]; self.local[:, 4] = out["depth_0"][0]
-            self.launches += 3
-            fb = self.gather(self.local)
+        if gather_frame:
+            fb = gat()                                                   # the renderer wrote straight into the send segment
+            if self.world > 1:
+                self.launches += 1 + (3 if self.rank == 0 else 0)
             if to_host and self.rank == 0:
                 ready = torch.cuda.Event(); ready.record()
                 with torch.cuda.stream(self.copy_stream):
                     self.copy_stream.wait_event(ready)
-                    self.host[slot].copy_(fb, non_blocking=True)             # trainer.py:589-593 .cpu().numpy() of the frame
+                    for k in ("image", "depth", "depth_0"):                 # trainer.py:589-593 .cpu().numpy() of the frame
+                        self.host[slot][k].copy_(fb[k], non_blocking=True)
                     done = torch.cuda.Event(); done.record()
                 self.copy_done[slot] = done
-                # the next gather may only overwrite `fb` after this copy has read it
-                self._fb_guard = done
         if step_done is not None:
             torch.cuda.current_stream().wait_event(step_done)           # frame k is complete only when step k is
         self.frame_id += 1

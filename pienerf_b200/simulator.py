@@ -18,7 +18,7 @@ torchfloat = torch.float64
 
 class Simulator:
     def __init__(self, dt=1e-2, iters=20, bbox=None, kres=7, dx=1, gravity=None, stiff=1e5, base=None,
-                 solver="inverse", pcg_iters=200, device="cuda"):
+                 solver="inverse", pcg_iters=200, device="cuda", use_graph=True):
         # solver.py:17-25: the reference scales the caller's tensors IN PLACE in the caller's dtype
         # (main_gui.py passes float32) — reproduce the rounding, not the aliasing bug (fresh tensors here).
         bbox = torch.tensor([1.0, 1.0, 1.0], dtype=torchfloat) if bbox is None else torch.as_tensor(bbox).clone()
@@ -37,9 +37,11 @@ class Simulator:
         self.kres = kres
         self.stiff = stiff
         self.solver = {"inverse": 0, "pcg": 1}[solver]
+        self.use_graph = use_graph
         self.pcg_iters = pcg_iters
         self.pos = self.mass = self.mu = self.lam = self.is_pin = None
         self._step_desc = None
+        self._graph = self._graph_key = self._graph_warm = None
 
     # ------------------------------------------------------------------ I/O (solver.py:109-137)
     def InitializeFromPly(self, path):
@@ -199,17 +201,42 @@ class Simulator:
         return self._step_desc
 
     @torch.no_grad()
-    def stepforward(self):
-        """solver.py:595-602: momentum, `iters` local-global iterations, damped velocity — one enqueue-only call."""
-        _qgmls.step(self._desc(), self.solver)
+    def stepforward(self, graph=None):
+        """solver.py:595-602: momentum, `iters` local-global iterations, damped velocity — one enqueue-only call.
+        The step is a fixed chain of 3 + 4*iters small kernels over buffers that never move, so after the first call it
+        is replayed as ONE CUDA graph launch (`graph=False` forces the plain enqueue; `self.use_graph` is the default)."""
+        use = self.use_graph if graph is None else graph
+        if not use or not self.dof.is_cuda:
+            _qgmls.step(self._desc(), self.solver)
+            return
+        key = (int(self.iters), int(self.pcg_iters), self.solver, self.dof.data_ptr(), self.dof_f.data_ptr())
+        if self._graph is None or self._graph_key != key:
+            if self._graph_warm != key:                                   # first call with this configuration: plain, warms everything up
+                _qgmls.step(self._desc(), self.solver)
+                self._graph_warm = key
+                return
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=self.dof.device)
+            side.wait_stream(cur)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    _qgmls.step(self._desc(), self.solver)            # captured, not executed
+            cur.wait_stream(side)
+            self._graph, self._graph_key = g, key
+        self._graph.replay()
 
     @torch.no_grad()
-    def get_IP_info(self):
-        """solver.py:402-424: (pos [n,3], F [n,9], dF [n,27]) float32 in the renderer's layouts."""
+    def get_IP_info(self, out=None):
+        """solver.py:402-424: (pos [n,3], F [n,9], dF [n,27]) float32 in the renderer's layouts.  `out` = three
+        preallocated contiguous tensors to fill (the multi-GPU driver passes views of its broadcast buffer)."""
         dev = self.device
-        pos = torch.empty(self.n_ip, 3, dtype=torch.float32, device=dev)
-        F = torch.empty(self.n_ip, 9, dtype=torch.float32, device=dev)
-        dF = torch.empty(self.n_ip, 27, dtype=torch.float32, device=dev)
+        if out is not None:
+            pos, F, dF = out
+        else:
+            pos = torch.empty(self.n_ip, 3, dtype=torch.float32, device=dev)
+            F = torch.empty(self.n_ip, 9, dtype=torch.float32, device=dev)
+            dF = torch.empty(self.n_ip, 27, dtype=torch.float32, device=dev)
         _qgmls.ip_info(self.IP_kernel, self.dof, self.IP_Nx, self.IP_dNx, self.IP_ddNx, pos, F, dF)
         return pos, F, dF
 

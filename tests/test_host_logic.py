@@ -97,6 +97,27 @@ def _worker(rank, world, port, q):
         frame = gather(full[torch.from_numpy(parts[rank])])
         if rank == 0:
             ok = ok and torch.equal(frame, full)
+        # the copy-free path of DistFrameDriver: IP state as views of one flat broadcast buffer, render outputs written
+        # into the gather's send segment, one scatter per channel group on rank 0 (uneven shares: 30 % / 70 %)
+        from pienerf_b200.dist import PlanarFrameGather, ip_state_views
+        flat = torch.zeros(39 * n)
+        pos, F, dF = ip_state_views(flat, n)
+        if rank == 0:
+            g = torch.Generator().manual_seed(1)
+            pos.copy_(torch.rand(n, 3, generator=g)); F.copy_(torch.rand(n, 9, generator=g)); dF.copy_(torch.rand(n, 27, generator=g))
+        broadcast_ip_state(flat)
+        g = torch.Generator().manual_seed(1)
+        ok = ok and torch.equal(pos, torch.rand(n, 3, generator=g)) and torch.equal(F, torch.rand(n, 9, generator=g)) and torch.equal(dF, torch.rand(n, 27, generator=g))
+        parts = tile_partition(H, W, world, tile=8, weights=[0.3, 0.7])
+        pg = PlanarFrameGather(parts, "cpu")
+        mine = torch.from_numpy(parts[rank])
+        img = torch.arange(H * W * 3, dtype=torch.float32).reshape(H * W, 3); dep = torch.arange(H * W, dtype=torch.float32) * 0.5
+        pg.out["image"].copy_(img[mine]); pg.out["depth"].copy_(dep[mine]); pg.out["depth_0"].copy_(-dep[mine])
+        fb = pg()
+        if rank == 0:
+            ok = ok and torch.equal(fb["image"], img) and torch.equal(fb["depth"], dep) and torch.equal(fb["depth_0"], -dep)
+        else:
+            ok = ok and fb is None
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
