@@ -360,7 +360,7 @@ int wave_capacity(uint32_t N) {
     long long c = 24ll * (long long)N;
     if (c < (1ll << 20)) c = 1ll << 20;
     if (c > (32ll << 20)) c = 32ll << 20;
-    return (int)(c / 256 * 256);
+    return (int)(c / 256 * 256);   // a multiple of every slab size and of the 128-row field tile
 }
 
 WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
@@ -386,7 +386,7 @@ WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
     w.alive0 = take(sizeof(int) * N); w.alive1 = take(sizeof(int) * N);
     w.rs_march = take(16 * (size_t)N); w.rs_comp = take(32 * (size_t)N); w.link = take(8 * (size_t)N);
     w.xyzdt = take(16 * (size_t)w.cap); w.meta = take(8 * (size_t)w.cap); w.out = take(16 * (size_t)w.cap);
-    w.slab_next = take(sizeof(int) * (size_t)(w.cap / 128));
+    w.slab_next = take(sizeof(int) * (size_t)(w.cap / 32));
     w.total = o;
     return w;
 }

@@ -3,7 +3,7 @@
 // The frame is rendered in a few device-resident passes; every pass is three launches on one stream, no host sync:
 //   wave_march_kernel      one warp = one ray at a time, 32 lanes = 32 consecutive lattice points (same exact
 //                          lattice/ballot replay as render_warp.cuh), inverse warp through the quadratic GMLS field,
-//                          occupancy test; kept samples are appended to a compact global sample list (slabs of 256
+//                          occupancy test; kept samples are appended to a compact global sample list (slabs of 32
 //                          rows handed out by one atomic each) — up to `pass_cap` samples per ray per pass;
 //   wave_field_kernel      THE hash-lookup + MLP pass: 128-row tiles of the sample list, 16-level hash-grid gather
 //                          straight into the bf16 hi/lo activation tile in shared memory, 5-layer MLP on tcgen05
@@ -23,9 +23,9 @@
 namespace {
 
 #ifndef PN_WAVE_SLAB
-#define PN_WAVE_SLAB 128
+#define PN_WAVE_SLAB 32
 #endif
-constexpr int kSlab = PN_WAVE_SLAB;   // sample rows per slab (a whole number of 128-row field tiles)
+constexpr int kSlab = PN_WAVE_SLAB;   // sample rows per slab: the allocation unit of a march warp (a field tile = 128 rows of whatever slabs)
 constexpr int kMaxPass = 8;
 #ifndef PN_WAVE_GROUPS
 #define PN_WAVE_GROUPS 4         // 128-row tile groups per field CTA
@@ -202,10 +202,10 @@ __global__ void __launch_bounds__(kWaveGroups * 128, 1) wave_field_kernel(const 
     pn::tc::group_sync(group);
     const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
     uint32_t phase = 0;
-    const int n_tiles = n_rows / 128;                                   // slabs are whole tiles
+    const int n_tiles = (n_rows + 127) / 128;                           // rows past n_rows in the last tile were never written
     for (int tile = blockIdx.x * kWaveGroups + group; tile < n_tiles; tile += gridDim.x * kWaveGroups) {
         const int i = tile * 128 + row;
-        const int2 mt = Wv.meta[i];
+        const int2 mt = i < n_rows ? Wv.meta[i] : make_int2(-1, 0);
         const bool valid = mt.x >= 0;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         float dx = 0, dy = 0, dz = 1;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
     __syncthreads();
     pn::tc::tc_fence_after();
     const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
-    const int n_tiles = n_rows / 128;                                   // slabs are whole tiles
+    const int n_tiles = (n_rows + 127) / 128;                           // rows past n_rows in the last tile were never written
     // the j-th tile of this CTA is tile blockIdx.x + j * gridDim.x and lives in stage j % kWsStages
     if (wg >= kWsCons) {
         // ---------------------------------------------------------------- producer
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
         for (int j = pg; blockIdx.x + j * (int)gridDim.x < n_tiles; j += kWsProd) {
             const int tile = blockIdx.x + j * gridDim.x, st = j % kWsStages, use = j / kWsStages;
             const int i = tile * 128 + row;
-            const int2 mt = Wv.meta[i];
+            const int2 mt = i < n_rows ? Wv.meta[i] : make_int2(-1, 0);
             const bool valid = mt.x >= 0;
             float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) sm = Wv.xyzdt[i];
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
         for (int j = cg; blockIdx.x + j * (int)gridDim.x < n_tiles; j += kWsCons) {
             const int tile = blockIdx.x + j * gridDim.x, st = j % kWsStages, use = j / kWsStages;
             const int i = tile * 128 + row;
-            const int2 mt = Wv.meta[i];
+            const int2 mt = i < n_rows ? Wv.meta[i] : make_int2(-1, 0);
             const bool valid = mt.x >= 0;
             float dt = 0.f, dx = 0, dy = 0, dz = 1;
             if (valid) {
