@@ -227,7 +227,7 @@ def run_ours(args):
     samp, evaluated, rows = float(st[0]), float(st[2]), float(st[3])
     achieved = evaluated * ALGO_BYTES_PER_SAMPLE_FUSED / (field_ms * 1e-3) / 1e9
     line = {
-        "metric": "simulated+rendered frames/s at 800x800", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "metric": f"simulated+rendered frames/s at {W}x{H}", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 render / f64 sim",
         "data": "synthetic", "impl": "ours",
         "config": {"workload": f"{args.config}: {sim.n_ip}-IP Q-GMLS body ({sim.n_k} kernels, sim_iters {sim.iters}) + {W}x{H} deformed render, "
