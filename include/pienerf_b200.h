@@ -132,7 +132,7 @@ int pn_set_profile_events(void *start_event, void *stop_event);
 /* Same for mode 3: events[2k], events[2k+1] (cudaEvent_t) bracket the k-th field-kernel launch of a frame, k < n/2;
  * the pair of pn_set_profile_events then brackets all passes.  (NULL, 0) disables.  The array must stay alive. */
 int pn_set_profile_event_list(void **events, int n);
-/* number of (march, field, composite) passes mode 3 enqueues for a per-ray sample cap of max_steps (pass caps 64, 128, ...
+/* number of (march, field, composite) passes mode 3 enqueues for a per-ray sample cap of max_steps (pass caps 32, 64, ...
  * plus one spare pass for the < 32-sample overshoot of a pass) */
 int pn_render_pass_count(uint32_t max_steps);
 /* bytes of scratch pn_render_deformed needs for N rays, n_vtx IPs, scene bound and IP-grid cell size hgs */

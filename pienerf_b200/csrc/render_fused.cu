@@ -484,9 +484,12 @@ extern "C" int pn_set_profile_events(void *start, void *stop) {
     return PN_OK;
 }
 
+#ifndef PN_WAVE_FIRST_CAP
+#define PN_WAVE_FIRST_CAP 32   // samples per ray in the first pass (doubles every pass): saturating rays waste <= one 32-sample chunk
+#endif
 extern "C" int pn_render_pass_count(uint32_t max_steps) {
     int n_pass = 0, covered = 0;
-    for (int cap_p = 64; covered < (int)max_steps && n_pass < kMaxPass - 1; cap_p *= 2) { covered += cap_p; n_pass++; }
+    for (int cap_p = PN_WAVE_FIRST_CAP; covered < (int)max_steps && n_pass < kMaxPass - 1; cap_p *= 2) { covered += cap_p; n_pass++; }
     return n_pass + 1;
 }
 
@@ -562,7 +565,7 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
         const uint32_t sms = (uint32_t)pn_sm_count_cached();
         // pass caps 64, 128, ... until the per-ray cap is covered; one spare pass absorbs the <32-sample overshoot per pass
         const int n_pass = pn_render_pass_count(d->max_steps);
-        int cap_p = 64, fk = 0;
+        int cap_p = PN_WAVE_FIRST_CAP, fk = 0;
         if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
         for (int p = 0; p < n_pass; p++, cap_p *= 2) {
             switch (d->num_seek_IP) {

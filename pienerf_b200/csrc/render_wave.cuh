@@ -11,7 +11,7 @@
 //   wave_composite_kernel  one thread = one ray: the reference's sequential front-to-back recurrence over the ray's
 //                          samples of this pass (raymarching.cu:862-913), early termination, survivors are compacted
 //                          into the next pass's ray list.
-// pass_cap doubles every pass (64, 128, ...), so a saturating ray wastes at most ~64 field evaluations (the reference's
+// pass_cap doubles every pass (32, 64, ...), so a saturating ray wastes at most ~32-63 field evaluations (the reference's
 // wavefront loop has the same property with n_step <= 8 per iteration) while fog rays need only a handful of passes.
 // Why three kernels instead of one fused one: marching (divergent neighbour search, ~100 registers), the field
 // (gather-bound, 16-20 warps per SM of tensor-core tiles) and compositing (a scalar recurrence) want different
@@ -50,7 +50,7 @@ struct WaveArgs {
 
 // --------------------------------------------------------------------------------------------- march
 #ifndef PN_MARCH_MINB
-#define PN_MARCH_MINB 3   // 24 warps / SM at 80 registers (a few spills) beat 16 warps at 128: the search is latency-bound
+#define PN_MARCH_MINB 4   // 32 warps / SM at 64 registers (some spills) beat 24 at 80 and 16 at 128: the list scan is latency-bound
 #endif
 template <int KMAX>
 __global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const RenderArgs A, const IpPack P, const WaveArgs Wv, int pass, int pass_cap) {
