@@ -558,12 +558,10 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
         Wv.xyzdt = (float4 *)(base + w.xyzdt); Wv.meta = (int2 *)(base + w.meta); Wv.out = (float4 *)(base + w.out);
         Wv.slab_next = (int *)(base + w.slab_next); Wv.cap = w.cap;
         PN_CUDA(cudaMemsetAsync(base + w.ctl, 0, 16 * 16 + 256, st));       // ctl + counters (adjacent, 256-byte aligned blocks)
-        // PN_FIELD_KERNEL=1 selects the unspecialised field kernel (A/B only); default: producer/consumer warp roles
-        static const int field_ws = [] { const char *e = getenv("PN_FIELD_KERNEL"); return !(e && e[0] == '1'); }();
-        const size_t smem = (field_ws ? sizeof(WaveWsSmem) : sizeof(WaveFieldSmem)) + 128;
-        if (int rc = field_ws ? set_smem(wave_field_ws_kernel, smem) : set_smem(wave_field_kernel, smem)) return rc;
+        const size_t smem = sizeof(WaveWsSmem) + 128;
+        if (int rc = set_smem(wave_field_ws_kernel, smem)) return rc;
         const uint32_t sms = (uint32_t)pn_sm_count_cached();
-        // pass caps 64, 128, ... until the per-ray cap is covered; one spare pass absorbs the <32-sample overshoot per pass
+        // pass caps 32, 64, ... until the per-ray cap is covered; one spare pass absorbs the <32-sample overshoot per pass
         const int n_pass = pn_render_pass_count(d->max_steps);
         int cap_p = PN_WAVE_FIRST_CAP, fk = 0;
         if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
@@ -574,8 +572,7 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
                 default: wave_march_kernel<3><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
             }
             if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk], st));
-            if (field_ws) wave_field_ws_kernel<<<sms, (kWsProd + kWsCons) * 128, smem, st>>>(A, Wv, p);
-            else wave_field_kernel<<<sms, kWaveGroups * 128, smem, st>>>(A, Wv, p);
+            wave_field_ws_kernel<<<sms, (kWsProd + kWsCons) * 128, smem, st>>>(A, Wv, p);
             if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk + 1], st));
             fk++;
             wave_composite_kernel<<<min(div_up(N, 256u), sms * 8u), 256, 0, st>>>(A, Wv, p, p == n_pass - 1);

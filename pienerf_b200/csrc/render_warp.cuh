@@ -154,101 +154,16 @@ __global__ void __launch_bounds__(256) ip_pack_kernel(const float *__restrict__ 
     r[15] = 0.f;
 }
 
-__device__ __forceinline__ bool key_less(float d, int r, float d2, int r2) { return d < d2 || (d == d2 && r < r2); }
-
-// Nearest-K search over the 27 cells around (g0,g1,g2) with the reference's semantics (raymarching.cu:986-1118):
-// candidates are ranked by (distance^2, order in which the reference would have visited them) so that exact ties
-// resolve as the reference's strict-less insertion does, independent of our traversal order.
-// rank[27] maps (dz+1)*9+(dy+1)*3+(dx+1) -> visit order of that cell.  Returns the number of slots filled;
-// ks[] are positions in the cell-sorted arrays.
-template <int KMAX>
-__device__ __forceinline__ int nearest_sorted(const IpPack &P, const pn::BendCfg &c, const unsigned char *rank, float x,
-                                              float y, float z, int g0, int g1, int g2, bool own_cell_only, float dmax,
-                                              int (&ks)[KMAX]) {
-    float bd[KMAX];
-    int br[KMAX];
-#pragma unroll
-    for (int i = 0; i < KMAX; i++) { bd[i] = dmax; br[i] = 0x7fffffff; ks[i] = -1; }
-    const int lo = max(g0 - 1, 0), hi = min(g0 + 1, c.res[0] - 1);
-    const int nb = hi - lo + 1, own = g0 - lo;                             // nb in 1..3 cells, own in 0..1
-    // conservative lower bounds on the distance to the neighbouring rows of cells (an IP lies inside its cell up to
-    // rounding of the cell assignment, hence the margin): a row whose bound already exceeds the current K-th best
-    // cannot change the result, ties included (strict >), so skipping it is exact.
-    const float eps = 1e-5f;
-    const float yl = fmaxf(y - (c.bbmin[1] + g1 * c.hgs) - eps, 0.f), yh = fmaxf((c.bbmin[1] + (g1 + 1) * c.hgs) - y - eps, 0.f);
-    const float zl = fmaxf(z - (c.bbmin[2] + g2 * c.hgs) - eps, 0.f), zh = fmaxf((c.bbmin[2] + (g2 + 1) * c.hgs) - z - eps, 0.f);
-#pragma unroll 1
-    for (int it = 0; it < 9; it++) {
-        // own row first so the bounds tighten early; the visiting order does not affect the result (rank keys)
-        const int dz = (it == 0) ? 0 : ((it <= 2) ? 0 : (it <= 5 ? -1 : 1));
-        const int dy = (it == 0) ? 0 : ((it == 1) ? -1 : (it == 2 ? 1 : ((it - 3) % 3) - 1));
-        if (own_cell_only && it != 0) break;
-        const int a1 = g1 + dy, a2 = g2 + dz;
-        if (a1 < 0 || a1 >= c.res[1] || a2 < 0 || a2 >= c.res[2]) continue;
-        const float gy = dy < 0 ? yl : (dy > 0 ? yh : 0.f), gz = dz < 0 ? zl : (dz > 0 ? zh : 0.f);
-        if (gy * gy + gz * gz > bd[KMAX - 1]) continue;
-        const int row = (a2 * c.res[1] + a1) * c.res[0];
-        // cells lo..hi of a row are contiguous in the cell-sorted array: one range, <= 4 boundaries
-        int b[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) b[j] = (j <= nb) ? __ldg(P.cell_start + row + lo + j) : 0x7fffffff;
-        int first = b[0], last = nb == 3 ? b[3] : (nb == 2 ? b[2] : b[1]);
-        if (own_cell_only) { first = own == 0 ? b[0] : b[1]; last = own == 0 ? b[1] : b[2]; }
-        for (int k = first; k < last; k++) {
-            const float4 q = __ldg(P.pos + k);
-            const float d = (q.x - x) * (q.x - x) + (q.y - y) * (q.y - y) + (q.z - z) * (q.z - z);
-            if (d > bd[KMAX - 1]) continue;                                // the common case: not among the K best
-            const int cell = lo + (k >= b[1]) + (k >= b[2]);              // which of the <=3 cells this entry is in
-            const int cbeg = cell == lo ? b[0] : (cell == lo + 1 ? b[1] : b[2]);
-            const int r = ((int)rank[(dz + 1) * 9 + (dy + 1) * 3 + (cell - g0 + 1)] << 8) + (k - cbeg);
-            if (KMAX == 1) {
-                if (key_less(d, r, bd[0], br[0])) { bd[0] = d; br[0] = r; ks[0] = k; }
-            } else if (KMAX == 2) {
-                if (key_less(d, r, bd[KMAX - 1], br[KMAX - 1])) {
-                    if (key_less(d, r, bd[0], br[0])) { bd[KMAX - 1] = bd[0]; br[KMAX - 1] = br[0]; ks[KMAX - 1] = ks[0]; bd[0] = d; br[0] = r; ks[0] = k; }
-                    else { bd[KMAX - 1] = d; br[KMAX - 1] = r; ks[KMAX - 1] = k; }
-                }
-            } else {
-                if (key_less(d, r, bd[KMAX - 1], br[KMAX - 1])) {
-                    if (key_less(d, r, bd[1 % KMAX], br[1 % KMAX])) {
-                        bd[KMAX - 1] = bd[1 % KMAX]; br[KMAX - 1] = br[1 % KMAX]; ks[KMAX - 1] = ks[1 % KMAX];
-                        if (key_less(d, r, bd[0], br[0])) {
-                            bd[1 % KMAX] = bd[0]; br[1 % KMAX] = br[0]; ks[1 % KMAX] = ks[0];
-                            bd[0] = d; br[0] = r; ks[0] = k;
-                        } else { bd[1 % KMAX] = d; br[1 % KMAX] = r; ks[1 % KMAX] = k; }
-                    } else { bd[KMAX - 1] = d; br[KMAX - 1] = r; ks[KMAX - 1] = k; }
-                }
-            }
-        }
-    }
-    int found = 0;
-#pragma unroll
-    for (int i = 0; i < KMAX; i++) found += ks[i] != -1;
-    return found;
-}
-
-
 // bend_sample (march_device.cuh) over the packed, cell-sorted IP state.  Identical decisions and arithmetic.
 template <int KMAX>
-__device__ __forceinline__ bool bend_sample_packed(const IpPack &P, const pn::BendCfg &c, const unsigned char *rankA,
-                                                   const unsigned char *rankB, float &x, float &y, float &z) {
+__device__ __forceinline__ bool bend_sample_packed(const IpPack &P, const pn::BendCfg &c, float &x, float &y, float &z) {
     if (c.cut && !(x > c.cb[0] && x < c.cb[1] && y > c.cb[2] && x < c.cb[3] && z > c.cb[4] && z < c.cb[5])) return true;
     int g0 = (int)floorf((x - c.bbmin[0]) / c.hgs);
     int g1 = (int)floorf((y - c.bbmin[1]) / c.hgs);
     int g2 = (int)floorf((z - c.bbmin[2]) / c.hgs);
     g0 = min(max(g0, 0), c.res[0] - 1); g1 = min(max(g1, 0), c.res[1] - 1); g2 = min(max(g2, 0), c.res[2] - 1);
     int ks[KMAX];
-#ifdef PN_SEARCH_SORTED   // A/B build: row-pruned search over cell_start (nearest_sorted)
-    int n_ip;
-    if (KMAX == 1) {
-        n_ip = nearest_sorted<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, true, 9999.9f, ks);
-        if (n_ip == 0) n_ip = nearest_sorted<KMAX>(P, c, rankB, x, y, z, g0, g1, g2, false, 9999.9f, ks);
-    } else {
-        n_ip = nearest_sorted<KMAX>(P, c, rankA, x, y, z, g0, g1, g2, false, FLT_MAX, ks);
-    }
-#else
     int n_ip = nearest_list<KMAX>(P, c, x, y, z, g0, g1, g2, ks);
-#endif
     if (n_ip <= 0) return false;
     for (int k = 0; k < n_ip; k++) {  // boundary filter with the shrinking loop bound (raymarching.cu:1246-1251)
         const float4 q = __ldg(P.pos + ks[k < KMAX ? k : 0]);
@@ -345,7 +260,6 @@ __global__ void __launch_bounds__(TC ? kTcGroups * 128 : 128, TC ? 1 : 3) render
     RenderTcSmem &TS = *reinterpret_cast<RenderTcSmem *>(smem_raw);
     const int group = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0), row = threadIdx.x & 127;  // provably warp-uniform
     WarpShared *wsh_all = reinterpret_cast<WarpShared *>(smem_raw + (((TC ? sizeof(RenderTcSmem) : sizeof(pn::FieldBlockSmem)) + 127) & ~size_t(127)));
-    __shared__ unsigned char rankA[27], rankB[27];
     uint32_t phase = 0;
     if constexpr (TC) {
         pn::tc::weights_fill(TS.w, A.field);
@@ -356,16 +270,6 @@ __global__ void __launch_bounds__(TC ? kTcGroups * 128 : 128, TC ? 1 : 3) render
         pn::tc::tc_fence_before();
     } else {
         pn::field_smem_fill(fs, A.field);
-    }
-    if (threadIdx.x < 27) {
-        // visit order of each of the 27 cells in the reference's two search routines (0 = own cell)
-        const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
-        int ra = 0, rb = 0;
-        for (int q = 0; q < 26; q++) {
-            if (pn::kNeigh[q][0] == dx && pn::kNeigh[q][1] == dy && pn::kNeigh[q][2] == dz) ra = q + 1;  // (x,y,z) offsets
-            if (pn::kNeigh[q][0] == dz && pn::kNeigh[q][1] == dy && pn::kNeigh[q][2] == dx) rb = q + 1;  // (z,y,x) offsets
-        }
-        rankA[threadIdx.x] = (unsigned char)ra; rankB[threadIdx.x] = (unsigned char)rb;
     }
     pn::BendCfg bc = A.bend;
 #pragma unroll
@@ -431,7 +335,7 @@ __global__ void __launch_bounds__(TC ? kTcGroups * 128 : 128, TC ? 1 : 3) render
             bool emit = false;
             if (need) {
                 pn::deformed_sample(bc, ox, oy, oz, dx, dy, dz, t, x, y, z);
-                const bool found = bend_sample_packed<KMAX>(P, bc, rankA, rankB, x, y, z);
+                const bool found = bend_sample_packed<KMAX>(P, bc, x, y, z);
                 const bool occ = pn::occupancy_and_exit(m, x, y, z, t, dt, dx, dy, dz, rdx, rdy, rdz, tt);
                 emit = occ && found;
             }

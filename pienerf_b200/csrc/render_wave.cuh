@@ -5,9 +5,9 @@
 //                          lattice/ballot replay as render_warp.cuh), inverse warp through the quadratic GMLS field,
 //                          occupancy test; kept samples are appended to a compact global sample list (slabs of 32
 //                          rows handed out by one atomic each) — up to `pass_cap` samples per ray per pass;
-//   wave_field_kernel      THE hash-lookup + MLP pass: 128-row tiles of the sample list, 16-level hash-grid gather
-//                          straight into the bf16 hi/lo activation tile in shared memory, 5-layer MLP on tcgen05
-//                          with TMEM accumulators (field_tc.cuh), writes (alpha, r, g, b) per sample;
+//   wave_field_ws_kernel   THE hash-lookup + MLP pass: 128-row tiles of the sample list; producer warps gather the 16
+//                          hash-grid levels into a shared-memory ring, consumer warps run the 5-layer MLP on tcgen05
+//                          with activations and accumulators in TMEM (field_tc.cuh); writes (alpha, r, g, b) per sample;
 //   wave_composite_kernel  one thread = one ray: the reference's sequential front-to-back recurrence over the ray's
 //                          samples of this pass (raymarching.cu:862-913), early termination, survivors are compacted
 //                          into the next pass's ray list.
@@ -27,10 +27,6 @@ namespace {
 #endif
 constexpr int kSlab = PN_WAVE_SLAB;   // sample rows per slab: the allocation unit of a march warp (a field tile = 128 rows of whatever slabs)
 constexpr int kMaxPass = 8;
-#ifndef PN_WAVE_GROUPS
-#define PN_WAVE_GROUPS 4         // 128-row tile groups per field CTA
-#endif
-constexpr int kWaveGroups = PN_WAVE_GROUPS;
 
 struct PassCtl { int n_alive; int next; int n_reserved; int pad; };
 
@@ -54,16 +50,6 @@ struct WaveArgs {
 #endif
 template <int KMAX>
 __global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const RenderArgs A, const IpPack P, const WaveArgs Wv, int pass, int pass_cap) {
-    __shared__ unsigned char rankA[27], rankB[27];
-    if (threadIdx.x < 27) {
-        const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
-        int ra = 0, rb = 0;
-        for (int q = 0; q < 26; q++) {
-            if (pn::kNeigh[q][0] == dx && pn::kNeigh[q][1] == dy && pn::kNeigh[q][2] == dz) ra = q + 1;
-            if (pn::kNeigh[q][0] == dz && pn::kNeigh[q][1] == dy && pn::kNeigh[q][2] == dx) rb = q + 1;
-        }
-        rankA[threadIdx.x] = (unsigned char)ra; rankB[threadIdx.x] = (unsigned char)rb;
-    }
     pn::BendCfg bc = A.bend;
 #pragma unroll
     for (int i = 0; i < 3; i++) { bc.bbmin[i] = A.geom->bbmin[i]; bc.bbmax[i] = A.geom->bbmax[i]; bc.hi[i] = A.geom->hi[i]; bc.res[i] = A.geom->res[i]; }
@@ -107,7 +93,7 @@ __global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const Re
             bool emit = false;
             if (need) {
                 pn::deformed_sample(bc, ox, oy, oz, dx, dy, dz, t, x, y, z);
-                const bool found = bend_sample_packed<KMAX>(P, bc, rankA, rankB, x, y, z);
+                const bool found = bend_sample_packed<KMAX>(P, bc, x, y, z);
                 const bool occ = pn::occupancy_and_exit(m, x, y, z, t, dt, dx, dy, dz, rdx, rdy, rdz, tt);
                 emit = occ && found;
             }
@@ -177,59 +163,7 @@ __global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const Re
 }
 
 // --------------------------------------------------------------------------------------------- field
-struct __align__(128) WaveFieldSmem {
-    pn::tc::Weights w;
-    pn::tc::TileSmem tile[kWaveGroups];
-    uint32_t tmem_base;
-};
-
-__global__ void __launch_bounds__(kWaveGroups * 128, 1) wave_field_kernel(const RenderArgs A, const WaveArgs Wv, int pass) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    WaveFieldSmem &S = *reinterpret_cast<WaveFieldSmem *>(smem_raw);
-    const int group = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0), row = threadIdx.x & 127;
-    const int n_rows = min(Wv.ctl[pass].n_reserved, Wv.cap);
-    if (n_rows == 0) return;
-    pn::tc::TileSmem &T = S.tile[group];
-    pn::tc::weights_fill(S.w, A.field);
-    if (row == 0) pn::tc::mbar_init(&T.bar, 1);
-    pn::tc::fence_barrier_init();
-    if (threadIdx.x < 32) pn::tc::tmem_alloc(&S.tmem_base, 512);
-    pn::tc::fence_async_smem();
-    pn::tc::tc_fence_before();
-    __syncthreads();
-    pn::tc::tc_fence_after();
-    if (row == 0) T.tmem = S.tmem_base + group * pn::tc::kTmemCols;
-    pn::tc::group_sync(group);
-    const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
-    uint32_t phase = 0;
-    const int n_tiles = (n_rows + 127) / 128;                           // rows past n_rows in the last tile were never written
-    for (int tile = blockIdx.x * kWaveGroups + group; tile < n_tiles; tile += gridDim.x * kWaveGroups) {
-        const int i = tile * 128 + row;
-        const int2 mt = i < n_rows ? Wv.meta[i] : make_int2(-1, 0);
-        const bool valid = mt.x >= 0;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        float dx = 0, dy = 0, dz = 1;
-        if (valid) {
-            s = Wv.xyzdt[i];
-            dx = __ldg(A.rays_d + 3 * mt.x); dy = __ldg(A.rays_d + 3 * mt.x + 1); dz = __ldg(A.rays_d + 3 * mt.x + 2);
-        }
-        float sh[16];
-        pn::sh_eval<4>(dx, dy, dz, sh);
-        pn::tc::encode_to_tile(T, S.w, table, A.field.bound, row, valid, s.x, s.y, s.z);
-        float sigma, r, g, b;
-        pn::tc::mlp_tile(T, S.w, group, row, sh, phase, sigma, r, g, b);
-        if (valid) {
-            sigma = A.density_scale * sigma;
-            Wv.out[i] = make_float4(1.0f - __expf(-sigma * s.w), r, g, b);
-        }
-    }
-    pn::tc::tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x < 32) pn::tc::tmem_dealloc(S.tmem_base, 512);
-}
-
-// --------------------------------------------------------------------------------------------- field, warp-specialised
-// Same work as wave_field_kernel, split by role inside one persistent CTA per SM:
+// One persistent CTA per SM, warps split by role:
 //   producer groups (4 warps = 128 rows each): hash-grid gather only — 32 gathers in flight per thread
 //                   (encode_rows_ilp) — writing the [128,32] bf16 hi/lo input of sigma_net[0] into a ring of stages;
 //   consumer groups (4 warps each): the five tensor-core layers; layer 1 reads its A operand straight from the ring
