@@ -436,6 +436,16 @@ __device__ __forceinline__ void mlp_tile_ts(TileT &t, const Weights &w, int grou
     tc_fence_before();
 }
 
+// ---- TMA (1-D bulk copy global -> shared, completion on an mbarrier)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {   // 16-byte multiples
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -444,61 +454,67 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // choice is a select, not a branch), then the 32 gathers are issued back to back, then interpolated, split and stored
 // as one 16-byte k-chunk of the hi and of the lo image at `hi_row`/`lo_row` (+ chunk * 2048).  Requires every level to
 // be dense or a power-of-two hash table (Weights::fast); same vertices, weights and summation order as lookup3_c2.
+// `L0S`: level 0 (chunk 0, j == 0) is read from its shared-memory copy `lvl0` instead of global memory.
+template <bool L0S>
+__device__ __forceinline__ void encode_chunk_ilp(int c4, char *hi_row, char *lo_row, const Weights &w, const float2 *__restrict__ table,
+                                                 const float2 *lvl0, bool in, float u, float vv, float ww) {
+    float fr[4][3];
+    // (one 128-bit load per x-neighbour pair that shares an aligned slot was measured here too: 3.5 vs 2.5 ms per
+    //  frame — 128-bit gathers cost more L1 wavefronts than they save; plain 64-bit gathers.)
+    uint32_t idx[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int l = 4 * c4 + j;
+        const LevelGeom g = w.geo[l];
+        const uint32_t off = w.level_off[l];   // entry offsets stay 32-bit (whole table < 2^32 entries): one IMAD.WIDE per gather
+        float px = u * g.scale + 0.5f, py = vv * g.scale + 0.5f, pz = ww * g.scale + 0.5f;
+        const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+        fr[j][0] = px - fx; fr[j][1] = py - fy; fr[j][2] = pz - fz;
+        const uint32_t gx = (uint32_t)fx, gy = (uint32_t)fy, gz = (uint32_t)fz;
+        const uint32_t s1 = g.stride1, s2 = g.stride1 * g.stride1;
+        const uint32_t dy0 = gy * s1, dz0 = gz * s2;
+        const uint32_t hy0 = gy * 2654435761u, hz0 = gz * 805459861u;
+        // per-axis terms: dense -> added, hashed -> xored; (v+1)*P == v*P + P mod 2^32
+        const uint32_t ty0 = g.dense3 ? dy0 : hy0, ty1 = g.dense3 ? dy0 + s1 : hy0 + 2654435761u;
+        const uint32_t tz0 = g.dense3 ? dz0 : hz0, tz1 = g.dense3 ? dz0 + s2 : hz0 + 805459861u;
+        const uint32_t m = g.dense3 ? 0xffffffffu : g.mask;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint32_t tx = gx + (c & 1), ty = (c & 2) ? ty1 : ty0, tz = (c & 4) ? tz1 : tz0;
+            const uint32_t id = g.dense3 ? (tx + ty + tz) : ((tx ^ ty ^ tz) & m);
+            idx[j][c] = in ? id + off : 0u;
+        }
+    }
+    float2 v[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) v[j][c] = (L0S && j == 0) ? lvl0[idx[j][c]] : __ldg(table + idx[j][c]);   // level 0 starts at entry 0
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float px = fr[j][0], py = fr[j][1], pz = fr[j][2];
+        const float qx = 1.0f - px, qy = 1.0f - py, qz = 1.0f - pz;
+        const float w00 = qx * qy, w10 = px * qy, w01 = qx * py, w11 = px * py;
+        const float wt[8] = {w00 * qz, w10 * qz, w01 * qz, w11 * qz, w00 * pz, w10 * pz, w01 * pz, w11 * pz};
+        float2 e = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 8; c++) { e.x += wt[c] * v[j][c].x; e.y += wt[c] * v[j][c].y; }
+        if (!in) e = make_float2(0.f, 0.f);
+        split_pair(e.x, e.y, hw[j], lw[j]);
+    }
+    *reinterpret_cast<uint4 *>(hi_row + c4 * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4 *>(lo_row + c4 * 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
 __device__ __forceinline__ void encode_rows_ilp(char *hi_row, char *lo_row, const Weights &w, const float2 *__restrict__ table, float bound,
-                                                bool valid, float x, float y, float z) {
+                                                bool valid, float x, float y, float z, const float2 *lvl0 = nullptr) {
     const float inv = 1.0f / (2 * bound);
     const float u = (x + bound) * inv, vv = (y + bound) * inv, ww = (z + bound) * inv;
     const bool in = valid && !(u < 0 || u > 1 || vv < 0 || vv > 1 || ww < 0 || ww > 1);
+    if (lvl0) encode_chunk_ilp<true>(0, hi_row, lo_row, w, table, lvl0, in, u, vv, ww);
+    else encode_chunk_ilp<false>(0, hi_row, lo_row, w, table, nullptr, in, u, vv, ww);
 #pragma unroll 1
-    for (int c4 = 0; c4 < 4; c4++) {
-        float fr[4][3];
-        // (one 128-bit load per x-neighbour pair that shares an aligned slot was measured here too: 3.5 vs 2.5 ms per
-        //  frame — 128-bit gathers cost more L1 wavefronts than they save; plain 64-bit gathers.)
-        uint32_t idx[4][8];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int l = 4 * c4 + j;
-            const LevelGeom g = w.geo[l];
-            const uint32_t off = w.level_off[l];   // entry offsets stay 32-bit (whole table < 2^32 entries): one IMAD.WIDE per gather
-            float px = u * g.scale + 0.5f, py = vv * g.scale + 0.5f, pz = ww * g.scale + 0.5f;
-            const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-            fr[j][0] = px - fx; fr[j][1] = py - fy; fr[j][2] = pz - fz;
-            const uint32_t gx = (uint32_t)fx, gy = (uint32_t)fy, gz = (uint32_t)fz;
-            const uint32_t s1 = g.stride1, s2 = g.stride1 * g.stride1;
-            const uint32_t dy0 = gy * s1, dz0 = gz * s2;
-            const uint32_t hy0 = gy * 2654435761u, hz0 = gz * 805459861u;
-            // per-axis terms: dense -> added, hashed -> xored; (v+1)*P == v*P + P mod 2^32
-            const uint32_t ty0 = g.dense3 ? dy0 : hy0, ty1 = g.dense3 ? dy0 + s1 : hy0 + 2654435761u;
-            const uint32_t tz0 = g.dense3 ? dz0 : hz0, tz1 = g.dense3 ? dz0 + s2 : hz0 + 805459861u;
-            const uint32_t m = g.dense3 ? 0xffffffffu : g.mask;
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const uint32_t tx = gx + (c & 1), ty = (c & 2) ? ty1 : ty0, tz = (c & 4) ? tz1 : tz0;
-                const uint32_t id = g.dense3 ? (tx + ty + tz) : ((tx ^ ty ^ tz) & m);
-                idx[j][c] = in ? id + off : 0u;
-            }
-        }
-        float2 v[4][8];
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int c = 0; c < 8; c++) v[j][c] = __ldg(table + idx[j][c]);
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float px = fr[j][0], py = fr[j][1], pz = fr[j][2];
-            const float qx = 1.0f - px, qy = 1.0f - py, qz = 1.0f - pz;
-            const float w00 = qx * qy, w10 = px * qy, w01 = qx * py, w11 = px * py;
-            const float wt[8] = {w00 * qz, w10 * qz, w01 * qz, w11 * qz, w00 * pz, w10 * pz, w01 * pz, w11 * pz};
-            float2 e = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < 8; c++) { e.x += wt[c] * v[j][c].x; e.y += wt[c] * v[j][c].y; }
-            if (!in) e = make_float2(0.f, 0.f);
-            split_pair(e.x, e.y, hw[j], lw[j]);
-        }
-        *reinterpret_cast<uint4 *>(hi_row + c4 * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4 *>(lo_row + c4 * 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-    }
+    for (int c4 = 1; c4 < 4; c4++) encode_chunk_ilp<false>(c4, hi_row, lo_row, w, table, nullptr, in, u, vv, ww);
 }
 
 // Encode one sample and store its 32 features (k = 2*level, 2*level+1; chunks 0..3) for sigma_net[0].  Zero row for

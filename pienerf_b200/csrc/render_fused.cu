@@ -214,7 +214,7 @@ struct RenderArgs {
 
 template <int KMAX>
 __global__ void __launch_bounds__(128, 3) render_persistent(const RenderArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     pn::FieldBlockSmem &fbs = *reinterpret_cast<pn::FieldBlockSmem *>(smem_raw);
     pn::FieldSmem &fs = fbs.w;
     float *scratch = fbs.scratch + threadIdx.x;
@@ -331,7 +331,7 @@ __global__ void copy_stats_kernel(const FrameQueue *q, long long *stats) {
 __global__ void __launch_bounds__(128, 3) field_forward_kernel(const pn_field_t f, const float *__restrict__ xyzs,
                                                                const float *__restrict__ dirs, uint32_t M,
                                                                float *__restrict__ sigmas, float *__restrict__ rgbs) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     pn::FieldBlockSmem &fbs = *reinterpret_cast<pn::FieldBlockSmem *>(smem_raw);
     pn::FieldSmem &fs = fbs.w;
     float *scratch = fbs.scratch + threadIdx.x;
@@ -348,9 +348,10 @@ __global__ void __launch_bounds__(128, 3) field_forward_kernel(const pn_field_t 
     }
 }
 
+constexpr size_t kWeightsImageBytes = 48 * 1024;   // >= sizeof(pn::tc::Weights), checked in render_wave.cuh
 struct WorkspaceLayout {
     size_t geom, queue, nears, fars, active, pig_cnt, pig_bgn, pig_fill, pig_idx, ip_pos, ip_rec, nb_cnt, nb_start, nb_fill, nb_list;
-    size_t ctl, alive0, alive1, rs_march, rs_comp, link, xyzdt, meta, out, slab_next, counters;   // wavefront mode
+    size_t ctl, alive0, alive1, rs_march, rs_comp, link, xyzdt, meta, out, slab_next, counters, weights_img;   // wavefront mode
     int cap;
     size_t total;
 };
@@ -383,6 +384,7 @@ WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
     w.cap = wave_capacity(N);
     w.ctl = take(16 * 16);
     w.counters = take(64);
+    w.weights_img = take(kWeightsImageBytes);
     w.alive0 = take(sizeof(int) * N); w.alive1 = take(sizeof(int) * N);
     w.rs_march = take(16 * (size_t)N); w.rs_comp = take(32 * (size_t)N); w.link = take(8 * (size_t)N);
     w.xyzdt = take(16 * (size_t)w.cap); w.meta = take(8 * (size_t)w.cap); w.out = take(16 * (size_t)w.cap);
@@ -557,6 +559,8 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
         Wv.rs_march = (float4 *)(base + w.rs_march); Wv.rs_comp = (float4 *)(base + w.rs_comp); Wv.link = (int2 *)(base + w.link);
         Wv.xyzdt = (float4 *)(base + w.xyzdt); Wv.meta = (int2 *)(base + w.meta); Wv.out = (float4 *)(base + w.out);
         Wv.slab_next = (int *)(base + w.slab_next); Wv.cap = w.cap;
+        Wv.weights_img = (const pn::tc::Weights *)(base + w.weights_img);
+        field_weights_kernel<<<1, 256, 0, st>>>(A.field, (pn::tc::Weights *)(base + w.weights_img));
         PN_CUDA(cudaMemsetAsync(base + w.ctl, 0, 16 * 16 + 256, st));       // ctl + counters (adjacent, 256-byte aligned blocks)
         const size_t smem = sizeof(WaveWsSmem) + 128;
         if (int rc = set_smem(wave_field_ws_kernel, smem)) return rc;

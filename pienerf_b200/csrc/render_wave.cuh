@@ -41,6 +41,7 @@ struct WaveArgs {
     float4 *out;           // [cap] alpha r g b
     int *slab_next;        // [cap / kSlab] row at which a warp's sample stream continues after this slab
     long long *counters;   // [0] composited samples, [1] emitted samples
+    const pn::tc::Weights *weights_img;   // bf16 hi/lo weight images + level geometry, built once per frame (field_weights_kernel)
     int cap;               // rows available per pass
 };
 
@@ -163,6 +164,10 @@ __global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const Re
 }
 
 // --------------------------------------------------------------------------------------------- field
+// the weight image every field CTA fetches with one TMA bulk copy (instead of converting the fp32 weights per CTA per launch)
+static_assert(sizeof(pn::tc::Weights) <= kWeightsImageBytes && sizeof(pn::tc::Weights) % 16 == 0, "weight image: workspace slot / TMA size");
+__global__ void __launch_bounds__(256) field_weights_kernel(const pn_field_t f, pn::tc::Weights *out) { pn::tc::weights_fill(*out, f); }
+
 // One persistent CTA per SM, warps split by role:
 //   producer groups (4 warps = 128 rows each): hash-grid gather only — 32 gathers in flight per thread
 //                   (encode_rows_ilp) — writing the [128,32] bf16 hi/lo input of sigma_net[0] into a ring of stages;
@@ -186,8 +191,16 @@ using WsTile = pn::tc::TileSmem;                                    // A/B build
 #else
 struct WsTile { uint64_t bar; uint32_t tmem; uint32_t pad; };       // activations live in TMEM: only the barrier + TMEM base
 #endif
+#ifndef PN_WS_LVL0
+#define PN_WS_LVL0 0            // 1: also stage hash level 0 (<= 4920 entries, 39 KB) in shared memory by TMA
+#endif
+constexpr int kLvl0Entries = 4920;
 struct __align__(128) WaveWsSmem {
     pn::tc::Weights w;
+#if PN_WS_LVL0
+    float2 lvl0[kLvl0Entries];
+#endif
+    uint64_t wbar;
     WsTile tile[kWsCons];
     WsStage stage[kWsStages];
     uint64_t full[kWsStages], empty[kWsStages];
@@ -200,18 +213,36 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
     const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0), row = threadIdx.x & 127, lane = threadIdx.x & 31;
     const int n_rows = min(Wv.ctl[pass].n_reserved, Wv.cap);
     if (n_rows == 0) return;
-    pn::tc::weights_fill(S.w, A.field);
+    const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
     if (threadIdx.x == 0) {
         for (int s = 0; s < kWsStages; s++) { pn::tc::mbar_init(&S.full[s], 4); pn::tc::mbar_init(&S.empty[s], 1); }
         for (int g = 0; g < kWsCons; g++) pn::tc::mbar_init(&S.tile[g].bar, 1);
+        pn::tc::mbar_init(&S.wbar, 1);
+        pn::tc::fence_barrier_init();
+        // TMA: the 41 KB weight image (bf16 hi/lo of the five layers + level geometry) — and the coarsest table level —
+        // arrive as bulk copies while the other threads allocate TMEM; one mbarrier counts the bytes
+        uint32_t bytes = (uint32_t)sizeof(pn::tc::Weights);
+#if PN_WS_LVL0
+        const uint32_t l0 = (uint32_t)(A.field.offsets[1] - A.field.offsets[0]);
+        const bool stage0 = l0 <= (uint32_t)kLvl0Entries && (l0 & 1u) == 0;
+        if (stage0) bytes += l0 * 8u;
+#endif
+        pn::tc::mbar_expect_tx(&S.wbar, bytes);
+        pn::tc::tma_load_1d(&S.w, Wv.weights_img, (uint32_t)sizeof(pn::tc::Weights), &S.wbar);
+#if PN_WS_LVL0
+        if (stage0) pn::tc::tma_load_1d(S.lvl0, table, l0 * 8u, &S.wbar);
+#endif
     }
-    pn::tc::fence_barrier_init();
     if (threadIdx.x < 32) pn::tc::tmem_alloc(&S.tmem_base, kWsCons <= 2 ? 256 : 512);
-    pn::tc::fence_async_smem();
     pn::tc::tc_fence_before();
     __syncthreads();
     pn::tc::tc_fence_after();
-    const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
+    pn::tc::mbar_wait(&S.wbar, 0);
+#if PN_WS_LVL0
+    const float2 *lvl0 = ((uint32_t)(A.field.offsets[1] - A.field.offsets[0]) <= (uint32_t)kLvl0Entries && S.w.geo[0].dense3) ? S.lvl0 : nullptr;
+#else
+    const float2 *lvl0 = nullptr;
+#endif
     const int n_tiles = (n_rows + 127) / 128;                           // rows past n_rows in the last tile were never written
     // the j-th tile of this CTA is tile blockIdx.x + j * gridDim.x and lives in stage j % kWsStages
     if (wg >= kWsCons) {
@@ -227,7 +258,7 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
             pn::tc::mbar_wait(&S.empty[st], (use & 1) ^ 1);               // stage free (a fresh barrier passes at once)
             char *hi = reinterpret_cast<char *>(S.stage[st].a[0]) + row * 16, *lo = reinterpret_cast<char *>(S.stage[st].a[1]) + row * 16;
             if (S.w.fast) {
-                pn::tc::encode_rows_ilp(hi, lo, S.w, table, A.field.bound, valid, sm.x, sm.y, sm.z);
+                pn::tc::encode_rows_ilp(hi, lo, S.w, table, A.field.bound, valid, sm.x, sm.y, sm.z, lvl0);
             } else {
                 // generic table shapes: per-level path (tiled grids, non power-of-two hash sizes)
                 const float inv = 1.0f / (2 * A.field.bound);

@@ -335,7 +335,7 @@ class NeRFNetwork(nn.Module):
             out = {"image": torch.empty(N, 3, dtype=torch.float32, device=device), "depth": torch.empty(N, dtype=torch.float32, device=device),
                    "depth_0": torch.empty(N, dtype=torch.float32, device=device), "weights_sum": torch.empty(N, dtype=torch.float32, device=device)}
         # kernels this call enqueues: bbox, 4 x IP grid, frame setup, IP pack, 3 x neighbourhood lists, (3 per pass | 1 fused), stats
-        self._render_launches = 11 + (3 * int(lib.pn_render_pass_count(int(max_steps))) if mode == 3 else 1)
+        self._render_launches = 11 + (1 + 3 * int(lib.pn_render_pass_count(int(max_steps))) if mode == 3 else 1)
         f = self._field_struct()
         check(lib.pn_render_deformed(C.byref(f), C.byref(d), dptr(rays_o), dptr(rays_d), N, dptr(out["image"]), dptr(out["depth"]),
                                      dptr(out["depth_0"]), dptr(out["weights_sum"]), dptr(self._workspace), need, dptr(self._stats),

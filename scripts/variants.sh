@@ -1,4 +1,4 @@
-for t in "" cap128 cap32 minb4; do
+for t in "" lvl0; do
   if [ -z "$t" ]; then L=""; else L="PN_LIB=$PWD/pienerf_b200/lib/libpienerf_b200_$t.so"; fi
-  echo "== variant ${t:-default}"; env $L timeout 200 python scripts/mode_compare.py 3 1.0 2>&1 | tail -1 | cut -c1-120; env $L timeout 200 python scripts/mode_compare.py 3 50.0 2>&1 | tail -1 | cut -c1-120
+  echo "== variant ${t:-default}"; env $L timeout 200 python scripts/mode_compare.py 0,3 1.0 2>&1 | tail -1 | cut -c1-150; env $L timeout 200 python scripts/mode_compare.py 0,3 50.0 2>&1 | tail -1 | cut -c1-150
 done
