@@ -2,15 +2,17 @@
 //
 // Replaces the host-driven wavefront loop of nerf/renderer.py:755-907 (rund_cuda) and the torch / Warp glue
 // around it (nerf/utils.py:55-138 get_rays, :355-443 get_pnts_in_grids, renderer.py:782-797 bbox + near/far)
-// with four launches and no host synchronisation:
+// with one enqueue-only call and no host synchronisation:
 //   1. ip_bbox_kernel        bbox of deformed IP centres -> bbmin/bbmax/resolution (device)
 //   2. ip_grid_*             deterministic counting sort of IPs into the hgs grid
 //   3. frame_setup_kernel    near/far, output init, compaction of the rays that hit the IP box
-//   4. render_persistent     one lane = one ray until it dies, then the lane pulls the next ray from a global
-//                            queue (warp-aggregated atomic): march -> inverse warp -> 16-level hash encode ->
-//                            sigma/colour MLP -> composite, all in registers, weights in shared memory.
-// The per-ray sample sequence is exactly the reference's (the wavefront loop only batches it differently), so
-// images agree to MLP rounding; see DESIGN.md for the one documented deviation (per-ray cap = max_steps).
+//   4. ip_pack / nb_*        cell-sorted IP records (with F^-1) and the per-cell neighbourhood lists (render_warp.cuh)
+//   5. the render itself     mode 3 (product path): wavefront passes of march / field / composite kernels (render_wave.cuh)
+//                            mode 0/1: one fused persistent kernel, warp = ray (render_warp.cuh)
+//                            mode 2: render_persistent below, one lane = one ray with the reference's own search order
+//                            (slow; kept as the in-tree cross-check of the march decisions)
+// The per-ray sample sequence is exactly the reference's in every mode (the reference's loop only batches it
+// differently), so images agree to MLP rounding; see DESIGN.md for the documented deviations (per-ray cap = max_steps).
 #include <cstdlib>
 #include "field_device.cuh"
 #include "march_device.cuh"
