@@ -42,7 +42,7 @@ class ClockSampler:
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -240,7 +240,7 @@ def run_ours(args):
         "gpu_launches": n_launch,
         "roofline": {"kernel": "wave_field_ws_kernel (16-level hash-grid gather + tcgen05 MLP over 128-row sample tiles; one launch per wavefront pass)",
                      "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": 164.5e6, "traffic_note": "dram__bytes_read+write of the first-pass launch (3.9 M rows, 4.1 GB algorithmic) in profiles/r1_ncu_summary.txt; the 46.7 MiB table is L2-resident",
+                     "traffic": 96.1e6, "traffic_note": "dram__bytes_read+write of the first-pass launch (2.15 M rows, 2.2 GB algorithmic) in profiles/r1_ncu_summary.txt; the 46.7 MiB table is L2-resident",
                      "peak_source": src, "kernel_ms_per_frame": field_ms, "launches_per_frame": n_pass, "first_pass_launch_ms": field0_ms,
                      "algorithmic_bytes": f"{ALGO_BYTES_PER_SAMPLE_FUSED} B/sample x {evaluated:.0f} field evaluations per frame (summed over the frame's launches; rows incl. slab padding: {rows:.0f})",
                      "share_of_step": field_ms / (total_ms / K), "render_passes_ms_per_frame": render_ms},
@@ -306,7 +306,7 @@ def run_reference(args):
     orc.initialize(body["pos"], body["mass"], body["mu"], body["lam"], body["pin"])
     field = make_field(bound=cfg["bound"]); bits = occupancy_bitfield(body["pos"], 0.6 * cfg["sim_dx"], bound=cfg["bound"])
     pose = orbit_pose(radius=cfg["radius"]); intr = orbit_intrinsics(cfg["W"], cfg["H"], cfg["fovy"])
-    common = {"metric": "simulated+rendered frames/s at 800x800", "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K,
+    common = {"metric": f"simulated+rendered frames/s at {cfg['W']}x{cfg['H']}", "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K,
               "warmup": Wm, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 render / f64 sim", "data": "synthetic",
               "impl": "reference"}
     have_gpu = torch.cuda.is_available()
