@@ -95,3 +95,14 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
                 assert "sim_oracle" not in txt and "render_oracle" not in txt and "_ref_" not in txt, f
+
+
+def test_pass_count_and_workspace_are_host_only_queries():
+    """pn_render_pass_count / pn_render_workspace_bytes need no GPU: pass caps 32, 64, ... cover max_steps, plus one spare pass."""
+    from pienerf_b200._lib import lib
+    want = {48: 3, 256: 5, 300: 5, 1024: 7, 4096: 8}      # 32+64 | 32..256 = 480 | 32..1024 = 2016 | capped at kMaxPass
+    for max_steps, n in want.items():
+        assert lib.pn_render_pass_count(max_steps) == n, (max_steps, lib.pn_render_pass_count(max_steps))
+    small = lib.pn_render_workspace_bytes(1000, 100, 1.0, 0.06)
+    big = lib.pn_render_workspace_bytes(640000, 2028, 1.0, 0.06)
+    assert 0 < small < big < (2 << 30)
