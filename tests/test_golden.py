@@ -90,3 +90,30 @@ def test_plain_march_and_composite_golden(G):
     live = alive >= 0
     assert np.abs(t[live] - G["cp_t"][live]).max() < 1e-6 if live.any() else True
     assert np.abs(ws - G["cp_ws"]).max() < 2e-6 and np.abs(dp - G["cp_depth"]).max() < 1e-5 and np.abs(im - G["cp_image"]).max() < 2e-6
+
+
+@pytest.mark.parametrize("tag", ["undeformed_K3", "deformed_K3", "deformed_K1"])
+def test_whole_frame_golden(tag):
+    """The numpy rund_cuda (the checker of every frame-level parity test) against frames rendered by the REFERENCE GPU
+    renderer — its CUDA kernels, its loop, fp32 nn.Linear MLP (tests/golden/make_golden_frame.py, made on a B200).
+    BASELINE.json's bar: RGB within 1e-3 absolute; a knife-edge silhouette pixel may flip."""
+    import os
+    from tests.util import deformed_ip_state, small_scene
+    R = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_frame.npz"))
+    W, H = int(R["W"]), int(R["H"])
+    amp, K, ds = R[f"{tag}_cfg"]
+    body, field, bits, pose, intr = small_scene(W=W, H=H, seed=0)
+    p_ori, p_def, F, dF = deformed_ip_state(body, seed=0, amp=float(amp))
+    rays_o, rays_d = ro.get_rays(pose, intr, H, W)
+    got = ro.rund_cuda(ro.OracleField(field), rays_o, rays_d, p_def, p_ori, F, dF, 0.0525, bits, 1.0, 1, min_near=0.2,
+                       density_scale=float(ds), dt_gamma=0.0, max_steps=256, T_thresh=1e-2, max_iter_num=1, hash_grid_size=0.06,
+                       num_seek_IP=int(K), return_stats=True)
+    want_img, want_ws = R[f"{tag}_image"], R[f"{tag}_weights_sum"]
+    hit = want_ws > 0
+    assert hit.sum() > 100
+    assert abs(got["n_samples"] - int(R[f"{tag}_n_samples"])) <= 0.005 * int(R[f"{tag}_n_samples"]) + 2
+    err = np.abs(got["image"] - want_img).max(-1)
+    assert (err > 1e-3).mean() <= 0.005, (err > 1e-3).mean()
+    assert np.median(err[hit]) < 5e-5
+    assert (np.abs(got["weights_sum"] - want_ws) > 1e-3).mean() <= 0.005
+    assert (np.abs(got["depth_0"] - R[f"{tag}_depth_0"]) > 2e-3).mean() <= 0.005
