@@ -87,6 +87,10 @@ int pn_composite_rays_train_backward(void);
 /* nerf/utils.py:55-138 get_rays (N=-1, B=1): pose_host = 16 floats row-major cam2world (HOST). */
 int pn_get_rays(const float *pose_host, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, float *rays_o,
                 float *rays_d, void *stream);
+/* Same rays for a subset of the pixels with the camera in DEVICE memory (so the launch can live in a CUDA graph):
+ * cam [20] f32 = pose (16, row-major cam2world) | fx fy cx cy; pix [n_rays] i32 row-major pixel indices (NULL: all H*W). */
+int pn_get_rays_pix(const float *cam, uint32_t H, uint32_t W, const int *pix, uint32_t n_rays, float *rays_o,
+                    float *rays_d, void *stream);
 /* nerf/utils.py:355-443 get_pnts_in_grids: deterministic counting sort (ascending IP index inside a
  * cell; the reference's order is atomic-race dependent).  bbmin [3] f32 and resolution [3] i32 are DEVICE
  * arrays as in the reference call; n_grid = res0*res1*res2 sizes pig_cnt/pig_bgn [n_grid]; pig_idx [n_vtx]. */
@@ -115,8 +119,10 @@ int pn_field_forward(const pn_field_t *field_host, const float *xyzs, const floa
  * inverse warp, samples appended to a compact list), the field kernel (hash-grid gather + tcgen05 MLP over 128-row
  * tiles) and a per-ray compositor; modes 0-2 = single fused persistent kernels (0: tcgen05 MLP, 1: fp32 SIMT MLP,
  * 2: one lane per ray).  Outputs image [N,3], depth [N], depth_0 [N], weights_sum [N] as rund_cuda returns them.
- * stats (optional, device int64[4]): [0] composited samples, [1] rays that hit the aabb, [2] field evaluations,
- * [3] rows the field kernel processed (mode 3; samples + slab padding). */
+ * stats (optional, device int64[8]): [0] composited samples, [1] rays that hit the aabb, [2] field evaluations,
+ * [3] rows the field kernel processed (mode 3; samples + slab padding), [4] error bits (1: the deformed IP bbox needed more
+ * grid cells than the workspace holds and was clamped — diverged body; 2: rays were cut short because the sample list and
+ * the passes ran out), [5] number of such rays, [6] chunks a full sample list deferred to a later pass, [7] 0. */
 typedef struct {
     const float *p_def, *p_ori, *F_IP, *dF_IP; int n_vtx; float IP_dx;
     const uint8_t *density_bitfield; float bound; uint32_t cascade; uint32_t grid_size;
@@ -126,6 +132,46 @@ typedef struct {
 int pn_render_deformed(const pn_field_t *field_host, const pn_deform_t *deform_host, const float *rays_o,
                        const float *rays_d, uint32_t N, float *image, float *depth, float *depth_0, float *weights_sum,
                        void *workspace, uint64_t workspace_bytes, long long *stats, int mode, void *stream);
+/* The same frame as one rank's share of a multi-GPU frame (trainer.py:284-329 ordering is the caller's):
+ * io->pix [N] maps ray -> pixel of the frame-sized image / depth / depth_0 (which may be PEER memory: another GPU's frame
+ * opened with pn_peer_open — the compositor's stores then cross NVLink and no gather is needed); weights_sum stays [N].
+ * io->epoch: device counter of this frame slot, bumped by the first kernel of the call; the call then waits until every
+ * *wait_flag[i] >= epoch (flags in THIS GPU's memory, raised by a peer: "this frame's IP state has landed") and, after
+ * the last output is written, stores epoch into every signal_flag[i] (usually one word in the frame owner's memory).
+ * A wait that exceeds timeout_ms stores a nonzero code in *status and lets the stream continue (no GPU hang).
+ * wait_flag / signal_flag are DEVICE arrays of pointers.  io == NULL: plain pn_render_deformed. */
+typedef struct {
+    const int *pix;
+    uint32_t *epoch;
+    const uint32_t *const *wait_flag; int n_wait;
+    uint32_t *const *signal_flag; int n_signal;
+    int *status; uint32_t timeout_ms;
+} pn_frame_io_t;
+int pn_render_deformed_ex(const pn_field_t *field_host, const pn_deform_t *deform_host, const float *rays_o,
+                          const float *rays_d, uint32_t N, float *image, float *depth, float *depth_0,
+                          float *weights_sum, void *workspace, uint64_t workspace_bytes, long long *stats, int mode,
+                          const pn_frame_io_t *io_host, void *stream);
+
+/* ---------------------------------------------------------------- D. peer memory (multi-GPU frame)
+ * The reference is single-GPU; these replace the NCCL broadcast / gather a straightforward port would use for the
+ * frame's two exchanges (IP state out, pixels back) with stores into peer memory + epoch flags.
+ * pn_peer_alloc: zero-filled cudaMalloc memory that can be exported; pn_peer_export / pn_peer_open: CUDA IPC handle
+ * (64 bytes) out / in — the opened pointer is valid in kernels of the opening process (NVLink peer access enabled
+ * lazily).  All three synchronise the device; they are set-up calls. */
+int pn_peer_alloc(uint64_t bytes, void **ptr);
+int pn_peer_free(void *ptr);
+int pn_peer_export(void *ptr, unsigned char *handle64_host);
+int pn_peer_open(const unsigned char *handle64_host, void **ptr);
+int pn_peer_close(void *ptr);
+/* One launch: copy `bytes` (multiple of 16) from src into each of the n_dst destinations (device array of pointers,
+ * local or peer) with 128-bit stores. */
+int pn_peer_put(const void *src, uint64_t bytes, void *const *dsts_dev, int n_dst, void *stream);
+/* Epoch flags.  wait: (bump ? ++*epoch : *epoch) = e, then spin until *flags[i] + lag >= e for all i (timeout -> *status).
+ * signal: system-scope fence, then *flags[i] = *epoch for all i.  flags_dev: device array of (local or peer) pointers. */
+int pn_epoch_wait(uint32_t *epoch, int bump, const uint32_t *const *flags_dev, int n_flags, uint32_t lag, int *status,
+                  uint32_t timeout_ms, void *stream);
+int pn_epoch_signal(const uint32_t *epoch, uint32_t *const *flags_dev, int n_flags, void *stream);
+
 /* Optional profiling hook: two cudaEvent_t (as void*) that pn_render_deformed records on its stream right
  * around the persistent render kernel (NULL, NULL disables).  Used by bench.py for the roofline line. */
 int pn_set_profile_events(void *start_event, void *stop_event);

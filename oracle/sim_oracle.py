@@ -1,7 +1,8 @@
 """ctypes front-end for oracle/sim_oracle.c -- TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
-legs may import this module.  PARITY UNPINNED (see sim_oracle.c header).
+legs may import this module.  Parity pinned by fixtures generated from the reference's own source
+(tests/golden/make_golden_sim.py, tests/test_sim_golden.py; see the sim_oracle.c header).
 
 Mirrors the reference `Simulator` API (simulator/solver.py:12-617) closely
 enough that parity tests read like reference usage.

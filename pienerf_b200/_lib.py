@@ -34,6 +34,11 @@ class DeformT(C.Structure):
                 ("bg_color", f32)]
 
 
+class FrameIoT(C.Structure):
+    _fields_ = [("pix", vp), ("epoch", vp), ("wait_flag", vp), ("n_wait", i32), ("signal_flag", vp), ("n_signal", i32),
+                ("status", vp), ("timeout_ms", u32)]
+
+
 class QgmlsStepT(C.Structure):
     _fields_ = [("n_ip", i32), ("n_k", i32), ("iters", i32), ("dt", f64), ("dx", f64),
                 ("topo", vp), ("mu", vp), ("lam", vp), ("dNx", vp), ("adj_bgn", vp), ("adj", vp), ("adj_slices", i32),
@@ -68,6 +73,16 @@ _PROTOS = {
     "pn_ip_bbox": (i32, [vp, i32, f32, i32, f32, vp, vp, vp, vp]),
     "pn_field_forward": (i32, [C.POINTER(FieldT), vp, vp, u32, vp, vp, i32, vp]),
     "pn_render_deformed": (i32, [C.POINTER(FieldT), C.POINTER(DeformT), vp, vp, u32, vp, vp, vp, vp, vp, u64, vp, i32, vp]),
+    "pn_render_deformed_ex": (i32, [C.POINTER(FieldT), C.POINTER(DeformT), vp, vp, u32, vp, vp, vp, vp, vp, u64, vp, i32, C.POINTER(FrameIoT), vp]),
+    "pn_get_rays_pix": (i32, [vp, u32, u32, vp, u32, vp, vp, vp]),
+    "pn_peer_alloc": (i32, [u64, C.POINTER(vp)]),
+    "pn_peer_free": (i32, [vp]),
+    "pn_peer_export": (i32, [vp, C.c_char_p]),
+    "pn_peer_open": (i32, [C.c_char_p, C.POINTER(vp)]),
+    "pn_peer_close": (i32, [vp]),
+    "pn_peer_put": (i32, [vp, u64, vp, i32, vp]),
+    "pn_epoch_wait": (i32, [vp, i32, vp, i32, u32, vp, u32, vp]),
+    "pn_epoch_signal": (i32, [vp, vp, i32, vp]),
     "pn_render_workspace_bytes": (u64, [u32, i32, f32, f32]),
     "pn_set_profile_events": (i32, [vp, vp]),
     "pn_set_profile_event_list": (i32, [vp, i32]),

@@ -36,17 +36,40 @@ __global__ void __launch_bounds__(256) get_rays_kernel(float r00, float r01, flo
     rays_o[3 * n] = tx; rays_o[3 * n + 1] = ty; rays_o[3 * n + 2] = tz;
 }
 
+// Same arithmetic for a subset of the pixels (one rank's image tiles), camera read from DEVICE memory so that the launch
+// can sit in a CUDA graph: cam = [pose 16 floats row-major | fx fy cx cy].  pix == nullptr: all H*W pixels in order.
+__global__ void __launch_bounds__(256) get_rays_pix_kernel(const float *__restrict__ cam, uint32_t W, const int *__restrict__ pix,
+                                                           uint32_t n_rays, float *__restrict__ rays_o, float *__restrict__ rays_d) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_rays) return;
+    const uint32_t n = pix ? (uint32_t)pix[k] : k;
+    const float fx = cam[16], fy = cam[17], cx = cam[18], cy = cam[19];
+    const float i = (float)(n % W) + 0.5f, j = (float)(n / W) + 0.5f;
+    const float xs = (i - cx) / fx * 1.0f, ys = (j - cy) / fy * 1.0f, zs = 1.0f;
+    const float nrm = sqrtf(xs * xs + ys * ys + zs * zs);
+    const float ux = xs / nrm, uy = ys / nrm, uz = zs / nrm;
+    rays_d[3 * k] = ux * cam[0] + uy * cam[1] + uz * cam[2];
+    rays_d[3 * k + 1] = ux * cam[4] + uy * cam[5] + uz * cam[6];
+    rays_d[3 * k + 2] = ux * cam[8] + uy * cam[9] + uz * cam[10];
+    rays_o[3 * k] = cam[3]; rays_o[3 * k + 1] = cam[7]; rays_o[3 * k + 2] = cam[11];
+}
+
 // ------------------------------------------------------------------------------------------- IP bbox
 struct FrameGeom {  // lives in the workspace, written by ip_bbox_kernel
     float bbmin[3], bbmax[3], hi[3];
     int res[3];
     int n_grid;
+    int overflow;   // 1: the IP bbox needed more cells than the workspace holds (diverged / out-of-scene body): resolution was clamped
 };
 
-__global__ void __launch_bounds__(1024) ip_bbox_kernel(const float *__restrict__ p, int n, float hgs, int cut, float bound,
+// res_max > 0 (frame path): every resolution component is clamped to [1, res_max] so that res0*res1*res2 never exceeds the
+// workspace's cell capacity (res_max^3, max_cells_for) — a diverged simulation (huge / NaN / inf positions) then renders
+// garbage instead of indexing out of bounds, and FrameGeom.overflow reports it (stats[4] bit 0).
+__global__ void __launch_bounds__(1024) ip_bbox_kernel(const float *__restrict__ p, int n, float hgs, int cut, float bound, int res_max,
                                                        FrameGeom *__restrict__ g, float *__restrict__ bbmin_out,
                                                        float *__restrict__ bbmax_out, int *__restrict__ res_out) {
     __shared__ float smin[3][32], smax[3][32];
+    __shared__ int s_over[3];
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
 #pragma unroll
@@ -68,20 +91,24 @@ __global__ void __launch_bounds__(1024) ip_bbox_kernel(const float *__restrict__
         if (cut) { a = -bound; b = bound; }                       // renderer.py:784-786
         const float mn = a - 1e-3f, mx = b + 1e-3f;               // renderer.py:787-789
         // renderer.py:791: tensor / python-scalar on CUDA multiplies by the fp32 reciprocal
-        const int r = (int)ceilf((mx - mn) * (1.0f / hgs));
+        const float rf = ceilf((mx - mn) * (1.0f / hgs));
+        int r = (int)rf;
+        s_over[c] = 0;
+        if (res_max > 0 && !(rf >= 1.0f && rf <= (float)res_max)) { r = rf >= 1.0f ? res_max : 1; s_over[c] = 1; }   // also catches NaN
         if (g) { g->bbmin[c] = mn; g->bbmax[c] = mx; g->hi[c] = (float)((double)mx - 1e-6); g->res[c] = r; }
         if (bbmin_out) { bbmin_out[c] = mn; bbmax_out[c] = mx; res_out[c] = r; }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && g) g->n_grid = g->res[0] * g->res[1] * g->res[2];
+    if (threadIdx.x == 0 && g) { g->n_grid = g->res[0] * g->res[1] * g->res[2]; g->overflow = s_over[0] | s_over[1] | s_over[2]; }
 }
 
 // ------------------------------------------------------------------------------------------- IP grid
 __device__ __forceinline__ int ip_cell(const float *__restrict__ p, int i, const float *bbmin, float hgs, const int *res) {
     // nerf/utils.py:388-408 p2g (true fp32 division)
-    const int g0 = (int)floorf((p[3 * i] - bbmin[0]) / hgs);
-    const int g1 = (int)floorf((p[3 * i + 1] - bbmin[1]) / hgs);
-    const int g2 = (int)floorf((p[3 * i + 2] - bbmin[2]) / hgs);
+    // the clamps only act when ip_bbox_kernel had to clamp the resolution (FrameGeom.overflow) or a coordinate is NaN
+    const int g0 = min(max((int)floorf((p[3 * i] - bbmin[0]) / hgs), 0), res[0] - 1);
+    const int g1 = min(max((int)floorf((p[3 * i + 1] - bbmin[1]) / hgs), 0), res[1] - 1);
+    const int g2 = min(max((int)floorf((p[3 * i + 2] - bbmin[2]) / hgs), 0), res[2] - 1);
     return (g2 * res[1] + g1) * res[0] + g0;
 }
 
@@ -156,8 +183,9 @@ __global__ void __launch_bounds__(256) frame_setup_kernel(const float *__restric
                                                           uint32_t N, const FrameGeom *__restrict__ g, float min_near,
                                                           float bg, float *__restrict__ nears, float *__restrict__ fars,
                                                           int *__restrict__ active, FrameQueue *__restrict__ q,
-                                                          float *__restrict__ image, float *__restrict__ depth,
-                                                          float *__restrict__ depth0, float *__restrict__ wsum) {
+                                                          const int *__restrict__ pix, float *__restrict__ image,
+                                                          float *__restrict__ depth, float *__restrict__ depth0,
+                                                          float *__restrict__ wsum) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     bool hit = false;
     if (n < N) {
@@ -185,9 +213,10 @@ __global__ void __launch_bounds__(256) frame_setup_kernel(const float *__restric
         hit = near < far;  // a ray with t >= far never emits a sample
         if (!hit) {
             // what rund_cuda leaves for a ray that never composites anything (renderer.py:896-901)
-            image[3 * n] = bg; image[3 * n + 1] = bg; image[3 * n + 2] = bg;
-            depth0[n] = 0.f; wsum[n] = 0.f;
-            depth[n] = fmaxf(0.f - near, 0.f) / (far - near);  // NaN for a miss, as in the reference
+            const size_t o = pix ? (size_t)pix[n] : (size_t)n;   // pixel of the (possibly remote) frame this ray belongs to
+            image[3 * o] = bg; image[3 * o + 1] = bg; image[3 * o + 2] = bg;
+            depth0[o] = 0.f; wsum[n] = 0.f;
+            depth[o] = fmaxf(0.f - near, 0.f) / (far - near);  // NaN for a miss, as in the reference
         }
     }
     const uint32_t m = __ballot_sync(0xffffffffu, hit);
@@ -209,7 +238,8 @@ struct RenderArgs {
     const float *rays_o, *rays_d, *nears, *fars;
     const int *active;
     FrameQueue *queue;
-    float *image, *depth, *depth0, *wsum;
+    float *image, *depth, *depth0, *wsum;   // image / depth / depth0 are indexed by pix[ray] when pix != nullptr (frame-sized, maybe peer memory)
+    const int *pix;
     float density_scale, T_thresh, bg;
     uint32_t max_samples;
 };
@@ -323,10 +353,13 @@ __global__ void __launch_bounds__(128, 3) render_persistent(const RenderArgs A) 
     if (lane == 0 && my_samples) atomicAdd((unsigned long long *)&A.queue->samples, (unsigned long long)my_samples);
 }
 
-__global__ void copy_stats_kernel(const FrameQueue *q, long long *stats) {
+__global__ void copy_stats_kernel(const FrameQueue *q, const FrameGeom *g, long long *stats) {
     stats[0] = q->samples;   // composited samples
     stats[1] = q->n_active;  // rays that hit the IP box
     stats[2] = q->pad;       // field evaluations (>= stats[0]: samples marched past an early termination)
+    stats[3] = 0;
+    stats[4] = g->overflow ? 1 : 0;
+    stats[5] = stats[6] = stats[7] = 0;
 }
 
 // stand-alone field pass over M samples (the body of NeRFNetwork.forward as one kernel)
@@ -395,8 +428,10 @@ WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
     return w;
 }
 
+// IP-grid capacity of the workspace: a body anywhere inside the scene box [-bound, bound]^3 fits (res_max cells per axis)
+int res_max_for(float bound, float hgs) { return (int)ceilf((2 * bound + 2e-3f) / hgs) + 1; }
 int max_cells_for(float bound, float hgs) {
-    const int r = (int)ceilf((2 * bound + 2e-3f) / hgs) + 1;
+    const int r = res_max_for(bound, hgs);
     return r * r * r;
 }
 
@@ -428,10 +463,20 @@ extern "C" int pn_get_rays(const float *pose, float fx, float fy, float cx, floa
     return PN_OK;
 }
 
+extern "C" int pn_get_rays_pix(const float *cam, uint32_t H, uint32_t W, const int *pix, uint32_t n_rays, float *rays_o,
+                               float *rays_d, void *stream) {
+    PN_REQUIRE(cam && rays_o && rays_d, "null pointer");
+    PN_REQUIRE(pix || n_rays == H * W, "without a pixel list n_rays must be H*W");
+    if (n_rays == 0) return PN_OK;
+    get_rays_pix_kernel<<<div_up(n_rays, 256u), 256, 0, PN_STREAM(stream)>>>(cam, W, pix, n_rays, rays_o, rays_d);
+    PN_LAUNCH_CHECK("get_rays_pix_kernel");
+    return PN_OK;
+}
+
 extern "C" int pn_ip_bbox(const float *p_def, int n_vtx, float hgs, int cut, float bound, float *bbmin, float *bbmax,
                           int *resolution, void *stream) {
     PN_REQUIRE(p_def && bbmin && bbmax && resolution && n_vtx > 0, "null pointer / empty IP set");
-    ip_bbox_kernel<<<1, 1024, 0, PN_STREAM(stream)>>>(p_def, n_vtx, hgs, cut, bound, nullptr, bbmin, bbmax, resolution);
+    ip_bbox_kernel<<<1, 1024, 0, PN_STREAM(stream)>>>(p_def, n_vtx, hgs, cut, bound, 0, nullptr, bbmin, bbmax, resolution);
     PN_LAUNCH_CHECK("ip_bbox_kernel");
     return PN_OK;
 }
@@ -504,7 +549,19 @@ extern "C" uint64_t pn_render_workspace_bytes(uint32_t N, int n_vtx, float bound
 extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, const float *rays_o, const float *rays_d,
                                   uint32_t N, float *image, float *depth, float *depth_0, float *weights_sum,
                                   void *workspace, uint64_t workspace_bytes, long long *stats, int mode, void *stream) {
+    return pn_render_deformed_ex(f, d, rays_o, rays_d, N, image, depth, depth_0, weights_sum, workspace, workspace_bytes, stats,
+                                 mode, nullptr, stream);
+}
+
+int pn_flag_wait_launch(const pn_frame_io_t *io, cudaStream_t st);      // peer.cu
+int pn_flag_signal_launch(const pn_frame_io_t *io, cudaStream_t st);
+
+extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, const float *rays_o, const float *rays_d,
+                                     uint32_t N, float *image, float *depth, float *depth_0, float *weights_sum,
+                                     void *workspace, uint64_t workspace_bytes, long long *stats, int mode,
+                                     const pn_frame_io_t *io, void *stream) {
     PN_REQUIRE(f && d && rays_o && rays_d && image && depth && depth_0 && weights_sum && workspace, "null pointer");
+    PN_REQUIRE(!io || !io->pix || mode == 3, "a pixel map (scattered / peer frame output) needs the wavefront renderer (mode 3)");
     PN_REQUIRE(f->L == pn::kLevels, "fused field expects the 16-level C=2 D=3 grid of nerf/network.py");
     PN_REQUIRE(mode >= 0 && mode <= 3, "render mode: 0 = fused warp-cooperative + tcgen05 MLP, 1 = same with the fp32 SIMT MLP, 2 = one lane per ray, 3 = wavefront (march / field / composite kernels)");
     PN_REQUIRE(d->n_vtx > 0 && d->num_seek_IP >= 1 && d->num_seek_IP <= 3, "need IPs and num_seek_IP in 1..3");
@@ -521,11 +578,13 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
     int *active = (int *)(base + w.active);
     int *cnt = (int *)(base + w.pig_cnt), *bgn = (int *)(base + w.pig_bgn), *fill = (int *)(base + w.pig_fill), *idx = (int *)(base + w.pig_idx);
 
+    if (io && io->epoch)
+        if (int rc = pn_flag_wait_launch(io, st)) return rc;       // bump the slot's epoch; wait e.g. for this frame's IP state to land in this GPU's memory
     PN_CUDA(cudaMemsetAsync(queue, 0, sizeof(FrameQueue), st));
-    ip_bbox_kernel<<<1, 1024, 0, st>>>(d->p_def, d->n_vtx, d->hgs, d->cut, d->bound, geom, nullptr, nullptr, nullptr);
+    ip_bbox_kernel<<<1, 1024, 0, st>>>(d->p_def, d->n_vtx, d->hgs, d->cut, d->bound, res_max_for(d->bound, d->hgs), geom, nullptr, nullptr, nullptr);
     if (int rc = build_ip_grid_impl(d->p_def, d->n_vtx, geom->bbmin, d->hgs, geom->res, max_cells, cnt, bgn, fill, idx, st)) return rc;
     frame_setup_kernel<<<div_up(N, 256u), 256, 0, st>>>(rays_o, rays_d, N, geom, d->min_near, d->bg_color, nears, fars,
-                                                         active, queue, image, depth, depth_0, weights_sum);
+                                                         active, queue, io ? io->pix : nullptr, image, depth, depth_0, weights_sum);
     PN_LAUNCH_CHECK("frame_setup_kernel");
 
     RenderArgs A{};
@@ -540,7 +599,7 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
     A.bend.hgs = d->hgs; A.bend.IP_dx = d->IP_dx; A.bend.bound = d->bound; A.bend.cut = d->cut != 0;
     for (int i = 0; i < 6; i++) A.bend.cb[i] = d->cut_bounds[i];
     A.geom = geom; A.rays_o = rays_o; A.rays_d = rays_d; A.nears = nears; A.fars = fars; A.active = active; A.queue = queue;
-    A.image = image; A.depth = depth; A.depth0 = depth_0; A.wsum = weights_sum;
+    A.image = image; A.depth = depth; A.depth0 = depth_0; A.wsum = weights_sum; A.pix = io ? io->pix : nullptr;
     A.density_scale = d->density_scale; A.T_thresh = d->T_thresh; A.bg = d->bg_color; A.max_samples = d->max_steps;
 
     const uint32_t blocks = (uint32_t)pn_sm_count_cached() * 3u;
@@ -586,9 +645,11 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
         PN_LAUNCH_CHECK("wavefront passes");
         if (g_prof_stop) PN_CUDA(cudaEventRecord(g_prof_stop, st));
         if (stats) {
-            wave_stats_kernel<<<1, 1, 0, st>>>(queue, Wv, n_pass, stats);
+            wave_stats_kernel<<<1, 1, 0, st>>>(queue, geom, Wv, n_pass, stats);
             PN_LAUNCH_CHECK("wave_stats_kernel");
         }
+        if (io && io->epoch && io->n_signal > 0)
+            if (int rc = pn_flag_signal_launch(io, st)) return rc;   // every pixel of this rank is in the frame: tell its owner
         return PN_OK;
     }
     if (mode == 0 || mode == 1) {
@@ -643,8 +704,10 @@ extern "C" int pn_render_deformed(const pn_field_t *f, const pn_deform_t *d, con
     PN_LAUNCH_CHECK("render_persistent");
     if (g_prof_stop) PN_CUDA(cudaEventRecord(g_prof_stop, st));
     if (stats) {
-        copy_stats_kernel<<<1, 1, 0, st>>>(queue, stats);
+        copy_stats_kernel<<<1, 1, 0, st>>>(queue, geom, stats);
         PN_LAUNCH_CHECK("copy_stats_kernel");
     }
+    if (io && io->epoch && io->n_signal > 0)
+        if (int rc = pn_flag_signal_launch(io, st)) return rc;
     return PN_OK;
 }

@@ -40,7 +40,7 @@ struct WaveArgs {
     int2 *meta;            // [cap] (ray or -1 for a padding row, bitcast t_after)
     float4 *out;           // [cap] alpha r g b
     int *slab_next;        // [cap / kSlab] row at which a warp's sample stream continues after this slab
-    long long *counters;   // [0] composited samples, [1] emitted samples
+    long long *counters;   // [0] composited samples, [1] emitted samples, [2] rays cut short by the last pass, [3] chunks deferred by a full sample list
     const pn::tc::Weights *weights_img;   // bf16 hi/lo weight images + level geometry, built once per frame (field_weights_kernel)
     int cap;               // rows available per pass
 };
@@ -135,7 +135,10 @@ __global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const Re
             if (ntake > room) {
                 if (lane == 0) nb = atomicAdd(&ctl->n_reserved, kSlab);
                 nb = __shfl_sync(0xffffffffu, nb, 0);
-                if (nb + kSlab > Wv.cap) break;                             // sample list full: this chunk is redone next pass
+                if (nb + kSlab > Wv.cap) {                                  // sample list full: this chunk is redone next pass
+                    if (lane == 0) atomicAdd((unsigned long long *)&Wv.counters[3], 1ull);
+                    break;
+                }
                 if (lane == 0 && end > 0) Wv.slab_next[(end - 1) / kSlab] = nb;
             }
             const int rank = __popc(take & lt_mask);
@@ -368,10 +371,12 @@ __global__ void __launch_bounds__(256) wave_composite_kernel(const RenderArgs A,
                 if (rem > 0 && !terminated) idx = Wv.slab_next[idx / kSlab - 1];   // idx sits on a slab boundary here
             }
             if (terminated || finished || last_pass) {
-                A.image[3 * ray] = cr + (1 - ws) * A.bg; A.image[3 * ray + 1] = cg + (1 - ws) * A.bg; A.image[3 * ray + 2] = cb + (1 - ws) * A.bg;
-                A.depth0[ray] = dep;
-                A.depth[ray] = fmaxf(dep - near, 0.f) / (far - near);
+                const size_t o = A.pix ? (size_t)A.pix[ray] : (size_t)ray;   // this ray's pixel in the (possibly remote) frame
+                A.image[3 * o] = cr + (1 - ws) * A.bg; A.image[3 * o + 1] = cg + (1 - ws) * A.bg; A.image[3 * o + 2] = cb + (1 - ws) * A.bg;
+                A.depth0[o] = dep;
+                A.depth[o] = fmaxf(dep - near, 0.f) / (far - near);
                 A.wsum[ray] = ws;
+                if (!terminated && !finished) atomicAdd((unsigned long long *)&Wv.counters[2], 1ull);   // cut short: out of passes
             } else {
                 survive = true;
                 Wv.rs_comp[2 * ray] = make_float4(ws, dep, cr, cg);
@@ -390,13 +395,17 @@ __global__ void __launch_bounds__(256) wave_composite_kernel(const RenderArgs A,
     if (lane == 0 && kept) atomicAdd((unsigned long long *)&Wv.counters[0], (unsigned long long)kept);
 }
 
-__global__ void wave_stats_kernel(const FrameQueue *q, const WaveArgs Wv, int n_pass, long long *stats) {
+__global__ void wave_stats_kernel(const FrameQueue *q, const FrameGeom *g, const WaveArgs Wv, int n_pass, long long *stats) {
     stats[0] = Wv.counters[0];   // composited samples
     stats[1] = q->n_active;      // rays that hit the IP box
     stats[2] = Wv.counters[1];   // field evaluations (>= stats[0]: samples marched past an early termination)
     long long rows = 0;
     for (int p = 0; p < n_pass; p++) rows += min(Wv.ctl[p].n_reserved, Wv.cap);
     stats[3] = rows;             // rows the field kernel processed (samples + slab padding)
+    stats[4] = (g->overflow ? 1 : 0) | (Wv.counters[2] ? 2 : 0);   // bit 0: IP grid clamped; bit 1: rays cut short (sample list + passes exhausted)
+    stats[5] = Wv.counters[2];   // rays finalised by the last pass before they finished or terminated
+    stats[6] = Wv.counters[3];   // 32-lattice-point chunks a full sample list deferred to the next pass (harmless unless [5] > 0)
+    stats[7] = 0;
 }
 
 }  // namespace

@@ -190,9 +190,21 @@ class NeRFNetwork(nn.Module):
                              f"({tuple(own['encoder.embeddings'].shape)}): construct NeRFNetwork with the checkpoint's bound")
         return self.load_state_dict({k: v for k, v in state.items() if strict or k in own}, strict=strict)
 
-    def _field_struct(self):
+    def _field_struct(self, embeddings=None):
+        """pn_field_t over this module's parameters (`embeddings`: another copy of the hash table, same shape).  The fused
+        kernels hard-wire the architecture of nerf/network.py:30-71 (16 x 2 hash grid -> 32-64-16 | SH(4) + 15 -> 31-64-64-3,
+        bias-free): anything else is refused here instead of reading weights out of bounds."""
+        shapes = [tuple(l.weight.shape) for l in self.sigma_net] + [tuple(l.weight.shape) for l in self.color_net]
+        enc = self.encoder
+        if (shapes != [(64, 32), (16, 64), (64, 31), (64, 64), (3, 64)] or enc.num_levels != 16 or enc.level_dim != 2 or enc.input_dim != 3
+                or getattr(enc, "align_corners", False) or getattr(enc, "interp_id", 0) != 0 or getattr(enc, "gridtype_id", 0) != 0):
+            raise NotImplementedError(f"the fused field kernels implement the default NeRFNetwork only (got layers {shapes}, "
+                                      f"{enc.num_levels} x {enc.level_dim} grid); use forward() / rund_cuda() for other shapes")
+        emb = self.encoder.embeddings.data if embeddings is None else embeddings
+        if emb.shape != self.encoder.embeddings.shape:
+            raise ValueError("hash-table copy has a different shape")
         f = FieldT()
-        self._keep = [self.encoder.embeddings.data, self.encoder.offsets] + [l.weight.data for l in self.sigma_net] + [l.weight.data for l in self.color_net]
+        self._keep = [emb, self.encoder.offsets] + [l.weight.data for l in self.sigma_net] + [l.weight.data for l in self.color_net]
         f.embeddings, f.offsets = dptr(self._keep[0], "embeddings", torch.float32), dptr(self._keep[1], "offsets", torch.int32)
         f.S = float(np.log2(self.encoder.per_level_scale)); f.H = int(self.encoder.base_resolution); f.L = int(self.encoder.num_levels)
         f.bound = float(self.bound)
@@ -299,11 +311,49 @@ class NeRFNetwork(nn.Module):
         return out
 
     # ------------------------------------------------------------------ fused frame (product path)
+    def deform_struct(self, ip_state=None, dt_gamma=0, bg_color=None, max_steps=1024, T_thresh=1e-2, **kwargs):
+        """pn_deform_t for one frame: `ip_state` = (p_def, p_ori, F, dF) fp32 contiguous CUDA tensors (default: the state wired
+        onto the module, main_gui.py:50-56) + the flat `opt` namespace the reference passes as **vars(opt)."""
+        if ip_state is None:
+            ip_state = (self.p_def, self.p_ori, self.IP_F, self.IP_dF)
+        keep = [t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous() for t in ip_state]
+        d = DeformT()
+        d.p_def, d.p_ori, d.F_IP, d.dF_IP = [dptr(t, "IP state", torch.float32) for t in keep]
+        d.n_vtx = keep[0].shape[0]; d.IP_dx = float(self.IP_dx)
+        d.density_bitfield = dptr(self.density_bitfield, "density_bitfield", torch.uint8)
+        d.bound, d.cascade, d.grid_size = float(self.bound), int(self.cascade), int(self.grid_size)
+        d.min_near, d.density_scale, d.dt_gamma = float(self.min_near), float(self.density_scale), float(dt_gamma)
+        d.max_steps, d.T_thresh, d.max_iter_num = int(max_steps), float(T_thresh), int(kwargs.get("max_iter_num"))
+        d.hgs, d.cut = float(kwargs.get("hash_grid_size")), int(bool(kwargs.get("cut")))
+        cb = kwargs.get("cut_bounds") or [0.0] * 6
+        for i in range(6):
+            d.cut_bounds[i] = float(cb[i])
+        d.num_seek_IP = int(kwargs.get("num_seek_IP"))
+        d.bg_color = 1.0 if bg_color is None else float(bg_color)
+        return d, keep
+
+    def workspace_bytes(self, N, n_vtx, **kwargs):
+        return int(lib.pn_render_workspace_bytes(int(N), int(n_vtx), float(kwargs.get("bound", self.bound)), float(kwargs.get("hash_grid_size"))))
+
+    @staticmethod
+    def check_stats(stats):
+        """Raise on the error bits of a finished frame's stats (pn_render_deformed: stats[4]).  Synchronises."""
+        st = [int(v) for v in stats.tolist()]
+        if st[4] & 1:
+            raise RuntimeError("render_deformed: the deformed IP bounding box needs more grid cells than the scene box allows "
+                               "(diverged simulation / IPs far outside [-bound, bound]); the frame is not valid")
+        if st[4] & 2:
+            raise RuntimeError(f"render_deformed: {st[5]} rays were cut short (sample list and passes exhausted); "
+                               "render with a larger workspace or mode 0")
+        return st
+
     @torch.no_grad()
     def render_deformed(self, rays_o, rays_d, staged=False, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024, T_thresh=1e-2,
-                        mode=None, out=None, **kwargs):
+                        mode=None, out=None, workspace=None, stats=None, io=None, embeddings=None, ip_state=None, **kwargs):
         """renderer.py:587-599 -> rund_cuda semantics in one device-resident call.  Returns the same dict.
-        mode 0: warp-cooperative march + tcgen05 MLP (default); 1: same with the fp32 SIMT MLP; 2: one lane per ray."""
+        mode 3: wavefront (default); 0: fused warp-cooperative kernel + tcgen05 MLP; 1: same with the fp32 SIMT MLP; 2: one lane
+        per ray.  `workspace` / `stats` / `embeddings` / `ip_state` / `io` (_lib.FrameIoT) let a frame pipeline keep several
+        frames in flight (pipeline.py); by default the module's own single workspace is used."""
         if mode is None:
             mode = DEFAULT_RENDER_MODE
         if perturb:
@@ -311,34 +361,30 @@ class NeRFNetwork(nn.Module):
         prefix = rays_o.shape[:-1]
         rays_o = rays_o.to(torch.float32).contiguous().view(-1, 3); rays_d = rays_d.to(torch.float32).contiguous().view(-1, 3)
         N = rays_o.shape[0]; device = rays_o.device
-        hgs = float(kwargs.get("hash_grid_size")); bound = float(kwargs.get("bound", self.bound))
-        d = DeformT()
-        keep = [self.p_def.to(torch.float32).contiguous(), self.p_ori.to(torch.float32).contiguous(),
-                self.IP_F.to(torch.float32).contiguous(), self.IP_dF.to(torch.float32).contiguous()]
-        d.p_def, d.p_ori, d.F_IP, d.dF_IP = [dptr(t) for t in keep]
-        d.n_vtx = keep[0].shape[0]; d.IP_dx = float(self.IP_dx)
-        d.density_bitfield = dptr(self.density_bitfield, "density_bitfield", torch.uint8)
-        d.bound, d.cascade, d.grid_size = float(self.bound), int(self.cascade), int(self.grid_size)
-        d.min_near, d.density_scale, d.dt_gamma = float(self.min_near), float(self.density_scale), float(dt_gamma)
-        d.max_steps, d.T_thresh, d.max_iter_num = int(max_steps), float(T_thresh), int(kwargs.get("max_iter_num"))
-        d.hgs, d.cut = hgs, int(bool(kwargs.get("cut")))
-        cb = kwargs.get("cut_bounds") or [0.0] * 6
-        for i in range(6):
-            d.cut_bounds[i] = float(cb[i])
-        d.num_seek_IP = int(kwargs.get("num_seek_IP"))
-        d.bg_color = 1.0 if bg_color is None else float(bg_color)
-        need = int(lib.pn_render_workspace_bytes(N, d.n_vtx, bound, hgs))
-        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
-            self._stats = torch.zeros(4, dtype=torch.int64, device=device)
+        d, keep = self.deform_struct(ip_state, dt_gamma=dt_gamma, bg_color=bg_color, max_steps=max_steps, T_thresh=T_thresh, **kwargs)
+        need = self.workspace_bytes(N, d.n_vtx, **kwargs)
+        if workspace is None:
+            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
+            workspace = self._workspace
+        if stats is None:
+            if self._stats is None or self._stats.device != device:
+                self._stats = torch.zeros(8, dtype=torch.int64, device=device)
+            stats = self._stats
+        if workspace.numel() < need:
+            raise ValueError(f"workspace too small: {workspace.numel()} < {need} bytes")
         if out is None:
             out = {"image": torch.empty(N, 3, dtype=torch.float32, device=device), "depth": torch.empty(N, dtype=torch.float32, device=device),
                    "depth_0": torch.empty(N, dtype=torch.float32, device=device), "weights_sum": torch.empty(N, dtype=torch.float32, device=device)}
         # kernels this call enqueues: bbox, 4 x IP grid, frame setup, IP pack, 3 x neighbourhood lists, (3 per pass | 1 fused), stats
         self._render_launches = 11 + (1 + 3 * int(lib.pn_render_pass_count(int(max_steps))) if mode == 3 else 1)
-        f = self._field_struct()
-        check(lib.pn_render_deformed(C.byref(f), C.byref(d), dptr(rays_o), dptr(rays_d), N, dptr(out["image"]), dptr(out["depth"]),
-                                     dptr(out["depth_0"]), dptr(out["weights_sum"]), dptr(self._workspace), need, dptr(self._stats),
-                                     int(mode), stream_ptr()))
+        if io is not None:
+            self._render_launches += (1 if io.epoch else 0) + (1 if io.n_signal else 0)
+        f = self._field_struct(embeddings)
+        check(lib.pn_render_deformed_ex(C.byref(f), C.byref(d), dptr(rays_o), dptr(rays_d), N, dptr(out["image"]), dptr(out["depth"]),
+                                        dptr(out["depth_0"]), dptr(out["weights_sum"]), dptr(workspace), workspace.numel(), dptr(stats),
+                                        int(mode), C.byref(io) if io is not None else None, stream_ptr()))
+        if io is not None and io.pix:
+            return {"image": out["image"], "depth": out["depth"], "depth_0": out["depth_0"], "weights_sum": out["weights_sum"], "stats": stats}
         return {"image": out["image"].view(*prefix, 3), "depth": out["depth"].view(*prefix), "depth_0": out["depth_0"].view(*prefix),
-                "weights_sum": out["weights_sum"], "stats": self._stats}
+                "weights_sum": out["weights_sum"], "stats": stats}
