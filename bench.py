@@ -75,8 +75,46 @@ class ClockSampler:
         return out
 
 
+def workload_config(args, n_ip, n_k, iters, W, H, num_seek_IP):
+    """`config` of the JSON line: the SAME dict in both arms (what is measured); how each arm runs it goes into `details`."""
+    return {"workload": f"{args.config}: {n_ip}-IP Q-GMLS body ({n_k} kernels, sim_iters {iters}) + {W}x{H} deformed render, random-init 16-level hash grid "
+                        f"+ 64-wide MLP, density_scale {args.density_scale}, num_seek_IP {num_seek_IP}", "rays": W * H, "n_ip": n_ip}
+
+
 # ------------------------------------------------------------------------------------------------- ours
+def hash_microbench(model, dev, rank, world, flush, hbm, src):
+    """BASELINE.json configs[4]: 2^22 samples x 16 levels through the stand-alone grid_encode_forward, samples split evenly
+    over the ranks (table replicated).  Returns this rank's (ms_coherent, ms_random, samples)."""
+    import torch
+    from pienerf_b200 import _gridencoder
+    B = (1 << 22) // world
+    g = torch.Generator(device=dev).manual_seed(rank)
+    enc = model.encoder
+    S = float(np.log2(enc.per_level_scale))
+    outbuf = torch.empty(16, B, 2, device=dev)
+    pts = torch.rand(B, 3, device=dev, generator=g)
+    # "warped samples": what the renderer feeds the encoder — rays x 128 consecutive samples, 0.0017 apart in table
+    # coordinates (= the chair's dt_min 0.0034 in [-1,1]); and the worst case, uniform random points
+    nr = B // 128
+    o = torch.rand(nr, 1, 3, device=dev, generator=g) * 0.5 + 0.1
+    dd = torch.nn.functional.normalize(torch.rand(nr, 1, 3, device=dev, generator=g) + 0.1, dim=-1)
+    coh = (o + dd * (torch.arange(128, device=dev).view(1, 128, 1) * 0.0017)).reshape(B, 3).contiguous().clamp(0, 1)
+
+    def run(x, reps=5):
+        fn = lambda: _gridencoder.grid_encode_forward(x, enc.embeddings.data, enc.offsets, outbuf, B, 3, 2, 16, S, 16, None, 0, False, 0)
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1.0)
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+    return run(coh), run(pts), B
+
+
 def run_ours(args):
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")               # frame slots + simulator + copy streams each get their own queue
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -84,27 +122,21 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from pienerf_b200.frame import DistFrameDriver, build_scene
+    from pienerf_b200 import _lib
+    from pienerf_b200.frame import build_scene
+    from pienerf_b200.pipeline import FramePipeline
 
     model, sim, opt, pose, intr, body, field = build_scene(args.config, device=dev, density_scale=args.density_scale)
-    drv = DistFrameDriver(model, sim, opt, overlap_sim=not args.no_overlap_sim)
     W, H = opt.W, opt.H
     N = W * H
-    host_pose = torch.from_numpy(pose).pin_memory()
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
-    calib = None
-    if world > 1 and not args.equal_tiles and args.no_overlap_sim:
-        # only when the step is serialised with rank 0's render does rank 0 need a smaller share of the tiles; with the
-        # step on its concurrent side stream (default) equal shares measured better (2 GPUs: 507 vs 484 fps)
-        calib = drv.calibrate(host_pose, intr)
-    from pienerf_b200 import _lib
+    weights = None
+    if world > 1 and args.rank0_share is not None:                            # rank 0 also runs the simulator: optional smaller tile share
+        f0 = args.rank0_share / world
+        weights = [f0] + [(1.0 - f0) / (world - 1)] * (world - 1)
+    pipe = FramePipeline(model, sim, opt, slots=args.slots, weights=weights)
+    pipe.build(pose, intr)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2 (stand-alone kernel timings only)
     n_pass = int(_lib.lib.pn_render_pass_count(int(opt.max_steps)))
-
-    def frame(e2e, prof=None):
-        """One GUI frame through the public multi-GPU frame API.  e2e=True adds the host<->device traffic: rays are
-        regenerated from the host pose and the gathered frame is copied to pinned host memory."""
-        out, _ = drv.frame(host_pose, intr, to_host=e2e, regenerate_rays=e2e, profile_events=prof)
-        return out
 
     def sync_all():
         torch.cuda.synchronize()
@@ -112,109 +144,132 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    enqueue_s = [0.0]                                                        # host time spent enqueueing frames (all timed loops)
-    enqueue_n = [0]
+    # ---- proof that the N-rank frame is the 1-rank frame: 12 frames from the rest state with a drag force, checksum of the last
+    check_frames = 12
+    if rank == 0:
+        sim.update_force(sim.n_ip // 3, torch.tensor([3e4, -1e4, 2e4]))
+    for k in range(check_frames):
+        slot = pipe.frame(pose, intr, to_host=True)
+    checksum = None
+    if rank == 0:
+        import hashlib
+        h = pipe.wait_host(slot)
+        img = np.nan_to_num(h["image"].numpy(), nan=-1.0)
+        checksum = {"frame": check_frames - 1, "sha1_image": hashlib.sha1(img.tobytes()).hexdigest(), "sum_image": float(img.astype(np.float64).sum()),
+                    "sha1_depth_0": hashlib.sha1(h["depth_0"].numpy().tobytes()).hexdigest(),
+                    "note": "frame after 11 simulator steps with a drag force, as delivered to the host; identical for every --gpus N"}
+        sim.clear_force()
+    pipe.drain(); sync_all()
 
-    def timed(K, e2e, with_prof=False):
-        enqueue_n[0] += K
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        # per frame: (start, stop) around all render passes + one event pair per field-kernel launch (one per pass)
-        pv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-               [torch.cuda.Event(enable_timing=True) for _ in range(2 * n_pass)]) for _ in range(K)] if with_prof else None
-        if pv:
-            for a, b, lst in pv:
-                a.record(); b.record()                                        # instantiate the handles
-                for e in lst:
-                    e.record()
-        samples0 = []
+    enqueue_s, enqueue_n = [0.0], [0]
+
+    def timed(K, to_host):
         sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        for i in range(K):
-            flush.fill_(float(i))                                             # evict L2 between timed frames (not timed)
-            ev[i][0].record()
+        e0.record()
+        for _ in range(K):
             c0 = time.perf_counter()
-            out = frame(e2e, pv[i] if pv else None)
+            pipe.frame(pose, intr, to_host=to_host)
             enqueue_s[0] += time.perf_counter() - c0
-            ev[i][1].record()
-            samples0.append(out["stats"].clone())
-        if e2e:
-            drv.wait_host()                                                   # every frame has landed in pinned host memory
+        enqueue_n[0] += K
+        pipe.drain()
+        e1.record()
         sync_all()
         wall = time.perf_counter() - t0
-        ms = [a.elapsed_time(b) for a, b in ev]
-        total_ms = float(sum(ms))
+        ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        kms = None
-        if pv:
-            kms = {"render": [a.elapsed_time(b) for a, b, _ in pv],
-                   "field": [sum(lst[2 * k].elapsed_time(lst[2 * k + 1]) for k in range(n_pass)) for _, _, lst in pv],
-                   "field_launch": [lst[0].elapsed_time(lst[1]) for _, _, lst in pv]}
-        samples = [[int(v) for v in s[:4]] for s in samples0]
-        return total_ms, wall, kms, samples
+            ms = float(t.item())
+        return ms, wall
 
-    for _ in range(max(args.warmup, 3)):
-        frame(False); frame(True)
-    drv.wait_host()
-    drv.launches = 0
+    Wm = max(args.warmup, 3)
+    for _ in range(Wm):
+        pipe.frame(pose, intr, to_host=False)
+    for _ in range(Wm):
+        pipe.frame(pose, intr, to_host=True)
+    pipe.drain(); sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
     torch.cuda.profiler.start()                                               # `ncu --profile-from-start off` sees exactly the timed frames
-    total_ms, wall, _, samples = timed(args.steps, e2e=False)
+    total_ms, wall = timed(args.steps, to_host=False)
     torch.cuda.profiler.stop()
-    n_launch = drv.launches
-    # the roofline kernel's own duration: a separate, shorter loop with an event pair around every field-kernel launch
-    # (kept out of the headline loop so that the instrumentation cannot perturb it)
-    _, _, kms, _ = timed(min(args.steps, 10), e2e=False, with_prof=True)
-    e2e_ms, e2e_wall, _, _ = timed(args.steps, e2e=True)
+    stats = np.mean(np.asarray([[int(v) for v in sl["stats"].tolist()] for sl in pipe.slots], dtype=np.float64), axis=0)
+    e2e_ms, e2e_wall = timed(args.steps, to_host=True)
     clocks = sampler.stop() if sampler else None
+    pipe.check()
 
-    # ---- stand-alone kernel rooflines on rank 0 (hash microbench = BASELINE.json configs[4], MLP pass)
-    extra = {}
+    # ---- the roofline kernel's own duration: eager (un-pipelined) frames with an event pair around every field-kernel launch
+    # (kept out of the headline loop so that the instrumentation cannot perturb it; L2 flushed before each)
+    reps = min(args.steps, 10)
+    pv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), [torch.cuda.Event(enable_timing=True) for _ in range(2 * n_pass)])
+          for _ in range(reps)]
+    for a, b, lst in pv:
+        a.record(); b.record()
+        for e in lst:
+            e.record()
+    sync_all()
+    for i in range(reps):
+        flush.fill_(float(i))
+        a, b, lst = pv[i]
+        _lib.lib.pn_set_profile_events(_lib.vp(a.cuda_event), _lib.vp(b.cuda_event))
+        arr = (_lib.vp * len(lst))(*[e.cuda_event for e in lst])
+        _lib.lib.pn_set_profile_event_list(arr, len(lst))
+        pipe._frame_body(pipe.slots[i % pipe.S], sync=False)
+        _lib.lib.pn_set_profile_events(_lib.vp(0), _lib.vp(0)); _lib.lib.pn_set_profile_event_list(None, 0)
+    sync_all()
+    render_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in pv]))
+    field_ms = float(np.mean([sum(lst[2 * k].elapsed_time(lst[2 * k + 1]) for k in range(n_pass)) for _, _, lst in pv]))
+    field0_ms = float(np.mean([lst[0].elapsed_time(lst[1]) for _, _, lst in pv]))
+
+    # ---- stand-alone kernel rooflines (hash microbench on EVERY rank = BASELINE.json configs[4]; MLP pass on rank 0)
     hbm, tf, src = measured_peaks()
+    ms_coh, ms_rand, Bm = hash_microbench(model, dev, rank, world, flush, hbm, src)
+    per_rank = torch.tensor([ms_coh, ms_rand, stats[2], field_ms], dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(per_rank) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, per_rank)
+    else:
+        allr = [per_rank]
+    allr = np.asarray([t.tolist() for t in allr])
+    extra = {}
     if rank == 0:
-        from pienerf_b200.gridencoder import grid_encode
-        B = 1 << 22
+        gb = Bm * ALGO_BYTES_PER_SAMPLE_GRID / 1e9
+        agg_c, agg_r = world * gb / (allr[:, 0].max() * 1e-3), world * gb / (allr[:, 1].max() * 1e-3)
+        extra["hash_microbench"] = {
+            "samples": Bm * world, "samples_per_gpu": Bm, "n_gpus": world, "kernel": "grid_forward_d3c2 (stand-alone grid_encode_forward)",
+            "ms_per_gpu": [round(float(v), 4) for v in allr[:, 0]],
+            "roofline": {"bound": "hbm", "achieved": agg_c, "peak": hbm * world, "unit": "GB/s", "frac": agg_c / (hbm * world), "traffic": None, "peak_source": src,
+                         "inputs": "ray-coherent warped samples: rays x 128 samples, 0.0017 apart; aggregate over all GPUs = total bytes / slowest GPU"},
+            "uniform_random": {"ms_per_gpu": [round(float(v), 4) for v in allr[:, 1]], "achieved": agg_r, "frac": agg_r / (hbm * world),
+                               "inputs": "uniform random in [0,1]^3 (no reuse between lanes)"},
+            "reference_kernel": "timed on the same inputs by `bench.py --impl reference` (key hash_microbench_reference)"}
+        M = 1 << 21
         g = torch.Generator(device=dev).manual_seed(0)
-        pts = torch.rand(B, 3, device=dev, generator=g)
-        enc = model.encoder
+        xs = (torch.rand(M, 3, device=dev, generator=g) * 2 - 1); ds = torch.nn.functional.normalize(torch.randn(M, 3, device=dev, generator=g), dim=-1)
 
         def time_kernel(fn, reps=5):
             fn(); torch.cuda.synchronize()
-            best = []
+            ts = []
             for _ in range(reps):
                 flush.fill_(1.0)
                 a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
                 a.record(); fn(); b.record(); torch.cuda.synchronize()
-                best.append(a.elapsed_time(b))
-            return float(np.mean(best))
-        outbuf = torch.empty(16, B, 2, device=dev)
-        from pienerf_b200 import _gridencoder
-        S = float(np.log2(enc.per_level_scale))
-        def grid_ms(x):
-            return time_kernel(lambda: _gridencoder.grid_encode_forward(x, enc.embeddings.data, enc.offsets, outbuf, B, 3, 2, 16, S, 16, None, 0, False, 0))
-        # "warped samples" (BASELINE.json configs[4]): what the renderer feeds the encoder — 2^15 rays x 128 consecutive samples,
-        # 0.0017 apart in table coordinates (= the chair's dt_min 0.0034 in [-1,1]); and the worst case, uniform random points
-        nr = B // 128
-        o = torch.rand(nr, 1, 3, device=dev, generator=g) * 0.5 + 0.1
-        dd = torch.nn.functional.normalize(torch.rand(nr, 1, 3, device=dev, generator=g) + 0.1, dim=-1)
-        coh = (o + dd * (torch.arange(128, device=dev).view(1, 128, 1) * 0.0017)).reshape(B, 3).contiguous().clamp(0, 1)
-        ms_coh, ms_rand = grid_ms(coh), grid_ms(pts)
-        gbs_c, gbs_r = (B * ALGO_BYTES_PER_SAMPLE_GRID / (m * 1e-3) / 1e9 for m in (ms_coh, ms_rand))
-        extra["hash_microbench"] = {"samples": B, "ms": ms_coh, "kernel": "grid_forward_d3c2 (stand-alone grid_encode_forward)",
-                                    "roofline": {"bound": "hbm", "achieved": gbs_c, "peak": hbm, "unit": "GB/s", "frac": gbs_c / hbm, "traffic": None,
-                                                 "peak_source": src, "inputs": "ray-coherent warped samples: 2^15 rays x 128 samples, 0.0017 apart"},
-                                    "uniform_random": {"ms": ms_rand, "achieved": gbs_r, "frac": gbs_r / hbm, "inputs": "uniform random in [0,1]^3 (no reuse between lanes)"}}
-        M = 1 << 21
-        xs = (torch.rand(M, 3, device=dev, generator=g) * 2 - 1); ds = torch.nn.functional.normalize(torch.randn(M, 3, device=dev, generator=g), dim=-1)
+                ts.append(a.elapsed_time(b))
+            return float(np.mean(ts))
         ms_field = time_kernel(lambda: model.forward_fused(xs, ds, mode=0))
         ms_field_tc = time_kernel(lambda: model.forward_fused(xs, ds, mode=1))
-        # tensor work actually issued: 3 bf16 MMAs per GEMM on padded tiles (20480 MAC/sample x 3), vs the algorithmic 18688 FLOP
         tfl = M * MLP_FLOP_PER_SAMPLE / (ms_field_tc * 1e-3) / 1e12
         extra["field_pass"] = {"samples": M, "ms_fp32_simt": ms_field, "ms_tcgen05": ms_field_tc,
                                "roofline": {"bound": "tensor", "achieved": tfl, "peak": tf, "unit": "TFLOP/s", "frac": tfl / tf, "traffic": None, "peak_source": src,
                                             "note": "algorithmic 18688 FLOP/sample; kernel = hash encode + 5-layer MLP (bf16x3 split, 3 MMAs per GEMM); gather-bound, not tensor-bound"}}
+        if hasattr(model, "mlp_only"):
+            enc = torch.randn(M, 32, device=dev, generator=g)
+            ms_mlp = time_kernel(lambda: model.mlp_only(enc, ds))
+            tfm = M * MLP_FLOP_PER_SAMPLE / (ms_mlp * 1e-3) / 1e12
+            extra["mlp_pass"] = {"samples": M, "ms": ms_mlp, "kernel": "wave_field_ws_kernel with the hash gather replaced by a coalesced load of pre-encoded features",
+                                 "roofline": {"bound": "tensor", "achieved": tfm, "peak": tf, "unit": "TFLOP/s", "frac": tfm / tf, "traffic": None, "peak_source": src,
+                                              "issued": tfm * 3 * 20480 / 18688, "note": "achieved = algorithmic 18688 FLOP/sample; issued = 3 bf16 MMAs per GEMM on 32/64/16-padded tiles"}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -222,28 +277,33 @@ def run_ours(args):
 
     K = args.steps
     fps = K / (total_ms * 1e-3)
-    render_ms = float(np.mean(kms["render"])); field_ms = float(np.mean(kms["field"])); field0_ms = float(np.mean(kms["field_launch"]))
-    st = np.mean(np.asarray(samples, dtype=np.float64), axis=0)           # composited, rays hit, field evaluations, field rows
-    samp, evaluated, rows = float(st[0]), float(st[2]), float(st[3])
+    evaluated_all = float(allr[:, 2].sum())
+    samp, evaluated, rows = float(stats[0]), float(stats[2]), float(stats[3])
     achieved = evaluated * ALGO_BYTES_PER_SAMPLE_FUSED / (field_ms * 1e-3) / 1e9
+    traffic = ncu_traffic(args.config, world)
     line = {
-        "metric": f"simulated+rendered frames/s at {W}x{H}", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "metric": f"simulated+rendered frames/s at {W}x{H}", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 render / f64 sim",
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": f"{args.config}: {sim.n_ip}-IP Q-GMLS body ({sim.n_k} kernels, sim_iters {sim.iters}) + {W}x{H} deformed render, "
-                               f"random-init 16-level hash grid + 64-wide MLP, density_scale {args.density_scale}, num_seek_IP {opt.num_seek_IP}",
-                   "rays": N, "n_ip": sim.n_ip, "kept_samples_per_frame": samp, "field_evaluations_per_frame": evaluated,
-                   "parallelism": f"16x16 ray tiles over {world} GPU(s), simulator on rank 0" + (f", sim-aware tile weights {[round(x, 4) for x in calib['weights']]}" if calib else ""),
-                   "l2": "flushed between timed frames (256 MiB fill)"},
-        "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 64 + 16, "d2h_bytes_per_step": N * 5 * 4,
-                "wall_fps": K / e2e_wall, "api": "pienerf_b200.frame.DistFrameDriver.frame(): host pose -> pn_get_rays -> sim step -> (bcast) -> pn_render_deformed -> (gather) -> async copy to pinned host frame (double buffered)"},
-        "gpu_launches": n_launch,
+        "config": workload_config(args, sim.n_ip, sim.n_k, sim.iters, W, H, opt.num_seek_IP),
+        "details": {"kept_samples_per_frame_rank0": samp, "field_evaluations_per_frame": evaluated_all,
+                    "parallelism": f"16x16 ray tiles over {world} GPU(s), simulator on rank 0; {pipe.S} frames in flight per GPU (one CUDA graph per rank-frame); "
+                                   + ("IP state pushed and pixels returned by peer-memory stores over NVLink (no collective in the frame loop)" if world > 1 else "single GPU")
+                                   + (f"; tile shares {[round(x, 4) for x in weights]}" if weights else ""),
+                    "l2": f"no flush in the timed loop: inputs larger than L2 — {pipe.S} frame slots rotate, each with its own 46.7 MiB copy of the hash table, "
+                          "its own sample lists and rays (per-frame traffic on rank 0 ~ %.0f MB); stand-alone kernel timings flush with a 256 MiB fill" % (rows * 40 / 1e6 + 46.7)},
+        "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 80, "d2h_bytes_per_step": N * 5 * 4,
+                "wall_fps": K / e2e_wall, "api": "pienerf_b200.pipeline.FramePipeline.frame(): pinned host pose -> H2D -> sim state + step -> (peer push) -> rays -> "
+                                                 "pn_render_deformed_ex -> (peer pixel stores) -> async D2H into pinned host frames (one per slot)"},
+        "gpu_launches": int(pipe.launches_per_frame * K),
+        "frame_checksum": checksum,
         "roofline": {"kernel": "wave_field_ws_kernel (16-level hash-grid gather + tcgen05 MLP over 128-row sample tiles; one launch per wavefront pass)",
                      "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": 96.1e6, "traffic_note": "dram__bytes_read+write of the first-pass launch (2.15 M rows, 2.2 GB algorithmic) in profiles/r1_ncu_summary.txt; the 46.7 MiB table is L2-resident",
+                     "traffic": traffic["bytes"], "traffic_note": traffic["note"],
                      "peak_source": src, "kernel_ms_per_frame": field_ms, "launches_per_frame": n_pass, "first_pass_launch_ms": field0_ms,
-                     "algorithmic_bytes": f"{ALGO_BYTES_PER_SAMPLE_FUSED} B/sample x {evaluated:.0f} field evaluations per frame (summed over the frame's launches; rows incl. slab padding: {rows:.0f})",
-                     "share_of_step": field_ms / (total_ms / K), "render_passes_ms_per_frame": render_ms},
+                     "algorithmic_bytes": f"{ALGO_BYTES_PER_SAMPLE_FUSED} B/sample x {evaluated:.0f} field evaluations per frame on rank 0 (summed over the frame's launches; rows incl. slab padding: {rows:.0f})",
+                     "measured": "eager un-pipelined frames, CUDA events around every field-kernel launch, L2 flushed before each frame",
+                     "share_of_eager_frame": field_ms / render_ms, "render_passes_ms_per_frame": render_ms},
         "clocks": clocks, "wall_fps": K / wall, "host_enqueue_ms_per_frame": 1e3 * enqueue_s[0] / max(enqueue_n[0], 1),
     }
     line.update(extra)
@@ -252,6 +312,17 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(config, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first-pass field-kernel launch, from the committed `ncu --set full`
+    capture of this config (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py).  None when there is no capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if world == 1 and os.path.exists(p):
+        d = json.load(open(p)).get(config)
+        if d:
+            return {"bytes": d["dram_bytes"], "note": f"first-pass launch ({d['rows']} rows), {d['source']}; the 46.7 MiB table is L2-resident within a frame"}
+    return {"bytes": None, "note": "no committed ncu capture for this config / GPU count"}
 
 
 # ------------------------------------------------------------------------------------------------- CPU baseline (oracle port)
@@ -296,8 +367,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the reference arm's host-side simulator must still get all cores
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(ncores)
     import torch
     from oracle.sim_oracle import OracleSimulator
+    OracleSimulator.set_threads(ncores)
     from pienerf_b200.synthetic import CONFIGS, make_body, make_field, occupancy_bitfield, orbit_intrinsics, orbit_pose
     cfg = CONFIGS[args.config]
     K, Wm = args.steps, max(args.warmup, 3)
@@ -310,6 +385,7 @@ def run_reference(args):
               "warmup": Wm, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 render / f64 sim", "data": "synthetic",
               "impl": "reference"}
     have_gpu = torch.cuda.is_available()
+    why = "no CUDA device"
     try:
         from oracle.ref_renderer import ReferenceRenderer
         ref = ReferenceRenderer(field, bits, bound=cfg["bound"], density_scale=args.density_scale, min_near=cfg["min_near"]) if have_gpu else None
@@ -319,7 +395,8 @@ def run_reference(args):
     if ref is None:
         cb = cpu_baseline(args, budget_s=30.0)
         line = dict(common, value=cb["value"], ms_per_step=1e3 / cb["value"], cpu_baseline=cb,
-                    config={"workload": f"{args.config} (oracle port on a bounded sample: reference kernels unavailable)"},
+                    config=workload_config(args, orc.n_ip, orc.n_k, 10, cfg["W"], cfg["H"], cfg["num_seek_IP"]),
+                    details={"arm": "oracle port on a bounded sample: reference kernels (oracle/_ref) unavailable: " + why},
                     e2e={"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         print(json.dumps(line))
         return
@@ -338,7 +415,7 @@ def run_reference(args):
         orc.stepforward()
         sim_t.append(time.perf_counter() - t0)
         out = ref.rund_cuda(rays_o, rays_d, torch.from_numpy(pos).to(dev), p_ori, torch.from_numpy(F).to(dev), torch.from_numpy(dF).to(dev),
-                            1.05 * cfg["sim_dx"], return_stats=True, **kw)
+                            1.05 * cfg["sim_dx"], return_stats=False, **kw)
         img = out["image"].cpu().numpy(); out["depth"].cpu().numpy(); out["depth_0"].cpu().numpy()   # trainer.py:589-593
         return out, img
     for _ in range(Wm):
@@ -351,11 +428,43 @@ def run_reference(args):
     torch.cuda.synchronize()
     total = time.perf_counter() - t0
     fps = K / total
-    line = dict(common, value=fps, ms_per_step=total / K * 1e3,
-                config={"workload": f"{args.config}: reference CUDA kernels (oracle/_ref, sm_100a build) in the reference rund_cuda loop + fp32 nn.Linear MLP; "
-                                    f"simulator = fp64 C restatement on host cores (Warp unavailable); density_scale {args.density_scale}",
-                        "kept_samples_per_frame": out["n_samples"], "loop_iterations": out["iters"],
-                        "timing": "wall clock between device synchronizes (the CPU sim step is part of the frame)"},
+    # sample / iteration counts of this frame: one extra UNTIMED frame (the per-iteration count costs a host sync each)
+    pos, F, dF = orc.get_IP_info()
+    out = ref.rund_cuda(rays_o, rays_d, torch.from_numpy(pos).to(dev), p_ori, torch.from_numpy(F).to(dev), torch.from_numpy(dF).to(dev),
+                        1.05 * cfg["sim_dx"], return_stats=True, **kw)
+    # the reference's own kernel_grid (gridencoder.cu:88-245) on the inputs of our hash microbench (BASELINE.json configs[4])
+    B = 1 << 22
+    g = torch.Generator(device=dev).manual_seed(0)
+    pts = torch.rand(B, 3, device=dev, generator=g)
+    nr = B // 128
+    o_ = torch.rand(nr, 1, 3, device=dev, generator=g) * 0.5 + 0.1
+    dd = torch.nn.functional.normalize(torch.rand(nr, 1, 3, device=dev, generator=g) + 0.1, dim=-1)
+    coh = (o_ + dd * (torch.arange(128, device=dev).view(1, 128, 1) * 0.0017)).reshape(B, 3).contiguous().clamp(0, 1)
+    outbuf = torch.empty(16, B, 2, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def ref_grid_ms(x):
+        fn = lambda: ref.ge.grid_encode_forward(x, ref.emb, ref.offsets, outbuf, B, 3, 2, 16, ref.S, ref.base_res, None, 0, False, 0)
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            flush.fill_(1.0)
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+    hbm, _, src = measured_peaks()
+    mc, mr = ref_grid_ms(coh), ref_grid_ms(pts)
+    hash_ref = {"kernel": "reference kernel_grid<float,3,2> (oracle/_ref/_ref_gridencoder.so, unmodified source, sm_100a build)", "samples": B,
+                "ms": mc, "achieved": B * ALGO_BYTES_PER_SAMPLE_GRID / (mc * 1e-3) / 1e9, "frac": B * ALGO_BYTES_PER_SAMPLE_GRID / (mc * 1e-3) / 1e9 / hbm,
+                "uniform_random": {"ms": mr, "achieved": B * ALGO_BYTES_PER_SAMPLE_GRID / (mr * 1e-3) / 1e9, "frac": B * ALGO_BYTES_PER_SAMPLE_GRID / (mr * 1e-3) / 1e9 / hbm},
+                "peak": hbm, "unit": "GB/s", "peak_source": src, "inputs": "same generators as the `ours` arm's hash_microbench at 1 GPU"}
+    line = dict(common, value=fps, ms_per_step=total / K * 1e3, hash_microbench_reference=hash_ref,
+                config=workload_config(args, orc.n_ip, orc.n_k, 10, cfg["W"], cfg["H"], cfg["num_seek_IP"]),
+                details={"arm": "reference CUDA kernels (oracle/_ref, unmodified source, sm_100a build) in the reference rund_cuda loop + fp32 nn.Linear MLP; "
+                                "simulator = fp64 C restatement on host cores (Warp unavailable)",
+                         "kept_samples_per_frame": out["n_samples"], "loop_iterations": out["iters"],
+                         "timing": "wall clock between device synchronizes (the CPU sim step is part of the frame)"},
                 cpu_baseline={"value": fps, "unit": "frames/s", "cores": OracleSimulator.threads(), "kind": "reference",
                               "sample": f"{K} whole frames; sim step {np.mean(sim_t) * 1e3:.1f} ms on {OracleSimulator.threads()} host threads, rest = reference GPU render loop"},
                 e2e={"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
@@ -376,8 +485,8 @@ def main():
     ap.add_argument("--config", default="chair")
     ap.add_argument("--density-scale", type=float, default=1.0, dest="density_scale")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap-sim", action="store_true", help="run the simulator step on the render stream instead of a concurrent side stream")
-    ap.add_argument("--equal-tiles", action="store_true", help="N>1: equal tile shares instead of sim-aware weights")
+    ap.add_argument("--slots", type=int, default=3, help="frames in flight per GPU (each with its own workspace and hash-table copy)")
+    ap.add_argument("--rank0-share", type=float, default=None, dest="rank0_share", help="N>1: rank 0's tile share relative to an equal split (e.g. 0.8)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--cpu-stride", type=int, default=16)
     args = ap.parse_args()

@@ -632,6 +632,14 @@ void qo_set_dof(QO *s, const double *dof, const double *vel) {
     if (vel) memcpy(s->dof_vel, vel, sizeof(double)*3*s->n);
 }
 void qo_build_rhs(const QO *s, double *out) { build_rhs(s, s->dof, out); }
+/* bench.py --impl reference under torchrun: the launcher exports OMP_NUM_THREADS=1; the reference arm must use every host core */
+void qo_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int qo_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

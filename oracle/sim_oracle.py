@@ -141,6 +141,10 @@ class OracleSimulator:
     def threads():
         return lib().qo_threads()
 
+    @staticmethod
+    def set_threads(n):
+        lib().qo_set_threads(C.c_int(int(n)))
+
 
 def svd3(F):
     F = np.ascontiguousarray(F, dtype=np.float64)

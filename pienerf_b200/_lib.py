@@ -146,8 +146,10 @@ def _chk(t, name, dtype=None, cuda=True, contiguous=True):
 
 
 def dptr(t, name="tensor", dtype=None):
-    """Device pointer of a checked tensor (None -> NULL)."""
+    """Device pointer of a checked tensor (None -> NULL; an int is taken as a raw device address, e.g. peer memory)."""
     if t is None:
         return vp(0)
+    if isinstance(t, int):
+        return vp(t)
     _chk(t, name, dtype)
     return vp(t.data_ptr())

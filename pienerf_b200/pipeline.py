@@ -1,0 +1,330 @@
+"""The frame loop as a device-side pipeline: several frames in flight per GPU, every per-rank frame one CUDA graph, and —
+on N GPUs of one NVLink node — the frame's two exchanges done by stores into peer memory instead of collectives.
+
+What a frame is (reference order, nerf/trainer.py:284-329,531-602): read the IP state, advance the simulator, render the
+state that was read BEFORE the step, hand the frame to the host.  Data flow here (rank 0 owns the simulator):
+
+    rank 0, sim stream    [cam H2D] -> ip_info -> (wait: peers finished the slot's previous frame) -> pn_peer_put of
+                          [cam | pos | F | dF] into every rank's state slot -> raise their `state` flags -> stepforward
+    every rank, slot s    wait `state` flag (own memory) -> rays of its tiles -> pn_render_deformed_ex: the compositor
+                          stores finished pixels straight into rank 0's frame slot over NVLink -> raise `done` flag on rank 0
+    rank 0, copy stream   wait all `done` flags -> frame slot -> pinned host buffer (async, double buffered by slot)
+
+Frames k, k+1, ... use slots k % S on their own streams, so the latency-bound parts of a frame (the small preparation
+kernels, near-empty late passes, the flag waits, launch gaps) overlap the bulk of its neighbours; what bounds the frame
+rate is the sum of kernel work per GPU, not the length of the dependency chain.  Every slot has its own workspace and
+its own copy of the hash table (S x 46.7 MiB > L2), so no frame finds its inputs L2-warm from the previous one.
+NCCL / torch.distributed is only used to exchange the 64-byte IPC handles at set-up.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _qgmls
+from ._lib import FrameIoT, check, dptr, lib, stream_ptr, vp
+
+
+class _CudaView:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerBlock:
+    """One cudaMalloc allocation that other processes on the node can map (CUDA IPC)."""
+
+    def __init__(self, nbytes, device):
+        self.nbytes = int((nbytes + 255) // 256 * 256)
+        self.device = device
+        p = vp()
+        check(lib.pn_peer_alloc(self.nbytes, C.byref(p)))
+        self.ptr = int(p.value)
+        self.bytes = torch.as_tensor(_CudaView(self.ptr, self.nbytes), device=device)
+        self._opened = []
+
+    def handle(self):
+        buf = C.create_string_buffer(64)
+        check(lib.pn_peer_export(vp(self.ptr), buf))
+        return buf.raw
+
+    def view(self, offset, dtype, shape):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        return self.bytes[offset:offset + n].view(dtype).view(*shape)
+
+    @staticmethod
+    def open(handle):
+        p = vp()
+        check(lib.pn_peer_open(handle, C.byref(p)))
+        return int(p.value)
+
+
+def _ptr_array(ptrs, device):
+    return torch.tensor([int(p) for p in ptrs], dtype=torch.int64, device=device)
+
+
+def _al(n, a=256):
+    return (int(n) + a - 1) // a * a
+
+
+class FramePipeline:
+    """Pipelined frame driver (see the module docstring).  world == 1 needs no process group.
+
+    frame(pose, intrinsics) enqueues one GUI frame and returns its slot; wait_host(slot) returns the pinned host frame once
+    it has landed; drain() joins every stream into the current one.  The simulator steps once per frame unless paused."""
+
+    def __init__(self, model, sim, opt, slots=3, tile=16, weights=None, timeout_ms=20000, table_copies=True, mode=3):
+        import torch.distributed as dist
+        from .dist import tile_partition
+        self.model, self.sim, self.opt = model, sim, opt
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.dev = next(model.parameters()).device
+        self.S, self.W, self.H, self.mode = int(slots), int(opt.W), int(opt.H), mode
+        self.timeout_ms = int(timeout_ms)
+        self.n_ip = n_ip = int(sim.n_ip) if sim is not None else int(model.p_ori.shape[0])
+        npx = self.W * self.H
+        dev = self.dev
+        # ---- static IP data: rest positions are the same on every rank (main_gui.py:50-56)
+        if self.rank == 0:
+            p_ori = sim.get_IP_info()[0]
+        else:
+            p_ori = torch.empty(n_ip, 3, dtype=torch.float32, device=dev)
+        if self.world > 1:
+            if dist.get_backend() == "nccl":
+                dist.broadcast(p_ori, src=0)
+            else:                                                               # gloo (two test ranks sharing one GPU): through the host
+                h = p_ori.cpu(); dist.broadcast(h, src=0); p_ori = h.to(dev)
+        self.p_ori = p_ori
+        model.p_ori = p_ori
+        model.IP_dx = float(opt.sim_dx) * 1.05
+        # ---- peer block: [state slots | state flags | done flags | (rank 0) frame slots]
+        self.state_floats = 32 + 39 * n_ip                                    # cam (20 used) | pos | F | dF
+        self.state_bytes = _al(self.state_floats * 4, 256)
+        self.off_state = 0
+        self.off_sflag = self.S * self.state_bytes
+        self.off_dflag = self.off_sflag + _al(self.S * 4)
+        self.off_frame = self.off_dflag + _al(self.S * self.world * 4)
+        self.frame_bytes = _al(npx * 5 * 4)
+        total = self.off_frame + (self.S * self.frame_bytes if self.rank == 0 else 0)
+        self.block = PeerBlock(total, dev)
+        self.peer_ptr = [self.block.ptr] * self.world                          # base address of every rank's block as seen from here
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.block.handle())
+            for r in range(self.world):
+                if r != self.rank:
+                    self.peer_ptr[r] = PeerBlock.open(handles[r])
+        # ---- partition of the frame
+        self.parts = tile_partition(self.H, self.W, self.world, tile, weights)
+        self.n_my = len(self.parts[self.rank])
+        self.pix = torch.from_numpy(self.parts[self.rank].astype(np.int32)).to(dev) if self.world > 1 else None
+        # ---- per-slot resources
+        need = model.workspace_bytes(self.n_my, n_ip, **opt)
+        self.slots = []
+        for s in range(self.S):
+            sl = {}
+            st = self.block.view(self.off_state + s * self.state_bytes, torch.float32, (self.state_floats,))
+            sl["state"] = st
+            sl["cam"] = st[:20]
+            sl["pos"] = st[32:32 + 3 * n_ip].view(n_ip, 3); sl["F"] = st[32 + 3 * n_ip:32 + 12 * n_ip].view(n_ip, 9)
+            sl["dF"] = st[32 + 12 * n_ip:32 + 39 * n_ip].view(n_ip, 27)
+            sl["workspace"] = torch.empty(need, dtype=torch.uint8, device=dev)
+            sl["stats"] = torch.zeros(8, dtype=torch.int64, device=dev)
+            sl["rays_o"] = torch.empty(self.n_my, 3, dtype=torch.float32, device=dev)
+            sl["rays_d"] = torch.empty(self.n_my, 3, dtype=torch.float32, device=dev)
+            sl["wsum"] = torch.empty(self.n_my, dtype=torch.float32, device=dev)
+            sl["table"] = model.encoder.embeddings.data if (s == 0 or not table_copies) else model.encoder.embeddings.data.clone()
+            sl["epoch"] = torch.zeros(1, dtype=torch.int32, device=dev)        # bumped by the slot's frame graph
+            sl["state_epoch"] = torch.zeros(1, dtype=torch.int32, device=dev)  # rank 0: bumped by the slot's state graph
+            sl["stream"] = torch.cuda.Stream(device=dev)
+            sl["render_done"] = None
+            sl["state_ready"] = None
+            sl["copy_done"] = None
+            # the frame this rank's compositor writes into: rank 0's slot (peer memory for the other ranks)
+            fbase = self.peer_ptr[0] + self.off_frame + s * self.frame_bytes
+            if self.rank == 0:
+                fb = self.block.view(self.off_frame + s * self.frame_bytes, torch.float32, (npx * 5,))
+                sl["frame"] = {"image": fb[:3 * npx].view(npx, 3), "depth": fb[3 * npx:4 * npx], "depth_0": fb[4 * npx:5 * npx]}
+                sl["cam_host"] = torch.zeros(20, dtype=torch.float32).pin_memory()
+                sl["host"] = {"image": torch.empty(npx, 3, dtype=torch.float32).pin_memory(), "depth": torch.empty(npx, dtype=torch.float32).pin_memory(),
+                              "depth_0": torch.empty(npx, dtype=torch.float32).pin_memory()}
+            sl["frame_ptr"] = (fbase, fbase + 12 * npx, fbase + 16 * npx)
+            # flag addresses
+            sl["my_state_flag"] = self.block.ptr + self.off_sflag + 4 * s
+            sl["state_flags_all"] = _ptr_array([self.peer_ptr[r] + self.off_sflag + 4 * s for r in range(1, self.world)], dev) if self.world > 1 else None
+            sl["state_dsts"] = _ptr_array([self.peer_ptr[r] + self.off_state + s * self.state_bytes for r in range(1, self.world)], dev) if self.world > 1 else None
+            sl["done_local"] = _ptr_array([self.block.ptr + self.off_dflag + 4 * (s * self.world + r) for r in range(1, self.world)], dev) if self.world > 1 else None
+            sl["my_done_flag"] = _ptr_array([self.peer_ptr[0] + self.off_dflag + 4 * (s * self.world + self.rank)], dev)
+            sl["wait_arr"] = _ptr_array([sl["my_state_flag"]], dev)
+            sl["graph"] = None
+            sl["state_graph"] = None
+            self.slots.append(sl)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sim_stream = torch.cuda.Stream(device=dev, priority=-1) if self.rank == 0 else None
+        self.copy_stream = torch.cuda.Stream(device=dev) if self.rank == 0 else None
+        self.frame_id = 0
+        self.launches_per_frame = 0
+        self._warm = False
+
+    # ------------------------------------------------------------------------------------------ graph bodies
+    def _io(self, sl):
+        io = FrameIoT()
+        io.pix = dptr(self.pix) if self.pix is not None else vp(0)
+        io.epoch = dptr(sl["epoch"])
+        if self.world > 1 and self.rank != 0:
+            io.wait_flag, io.n_wait = dptr(sl["wait_arr"]), 1
+            io.signal_flag, io.n_signal = dptr(sl["my_done_flag"]), 1
+        else:
+            io.wait_flag, io.n_wait, io.signal_flag, io.n_signal = vp(0), 0, vp(0), 0
+        io.status, io.timeout_ms = dptr(self.status), self.timeout_ms
+        return io
+
+    def _frame_body(self, sl, sync=True):
+        """rays of this rank's tiles + the deformed render into rank 0's frame slot (+ on rank 0: wait for the peers' pixels)."""
+        m = self.model
+        check(lib.pn_get_rays_pix(dptr(sl["cam"]), self.H, self.W, dptr(self.pix) if self.pix is not None else vp(0), self.n_my,
+                                  dptr(sl["rays_o"]), dptr(sl["rays_d"]), stream_ptr()))
+        fp = sl["frame_ptr"]
+        if self.rank == 0:
+            out = {"image": sl["frame"]["image"], "depth": sl["frame"]["depth"], "depth_0": sl["frame"]["depth_0"], "weights_sum": sl["wsum"]}
+        else:                                                                   # raw addresses of rank 0's frame slot (peer memory)
+            out = {"image": fp[0], "depth": fp[1], "depth_0": fp[2], "weights_sum": sl["wsum"]}
+        io = self._io(sl) if sync else None
+        if io is None and self.pix is not None:
+            io = FrameIoT(); io.pix = dptr(self.pix)
+        m.render_deformed(sl["rays_o"], sl["rays_d"], out=out, workspace=sl["workspace"], stats=sl["stats"], io=io, embeddings=sl["table"],
+                          ip_state=(sl["pos"], self.p_ori, sl["F"], sl["dF"]), mode=self.mode, **self.opt)
+        n = 1 + m._render_launches
+        if sync and self.rank == 0 and self.world > 1:                          # the frame is complete when every peer's pixels are in
+            check(lib.pn_epoch_wait(dptr(sl["epoch"]), 0, dptr(sl["done_local"]), self.world - 1, 0, dptr(self.status), self.timeout_ms, stream_ptr()))
+            n += 1
+        return n
+
+    def _state_body(self, sl, sync=True):
+        """rank 0: camera + IP state of this frame into the slot, then out to every rank."""
+        sl["cam"].copy_(sl["cam_host"], non_blocking=True)
+        self.sim.get_IP_info(out=(sl["pos"], sl["F"], sl["dF"]))                # state BEFORE the step (trainer.py:303-306)
+        n = 2
+        if self.world > 1 and sync:
+            # the slot's previous frame must be finished everywhere before its state (and rank 0's frame slot) are overwritten
+            check(lib.pn_epoch_wait(dptr(sl["state_epoch"]), 1, dptr(sl["done_local"]), self.world - 1, 1, dptr(self.status), self.timeout_ms, stream_ptr()))
+            check(lib.pn_peer_put(dptr(sl["state"]), _al(self.state_floats * 4, 16), dptr(sl["state_dsts"]), self.world - 1, stream_ptr()))
+            check(lib.pn_epoch_signal(dptr(sl["state_epoch"]), dptr(sl["state_flags_all"]), self.world - 1, stream_ptr()))
+            n += 3
+        return n
+
+    def _capture(self, fn, stream):
+        g = torch.cuda.CUDAGraph()
+        cur = torch.cuda.current_stream()
+        stream.wait_stream(cur)
+        with torch.cuda.stream(stream):
+            with torch.cuda.graph(g, stream=stream):
+                n = fn()
+        cur.wait_stream(stream)
+        return g, n
+
+    def build(self, pose, intrinsics):
+        """Warm every kernel up eagerly (no flags, so epochs stay in step across ranks), then capture the graphs."""
+        cam = self._cam(pose, intrinsics)
+        for sl in self.slots:
+            if self.rank == 0:
+                sl["cam_host"].copy_(cam)
+                self._state_body(sl, sync=False)
+            else:
+                sl["cam"].copy_(cam.to(self.dev))
+                sl["pos"].copy_(self.p_ori); sl["F"].zero_(); sl["F"][:, 0] = 1; sl["F"][:, 4] = 1; sl["F"][:, 8] = 1; sl["dF"].zero_()
+            self._frame_body(sl, sync=False)
+        if self.rank == 0 and self.sim is not None:
+            dof, vel = self.sim.dof.clone(), self.sim.dof_vel.clone()
+            self.sim.stepforward(); self.sim.stepforward()                      # plain call + graph capture inside the simulator
+            self.sim.dof.copy_(dof); self.sim.dof_vel.copy_(vel)
+        torch.cuda.synchronize()
+        self._barrier()
+        n_frame = n_state = 0
+        for sl in self.slots:
+            sl["graph"], n_frame = self._capture(lambda sl=sl: self._frame_body(sl), sl["stream"])
+            if self.rank == 0:
+                sl["state_graph"], n_state = self._capture(lambda sl=sl: self._state_body(sl), self.sim_stream)
+        self.launches_per_frame = n_frame + n_state + ((3 + 4 * int(self.sim.iters)) if self.rank == 0 else 0)
+        torch.cuda.synchronize()
+        self._barrier()
+        self._warm = True
+
+    def _barrier(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+
+    @staticmethod
+    def _cam(pose, intrinsics):
+        p = torch.as_tensor(np.asarray(pose, dtype=np.float32)).reshape(-1)[:16]
+        return torch.cat([p, torch.as_tensor(np.asarray(intrinsics, dtype=np.float32)).reshape(4)])
+
+    # ------------------------------------------------------------------------------------------ per frame
+    @torch.no_grad()
+    def frame(self, pose, intrinsics, to_host=True, paused=False):
+        """Enqueue one GUI frame (host pose -> frame in rank 0's slot [-> pinned host buffer]).  Returns the slot index."""
+        if not self._warm:
+            self.build(pose, intrinsics)
+        s = self.frame_id % self.S
+        sl = self.slots[s]
+        cur = torch.cuda.current_stream()
+        if self.rank == 0:
+            if sl["state_ready"] is not None:
+                sl["state_ready"].synchronize()                                  # bounds the host's run-ahead to S frames (cam_host reuse)
+            sl["cam_host"].copy_(self._cam(pose, intrinsics))
+            sim_st = self.sim_stream
+            sim_st.wait_stream(cur)
+            if sl["render_done"] is not None:
+                sim_st.wait_event(sl["render_done"])                             # rank 0's previous frame in this slot has read the old state
+            if sl["copy_done"] is not None:
+                sim_st.wait_event(sl["copy_done"])                               # ... and its pixels have left for the host
+            with torch.cuda.stream(sim_st):
+                sl["state_graph"].replay()
+                ev = torch.cuda.Event(); ev.record(sim_st)
+                sl["state_ready"] = ev
+                if not paused:
+                    self.sim.stepforward()                                       # trainer.py:308 — concurrent with the render of the state read above
+            sl["stream"].wait_stream(cur)
+            sl["stream"].wait_event(sl["state_ready"])
+        else:
+            if sl["render_done"] is not None:
+                sl["render_done"].synchronize()                                  # host run-ahead bound
+            sl["stream"].wait_stream(cur)
+        with torch.cuda.stream(sl["stream"]):
+            sl["graph"].replay()
+            ev = torch.cuda.Event(); ev.record(sl["stream"])
+            sl["render_done"] = ev
+        if self.rank == 0 and to_host:
+            cs = self.copy_stream
+            cs.wait_event(sl["render_done"])
+            with torch.cuda.stream(cs):
+                for k in ("image", "depth", "depth_0"):                          # trainer.py:589-593 .cpu().numpy() of the frame
+                    sl["host"][k].copy_(sl["frame"][k], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(cs)
+                sl["copy_done"] = ev
+        self.frame_id += 1
+        return s
+
+    def drain(self):
+        """Make the current stream wait for everything enqueued so far (frames, simulator, host copies)."""
+        cur = torch.cuda.current_stream()
+        for sl in self.slots:
+            cur.wait_stream(sl["stream"])
+        if self.rank == 0:
+            cur.wait_stream(self.sim_stream); cur.wait_stream(self.copy_stream)
+
+    def wait_host(self, slot):
+        if self.rank != 0:
+            return None
+        sl = self.slots[slot]
+        if sl["copy_done"] is not None:
+            sl["copy_done"].synchronize()
+        return sl["host"]
+
+    def check(self):
+        """After a synchronize: raise if a flag wait timed out or a frame reported an error."""
+        code = int(self.status.item())
+        if code:
+            raise RuntimeError(f"rank {self.rank}: peer flag wait timed out (code {code}) — a rank died or fell more than {self.timeout_ms} ms behind")
+        return [self.model.check_stats(sl["stats"]) for sl in self.slots]
