@@ -133,7 +133,7 @@ def run_ours(args):
     if world > 1 and args.rank0_share is not None:                            # rank 0 also runs the simulator: optional smaller tile share
         f0 = args.rank0_share / world
         weights = [f0] + [(1.0 - f0) / (world - 1)] * (world - 1)
-    pipe = FramePipeline(model, sim, opt, slots=args.slots, weights=weights)
+    pipe = FramePipeline(model, sim, opt, slots=args.slots, weights=weights, sim_sm_reserve=args.sim_sm_reserve)
     pipe.build(pose, intr)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2 (stand-alone kernel timings only)
     n_pass = int(_lib.lib.pn_render_pass_count(int(opt.max_steps)))
@@ -224,7 +224,7 @@ def run_ours(args):
 
     # ---- stand-alone kernel rooflines (hash microbench on EVERY rank = BASELINE.json configs[4]; MLP pass on rank 0)
     hbm, tf, src = measured_peaks()
-    ms_coh, ms_rand, Bm = hash_microbench(model, dev, rank, world, flush, hbm, src)
+    ms_coh, ms_rand, Bm = hash_microbench(model, dev, rank, world, flush, hbm, src) if not args.quick else (1.0, 1.0, 1)
     per_rank = torch.tensor([ms_coh, ms_rand, stats[2], field_ms], dtype=torch.float64, device=dev)
     allr = [torch.zeros_like(per_rank) for _ in range(world)]
     if world > 1:
@@ -233,7 +233,7 @@ def run_ours(args):
         allr = [per_rank]
     allr = np.asarray([t.tolist() for t in allr])
     extra = {}
-    if rank == 0:
+    if rank == 0 and not args.quick:
         gb = Bm * ALGO_BYTES_PER_SAMPLE_GRID / 1e9
         agg_c, agg_r = world * gb / (allr[:, 0].max() * 1e-3), world * gb / (allr[:, 1].max() * 1e-3)
         extra["hash_microbench"] = {
@@ -289,7 +289,8 @@ def run_ours(args):
         "details": {"kept_samples_per_frame_rank0": samp, "field_evaluations_per_frame": evaluated_all,
                     "parallelism": f"16x16 ray tiles over {world} GPU(s), simulator on rank 0; {pipe.S} frames in flight per GPU (one CUDA graph per rank-frame); "
                                    + ("IP state pushed and pixels returned by peer-memory stores over NVLink (no collective in the frame loop)" if world > 1 else "single GPU")
-                                   + (f"; tile shares {[round(x, 4) for x in weights]}" if weights else ""),
+                                   + (f"; tile shares {[round(x, 4) for x in weights]}" if weights else "")
+                                   + (f"; rank 0 keeps {pipe.sim_sm_reserve} SMs out of its render grids for the simulator" if pipe.sim_sm_reserve else ""),
                     "l2": f"no flush in the timed loop: inputs larger than L2 — {pipe.S} frame slots rotate, each with its own 46.7 MiB copy of the hash table, "
                           "its own sample lists and rays (per-frame traffic on rank 0 ~ %.0f MB); stand-alone kernel timings flush with a 256 MiB fill" % (rows * 40 / 1e6 + 46.7)},
         "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 80, "d2h_bytes_per_step": N * 5 * 4,
@@ -307,7 +308,7 @@ def run_ours(args):
         "clocks": clocks, "wall_fps": K / wall, "host_enqueue_ms_per_frame": 1e3 * enqueue_s[0] / max(enqueue_n[0], 1),
     }
     line.update(extra)
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.quick:
         line["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_budget)
     print(json.dumps(line))
     if world > 1:
@@ -487,6 +488,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=3, help="frames in flight per GPU (each with its own workspace and hash-table copy)")
     ap.add_argument("--rank0-share", type=float, default=None, dest="rank0_share", help="N>1: rank 0's tile share relative to an equal split (e.g. 0.8)")
+    ap.add_argument("--sim-sm-reserve", type=int, default=None, dest="sim_sm_reserve", help="SMs rank 0 keeps out of its render grids for the simulator (default 16 when N>1, else 0)")
+    ap.add_argument("--quick", action="store_true", help="skip the stand-alone kernel microbenches and the CPU baseline (development runs)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--cpu-stride", type=int, default=16)
     args = ap.parse_args()

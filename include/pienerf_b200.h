@@ -172,6 +172,10 @@ int pn_epoch_wait(uint32_t *epoch, int bump, const uint32_t *const *flags_dev, i
                   uint32_t timeout_ms, void *stream);
 int pn_epoch_signal(const uint32_t *epoch, uint32_t *const *flags_dev, int n_flags, void *stream);
 
+/* Size the persistent march / field grids of mode 3 for (SM count - n_sm) SMs, leaving n_sm SMs' worth of CTA slots to kernels of
+ * other streams (the simulator's launches on the GPU that also renders).  0 = use every SM (default).  Process-wide; a CUDA
+ * graph captured afterwards keeps the grid sizes it was captured with. */
+int pn_set_render_sm_reserve(int n_sm);
 /* Optional profiling hook: two cudaEvent_t (as void*) that pn_render_deformed records on its stream right
  * around the persistent render kernel (NULL, NULL disables).  Used by bench.py for the roofline line. */
 int pn_set_profile_events(void *start_event, void *stop_event);
@@ -226,6 +230,12 @@ typedef struct {
 } pn_qgmls_step_t;
 uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k, int adj_slices);
 int pn_qgmls_step(const pn_qgmls_step_t *step_host, int solver /*0 dense inverse, 1 PCG on A*/, void *stream);
+/* How pn_qgmls_step (solver 0) runs: force_multi_kernel = 1 (default) = 3 + 4*iters launches; 0 = ONE thread-block-cluster
+ * kernel for the whole step when the system is small enough (n <= 1280; experimental, measured slower on B200).  The two
+ * differ by fp64 round-off (different fixed summation order in the rhs gather); each is bit-reproducible. */
+int pn_qgmls_step_mode(int force_multi_kernel);
+/* kernels one pn_qgmls_step enqueues for this problem size (1 when the cluster kernel applies) */
+int pn_qgmls_step_launches(int n_ip, int n_k, int iters, int solver, int pcg_iters);
 /* simulator/solver.py:402-424 get_IP_info + cuda_utils.py:206-233 update_F_kernel: emits the fp32
  * renderer layouts directly: pos [n,3], F [n,9] (F[b][a] at a*3+b), dF [n,27] (c*9+r*3+j). */
 int pn_qgmls_ip_info(const int *topo, const double *dof, const double *Nx, const double *dNx, const double *ddNx,

@@ -84,6 +84,7 @@ _PROTOS = {
     "pn_epoch_wait": (i32, [vp, i32, vp, i32, u32, vp, u32, vp]),
     "pn_epoch_signal": (i32, [vp, vp, i32, vp]),
     "pn_render_workspace_bytes": (u64, [u32, i32, f32, f32]),
+    "pn_set_render_sm_reserve": (i32, [i32]),
     "pn_set_profile_events": (i32, [vp, vp]),
     "pn_set_profile_event_list": (i32, [vp, i32]),
     "pn_render_pass_count": (i32, [u32]),
@@ -96,6 +97,8 @@ _PROTOS = {
     "pn_qgmls_matvec3": (i32, [vp, vp, i32, vp, vp]),
     "pn_qgmls_step_scratch_doubles": (u64, [i32, i32, i32]),
     "pn_qgmls_step": (i32, [C.POINTER(QgmlsStepT), i32, vp]),
+    "pn_qgmls_step_mode": (i32, [i32]),
+    "pn_qgmls_step_launches": (i32, [i32, i32, i32, i32, i32]),
     "pn_qgmls_ip_info": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "pn_qgmls_update_pos": (i32, [vp, vp, vp, i32, vp, vp]),
     "pn_qgmls_update_force": (i32, [i32, vp, vp, vp, vp, f64, i32, vp, vp]),

@@ -70,6 +70,20 @@ def step(desc, solver=0):
     check(lib.pn_qgmls_step(C.byref(desc), int(solver), stream_ptr()))
 
 
+_step_mode = [True]
+
+
+def step_mode(force_multi_kernel):
+    """True (default): 3 + 4*iters launches replayed as one CUDA graph; False: the whole step as ONE thread-block-cluster kernel
+    when n <= 1280 (experimental: measured slower on B200)."""
+    check(lib.pn_qgmls_step_mode(1 if force_multi_kernel else 0))
+    _step_mode[0] = bool(force_multi_kernel)
+
+
+def step_mode_value():
+    return _step_mode[0]
+
+
 def ip_info(topo, dof, Nx, dNx, ddNx, pos, F, dF):
     check(lib.pn_qgmls_ip_info(dptr(topo, "topo", i32), dptr(dof, "dof", f64), dptr(Nx, "Nx", f64), dptr(dNx, "dNx", f64),
                                dptr(ddNx, "ddNx", f64), topo.shape[0], dptr(pos, "pos", torch.float32), dptr(F, "F", torch.float32),

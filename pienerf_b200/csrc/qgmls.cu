@@ -250,21 +250,28 @@ __device__ void svd3x3(const double *F, double *U, double *sg, double *V) {
     double S[9];
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) S[i * 3 + j] = F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j];
     double Q[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    // the three rotations of a sweep are spelled out with constant indices so that S and Q stay in registers
+    // (a (p, q) loop indexes them dynamically -> local memory on the serial critical path of every step)
+#define PN_JACOBI(p, q)                                                                                                   \
+    {                                                                                                                     \
+        const double apq = S[p * 3 + q];                                                                                  \
+        if (apq != 0.0) {                                                                                                 \
+            const double th = (S[q * 3 + q] - S[p * 3 + p]) / (2.0 * apq);                                                \
+            const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));                                   \
+            const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;                                                          \
+            _Pragma("unroll") for (int k = 0; k < 3; k++) { const double a = S[k * 3 + p], b = S[k * 3 + q]; S[k * 3 + p] = c * a - s * b; S[k * 3 + q] = s * a + c * b; } \
+            _Pragma("unroll") for (int k = 0; k < 3; k++) { const double a = S[p * 3 + k], b = S[q * 3 + k]; S[p * 3 + k] = c * a - s * b; S[q * 3 + k] = s * a + c * b; } \
+            _Pragma("unroll") for (int k = 0; k < 3; k++) { const double a = Q[k * 3 + p], b = Q[k * 3 + q]; Q[k * 3 + p] = c * a - s * b; Q[k * 3 + q] = s * a + c * b; } \
+        }                                                                                                                 \
+    }
     for (int sweep = 0; sweep < 12; sweep++) {
         const double off = fabs(S[1]) + fabs(S[2]) + fabs(S[5]);
         if (off <= 1e-30 * (fabs(S[0]) + fabs(S[4]) + fabs(S[8]))) break;
-        for (int p = 0; p < 2; p++)
-            for (int q = p + 1; q < 3; q++) {
-                const double apq = S[p * 3 + q];
-                if (apq == 0.0) continue;
-                const double th = (S[q * 3 + q] - S[p * 3 + p]) / (2.0 * apq);
-                const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 3; k++) { const double a = S[k * 3 + p], b = S[k * 3 + q]; S[k * 3 + p] = c * a - s * b; S[k * 3 + q] = s * a + c * b; }
-                for (int k = 0; k < 3; k++) { const double a = S[p * 3 + k], b = S[q * 3 + k]; S[p * 3 + k] = c * a - s * b; S[q * 3 + k] = s * a + c * b; }
-                for (int k = 0; k < 3; k++) { const double a = Q[k * 3 + p], b = Q[k * 3 + q]; Q[k * 3 + p] = c * a - s * b; Q[k * 3 + q] = s * a + c * b; }
-            }
+        PN_JACOBI(0, 1)
+        PN_JACOBI(0, 2)
+        PN_JACOBI(1, 2)
     }
+#undef PN_JACOBI
     double lam[3] = {S[0], S[4], S[8]};
     int o0 = 0, o1 = 1, o2 = 2;
     if (lam[o1] > lam[o0]) { const int t = o0; o0 = o1; o1 = t; }
@@ -450,6 +457,246 @@ __global__ void finish_step_kernel(const double *__restrict__ dof, const double 
                                    double *__restrict__ vel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n3) vel[i] = (dof[i] - last[i]) / dt * 0.998;  // solver.py:602
+}
+
+// ---------------------------------------------------------------- the whole step as ONE thread-block-cluster kernel
+// stepforward (solver.py:574-602) is a strictly sequential chain — per local-global iteration: per-IP F + SVD, rhs gather,
+// one dense mat-vec — over a few thousand IPs and a few hundred DOFs: as 3 + 4*iters launches it is pure launch latency
+// (43 graph nodes, 0.31 ms), and on the GPU that also renders, every one of those launches queues behind persistent render
+// CTAs.  Here one cluster of kStepCluster CTAs (one GPC) runs the entire step: phases are separated by the hardware
+// cluster barrier (barrier.cluster, release/acquire), DOFs and the rhs live in shared memory, everything that crosses CTAs
+// goes through L2 (written with plain stores, read back with ld.global.cg after the barrier).  Each phase repeats the
+// arithmetic of the stand-alone kernels above operation for operation (same lane mapping, same reduction trees), so the
+// result is bit-identical to the multi-kernel path (tested) and steps stay bit-reproducible.
+struct StepClusterArgs {
+    int n_ip, n_k, n, iters, slices;
+    double dt, dx3;
+    const int *topo; const double *mu, *lam, *dNx;
+    const int *adj_bgn, *adj;
+    const double *Ainv, *M, *dof_rest, *dof_f, *rhs_rest, *rhs_gravity;
+    double *dof, *dof_vel;
+    double *stress, *last, *mom, *partial;     // scratch in global memory (L2)
+    long long *prof;                           // [8] cycles of CTA 0 per phase, summed over the iterations (diagnostics)
+};
+constexpr int kStepThreads = 512;
+constexpr int kGatherUnroll = 2;           // entries in flight per lane group in the rhs gather
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+
+// y[row] = (Mat x)[row] (+ add0 + add1) for the rows of this cluster-wide warp; x in shared memory.  Lane j takes the
+// element pairs j, j + 32, ... of the row (matvec3_kernel's partition), four 128-bit row loads in flight per lane.
+__device__ __forceinline__ void cluster_matvec_rows(const double *__restrict__ mat, const double *x_s, int n, int gwarp, int nwarps, int lane,
+                                                    const double *__restrict__ add0, const double *__restrict__ add1, double *__restrict__ y) {
+    for (int row = gwarp; row < n; row += nwarps) {
+        const double *m = mat + (size_t)row * n;
+        double a0 = 0, a1 = 0, a2 = 0;
+        if ((n & 1) == 0) {
+            const double2 *m2 = reinterpret_cast<const double2 *>(m);
+            const int h = n / 2;
+            for (int j0 = lane; j0 < h; j0 += 128) {
+                double2 w[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) w[u] = (j0 + 32 * u < h) ? __ldg(m2 + j0 + 32 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j0 + 32 * u < h) {
+                        const double *xa = x_s + 6 * (size_t)(j0 + 32 * u);
+                        a0 += w[u].x * xa[0] + w[u].y * xa[3]; a1 += w[u].x * xa[1] + w[u].y * xa[4]; a2 += w[u].x * xa[2] + w[u].y * xa[5];
+                    }
+                }
+            }
+        } else {
+            for (int j = lane; j < n; j += 32) {
+                const double w = __ldg(m + j);
+                a0 += w * x_s[3 * j]; a1 += w * x_s[3 * j + 1]; a2 += w * x_s[3 * j + 2];
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(kFull, a0, o); a1 += __shfl_xor_sync(kFull, a1, o); a2 += __shfl_xor_sync(kFull, a2, o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                double v = c == 0 ? a0 : (c == 1 ? a1 : a2);
+                if (add0) v += add0[3 * row + c];
+                if (add1) v += add1[3 * row + c];
+                y[3 * row + c] = v;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kStepThreads, 1) qgmls_step_cluster_kernel(const StepClusterArgs a) {
+    extern __shared__ __align__(16) double step_smem[];
+    const int n3 = 3 * a.n;
+    double *dof_s = step_smem;                 // [n3] current DOFs (every CTA holds a copy)
+    double *vec_s = dof_s + n3;                // [n3] dof_tilde, then the rhs of each iteration
+    double *F_s = vec_s + n3;                  // [ips_per_cta][9]
+    double *stage_s = nullptr;                 // [warps][960] gradient staging (7680 B per warp), placed after F_s below
+    const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gwarp = rank * (kStepThreads / 32) + wid, nwarps = C * (kStepThreads / 32);
+    const int ips_per_cta = ((a.n_ip + C - 1) / C + 3) & ~3;                  // multiple of 4: a warp's 4 IPs never straddle CTAs
+    stage_s = F_s + 9 * (size_t)ips_per_cta;
+    stage_s = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(stage_s) + 15) & ~uintptr_t(15));
+    const int ip0 = rank * ips_per_cta, ip1 = min(a.n_ip, ip0 + ips_per_cta);
+
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
+#define PN_STEP_TICK(k) { const long long t_ = clock64(); pc[k] += t_ - tc; tc = t_; }
+    // ---- dof_tilde = dof + dt vel, last = dof (solver.py:575,597); momentum = M/dt^2 tilde + f + g (solver.py:576)
+    for (int i = tid; i < n3; i += kStepThreads) {
+        const double d = a.dof[i];
+        dof_s[i] = d;
+        vec_s[i] = d + a.dt * a.dof_vel[i];
+        if (rank == 0) a.last[i] = d;
+    }
+    __syncthreads();
+    cluster_matvec_rows(a.M, vec_s, a.n, gwarp, nwarps, lane, a.dof_f, a.rhs_gravity, a.mom);
+    cluster_sync_all();
+    PN_STEP_TICK(0)
+
+    for (int it = 0; it < a.iters; it++) {
+        // ---- calc_elastic, part 1: F per IP, 8 lanes per IP (ip_stress_kernel's mapping and shuffle tree).  A warp's 4 IPs x 8
+        // corners x [3][10] gradients are ONE contiguous 7680-byte run of dNx: it is staged into shared memory with fifteen
+        // coalesced 128-bit loads per lane (per-lane 240-byte blocks read straight from global cost 32 sectors per instruction)
+        for (int t = tid; t < ips_per_cta * 8; t += kStepThreads) {
+            const int lv = t >> 3, v = ip0 + lv, i = t & 7;
+            const bool live = v < ip1;
+            const int v_warp = ip0 + ((t & ~31) >> 3);                         // first IP of this warp's run
+            double2 *st2 = reinterpret_cast<double2 *>(stage_s + (size_t)wid * 960);
+            const double2 *src2 = reinterpret_cast<const double2 *>(a.dNx + (size_t)v_warp * 240);
+            const int n2 = max(0, min(4, a.n_ip - v_warp)) * 120;             // double2 elements that exist
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 15; u++) { const int e = lane + 32 * u; if (e < n2) st2[e] = __ldg(src2 + e); }
+            __syncwarp();
+            double F[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (live) {
+                const double *dN = stage_s + (size_t)wid * 960 + (size_t)(t & 31) * 30;
+                const double *d = dof_s + 3 * (size_t)(a.topo[8 * v + i] * 10);
+#pragma unroll
+                for (int x = 0; x < 10; x++) {
+                    const double g0 = dN[x], g1 = dN[10 + x], g2 = dN[20 + x];
+                    const double d0 = d[3 * x], d1 = d[3 * x + 1], d2 = d[3 * x + 2];
+                    F[0] += d0 * g0; F[1] += d0 * g1; F[2] += d0 * g2;
+                    F[3] += d1 * g0; F[4] += d1 * g1; F[5] += d1 * g2;
+                    F[6] += d2 * g0; F[7] += d2 * g1; F[8] += d2 * g2;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 9; k++)
+                for (int o = 4; o > 0; o >>= 1) F[k] += __shfl_xor_sync(kFull, F[k], o);
+            if (live && i == 0) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) F_s[9 * lv + k] = F[k];
+            }
+        }
+        __syncthreads();
+        PN_STEP_TICK(1)
+        // ---- part 2: one thread per IP: SVD, R = U V^T, V = U proj(sigma) V^T, stress = dx^3 (mu R + lam V)
+        for (int lv = tid; lv < ip1 - ip0; lv += kStepThreads) {
+            const int v = ip0 + lv;
+            double F[9], U[9], sg[3], V[9], sp[3];
+#pragma unroll
+            for (int k = 0; k < 9; k++) F[k] = F_s[9 * lv + k];
+            svd3x3(F, U, sg, V);
+            volume_project(sg, sp);
+            const double m = a.mu[v], l = a.lam[v];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) {
+                    double x = 0, y = 0;
+                    for (int k = 0; k < 3; k++) { x += U[r * 3 + k] * V[c * 3 + k]; y += U[r * 3 + k] * sp[k] * V[c * 3 + k]; }
+                    a.stress[(size_t)v * 9 + r * 3 + c] = a.dx3 * (m * x + l * y);
+                }
+        }
+        PN_STEP_TICK(2)
+        cluster_sync_all();
+        PN_STEP_TICK(3)
+        // ---- collect_rhs_IP as a gather: one warp per (kernel, 128-entry slice).  Lane group g = lane / 10 (three groups, lanes
+        // 30-31 idle) walks the slice's entries g, g + 3, ... in order; lane x = lane % 10 of a group owns DOF slot x and reads the
+        // entry's three gradient rows with coalesced 80-byte loads; the 3x3 stress is a broadcast load.  Sums run in a fixed order
+        // (entry order within a group, then (g0 + g1) + g2): deterministic, no atomics, no 30 x 5 shuffle trees.
+        for (int item = gwarp; item < a.n_k * a.slices; item += nwarps) {
+            const int k = item / a.slices, sl = item % a.slices;
+            const int e0 = a.adj_bgn[k] + sl * 128, cnt = max(0, min(128, a.adj_bgn[k + 1] - e0));
+            int codes[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) codes[u] = (lane + 32 * u < cnt) ? a.adj[e0 + lane + 32 * u] : -1;
+            const int g = lane / 10, x = lane - 10 * g;
+            double r0 = 0, r1 = 0, r2 = 0;
+            for (int base = 0; base < cnt; base += 3 * kGatherUnroll) {       // warp-uniform trip count: every lane joins the shuffles
+                double S[kGatherUnroll][9], G[kGatherUnroll][3];
+                bool ok[kGatherUnroll];
+#pragma unroll
+                for (int u = 0; u < kGatherUnroll; u++) {
+                    const int j = base + 3 * u + g;
+                    ok[u] = g < 3 && j < cnt;
+                    // entry j's code sits in register codes[j / 32] of lane j % 32
+                    const int c0 = __shfl_sync(kFull, codes[0], j & 31), c1 = __shfl_sync(kFull, codes[1], j & 31);
+                    const int c2 = __shfl_sync(kFull, codes[2], j & 31), c3 = __shfl_sync(kFull, codes[3], j & 31);
+                    const int code = (j >> 5) == 0 ? c0 : ((j >> 5) == 1 ? c1 : ((j >> 5) == 2 ? c2 : c3));
+                    if (ok[u]) {
+                        const int v = code >> 3, i = code & 7;
+                        const double *Sp = a.stress + (size_t)v * 9;
+                        const double *dN = a.dNx + (size_t)v * 240 + i * 30 + x;
+#pragma unroll
+                        for (int q = 0; q < 9; q++) S[u][q] = __ldcg(Sp + q);
+                        G[u][0] = __ldg(dN); G[u][1] = __ldg(dN + 10); G[u][2] = __ldg(dN + 20);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kGatherUnroll; u++) {
+                    if (ok[u]) {
+                        r0 += S[u][0] * G[u][0] + S[u][1] * G[u][1] + S[u][2] * G[u][2];
+                        r1 += S[u][3] * G[u][0] + S[u][4] * G[u][1] + S[u][5] * G[u][2];
+                        r2 += S[u][6] * G[u][0] + S[u][7] * G[u][1] + S[u][8] * G[u][2];
+                    }
+                }
+            }
+            // (group 0 + group 1) + group 2, lanes 0-9 write slot x
+            const double b0 = __shfl_sync(kFull, r0, (lane + 10) & 31), b1 = __shfl_sync(kFull, r1, (lane + 10) & 31), b2 = __shfl_sync(kFull, r2, (lane + 10) & 31);
+            const double c0 = __shfl_sync(kFull, r0, (lane + 20) & 31), c1 = __shfl_sync(kFull, r1, (lane + 20) & 31), c2 = __shfl_sync(kFull, r2, (lane + 20) & 31);
+            if (lane < 10) {
+                double *o = a.partial + (size_t)item * 30 + 3 * lane;
+                o[0] = (r0 + b0) + c0; o[1] = (r1 + b1) + c1; o[2] = (r2 + b2) + c2;
+            }
+        }
+        PN_STEP_TICK(4)
+        cluster_sync_all();
+        PN_STEP_TICK(3)
+        // ---- rhs = momentum + gathered - rhs_rest (solver.py:599; rhs_final_kernel), every CTA its own copy in shared memory
+        for (int id = tid; id < n3; id += kStepThreads) {
+            const int k = id / 30, i = id % 30;
+            double sum = 0.0;
+            for (int sl = 0; sl < a.slices; sl++) sum += __ldcg(a.partial + ((size_t)k * a.slices + sl) * 30 + i);
+            vec_s[id] = (__ldcg(a.mom + id) + sum) - a.rhs_rest[id];
+        }
+        __syncthreads();
+        // ---- dof = dof_rest + Ainv rhs (solver.py:600-601)
+        cluster_matvec_rows(a.Ainv, vec_s, a.n, gwarp, nwarps, lane, a.dof_rest, nullptr, a.dof);
+        PN_STEP_TICK(5)
+        cluster_sync_all();
+        PN_STEP_TICK(3)
+        for (int i = tid; i < n3; i += kStepThreads) dof_s[i] = __ldcg(a.dof + i);
+        __syncthreads();
+        PN_STEP_TICK(6)
+    }
+    // ---- dof_vel = (dof - dof_last) / dt * 0.998 (solver.py:602)
+    for (int i = rank * kStepThreads + tid; i < n3; i += C * kStepThreads) a.dof_vel[i] = (dof_s[i] - __ldcg(a.last + i)) / a.dt * 0.998;
+    PN_STEP_TICK(7)
+#undef PN_STEP_TICK
+    if (a.prof && rank == 0 && tid == 0)
+        for (int k = 0; k < 8; k++) a.prof[k] = pc[k];
+}
+
+size_t step_cluster_smem(int n_ip, int n, int C) {
+    const int ips_per_cta = ((n_ip + C - 1) / C + 3) & ~3;
+    return sizeof(double) * (2 * 3 * (size_t)n + 9 * (size_t)ips_per_cta + (kStepThreads / 32) * 960) + 32;
 }
 
 // ---------------------------------------------------------------- PCG on (A + 1e-3 I) x = b, 3 right-hand sides
@@ -701,7 +948,39 @@ extern "C" int pn_qgmls_matvec3(const double *mat, const double *x, int n, doubl
 }
 
 extern "C" uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k, int adj_slices) {
-    return 9ull * n_ip + 9ull * 30 * n_k + 16 + 30ull * n_k * (adj_slices > 0 ? adj_slices : 1);
+    return 9ull * n_ip + 9ull * 30 * n_k + 16 + 30ull * n_k * (adj_slices > 0 ? adj_slices : 1) + 8;   // last 8: phase cycle counters of the cluster kernel
+}
+
+// Cluster size for the one-kernel step: 16 CTAs (non-portable size, one GPC) if the device can co-schedule them, else 8;
+// 0 = use the multi-kernel path (big systems: the dense mat-vec wants the whole GPU's bandwidth, not one GPC's).
+static int g_step_force_multi = 1;   // measured on B200: the cluster kernel is slower (469 vs 219 us, chair body) -> opt-in
+extern "C" int pn_qgmls_step_mode(int force_multi_kernel) { g_step_force_multi = force_multi_kernel; return PN_OK; }
+static int step_cluster_size(int n_ip, int n) {
+    static int cached_key_n = -1, cached_key_ip = -1, cached = 0;
+    if (n > 1280) return 0;                                  // matrix > 13 MB (x (1 + iters) reads per step)
+    if (cached_key_n == n && cached_key_ip == n_ip) return cached;
+    int best = 0;
+    for (int C : {16, 8}) {
+        const size_t smem = step_cluster_smem(n_ip, n, C);
+        if (smem > 200 * 1024) continue;
+        if (cudaFuncSetAttribute(qgmls_step_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (C > 8 && cudaFuncSetAttribute(qgmls_step_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(C); cfg.blockDim = dim3(kStepThreads); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, qgmls_step_cluster_kernel, &cfg) == cudaSuccess && nclusters >= 1) { best = C; break; }
+        cudaGetLastError();
+    }
+    cached_key_n = n; cached_key_ip = n_ip; cached = best;
+    return best;
+}
+
+extern "C" int pn_qgmls_step_launches(int n_ip, int n_k, int iters, int solver, int pcg_iters) {
+    if (solver == 0 && !g_step_force_multi && step_cluster_size(n_ip, 10 * n_k) > 0) return 1;
+    return 3 + iters * (solver == 0 ? 4 : 6 + 4 * pcg_iters);
 }
 
 extern "C" int pn_qgmls_step(const pn_qgmls_step_t *s, int solver, void *stream) {
@@ -719,6 +998,24 @@ extern "C" int pn_qgmls_step(const pn_qgmls_step_t *s, int solver, void *stream)
     double *partial = pcg + 4 * (size_t)n3 + 16;
     const double dx3 = s->dx * s->dx * s->dx;
     const int eb = div_up(n3, 256);
+    if (solver == 0 && !g_step_force_multi) {
+        const int C = step_cluster_size(s->n_ip, n);
+        if (C > 0) {
+            StepClusterArgs a{};
+            a.n_ip = s->n_ip; a.n_k = s->n_k; a.n = n; a.iters = s->iters; a.slices = s->adj_slices; a.dt = s->dt; a.dx3 = dx3;
+            a.topo = s->topo; a.mu = s->mu; a.lam = s->lam; a.dNx = s->dNx; a.adj_bgn = s->adj_bgn; a.adj = s->adj;
+            a.Ainv = s->Ainv; a.M = s->M; a.dof_rest = s->dof_rest; a.dof_f = s->dof_f; a.rhs_rest = s->rhs_rest; a.rhs_gravity = s->rhs_gravity;
+            a.dof = s->dof; a.dof_vel = s->dof_vel; a.stress = stress; a.last = last; a.mom = mom; a.partial = partial;
+            a.prof = reinterpret_cast<long long *>(partial + 30 * (size_t)s->n_k * s->adj_slices);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(C); cfg.blockDim = dim3(kStepThreads); cfg.dynamicSmemBytes = step_cluster_smem(s->n_ip, n, C); cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            PN_CUDA(cudaLaunchKernelEx(&cfg, qgmls_step_cluster_kernel, a));
+            return PN_OK;
+        }
+    }
     axpy_tilde_kernel<<<eb, 256, 0, st>>>(s->dof, s->dof_vel, s->dt, n3, tilde, last);
     // momentum = M/dt^2 @ dof_tilde + dof_f + rhs_gravity  (solver.py:576)
     matvec3_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(s->M, tilde, n, s->dof_f, s->rhs_gravity, nullptr, mom);

@@ -519,6 +519,12 @@ extern "C" int pn_field_forward(const pn_field_t *f, const float *xyzs, const fl
     return PN_OK;
 }
 
+static int g_sm_reserve = 0;
+extern "C" int pn_set_render_sm_reserve(int n_sm) {
+    PN_REQUIRE(n_sm >= 0 && n_sm < pn_sm_count_cached(), "reserve must leave SMs for the renderer");
+    g_sm_reserve = n_sm;
+    return PN_OK;
+}
 static cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
 static cudaEvent_t *g_prof_list = nullptr;   // wavefront mode: events [2k], [2k+1] bracket the k-th field-kernel launch of a frame
 static int g_prof_n = 0;
@@ -625,7 +631,10 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
         PN_CUDA(cudaMemsetAsync(base + w.ctl, 0, 16 * 16 + 256, st));       // ctl + counters (adjacent, 256-byte aligned blocks)
         const size_t smem = sizeof(WaveWsSmem) + 128;
         if (int rc = set_smem(wave_field_ws_kernel, smem)) return rc;
-        const uint32_t sms = (uint32_t)pn_sm_count_cached();
+        // SMs the persistent march / field grids are sized for: all of them, minus the ones the caller keeps free for kernels of
+        // another stream (pn_set_render_sm_reserve: on the GPU that also runs the simulator, its many tiny launches otherwise queue
+        // behind render CTAs that hold every SM until their kernel ends)
+        const uint32_t sms = (uint32_t)max(8, pn_sm_count_cached() - g_sm_reserve);
         // pass caps 32, 64, ... until the per-ray cap is covered; one spare pass absorbs the <32-sample overshoot per pass
         const int n_pass = pn_render_pass_count(d->max_steps);
         int cap_p = PN_WAVE_FIRST_CAP, fk = 0;

@@ -72,7 +72,7 @@ class FramePipeline:
     frame(pose, intrinsics) enqueues one GUI frame and returns its slot; wait_host(slot) returns the pinned host frame once
     it has landed; drain() joins every stream into the current one.  The simulator steps once per frame unless paused."""
 
-    def __init__(self, model, sim, opt, slots=3, tile=16, weights=None, timeout_ms=20000, table_copies=True, mode=3):
+    def __init__(self, model, sim, opt, slots=3, tile=16, weights=None, timeout_ms=20000, table_copies=True, mode=3, sim_sm_reserve=None):
         import torch.distributed as dist
         from .dist import tile_partition
         self.model, self.sim, self.opt = model, sim, opt
@@ -81,6 +81,13 @@ class FramePipeline:
         self.dev = next(model.parameters()).device
         self.S, self.W, self.H, self.mode = int(slots), int(opt.W), int(opt.H), mode
         self.timeout_ms = int(timeout_ms)
+        # the GPU that also simulates keeps a few SMs' worth of CTA slots out of the persistent render grids, so that the
+        # simulator's launches (high-priority stream) never queue behind a whole render kernel (multi-GPU runs only by default:
+        # on one GPU the 0.2 ms step hides inside the 2.4 ms frame anyway)
+        if sim_sm_reserve is None:
+            sim_sm_reserve = 16 if (self.world > 1 and self.rank == 0) else 0
+        self.sim_sm_reserve = int(sim_sm_reserve) if self.rank == 0 else 0
+        check(lib.pn_set_render_sm_reserve(self.sim_sm_reserve))
         self.n_ip = n_ip = int(sim.n_ip) if sim is not None else int(model.p_ori.shape[0])
         npx = self.W * self.H
         dev = self.dev
@@ -245,7 +252,7 @@ class FramePipeline:
             sl["graph"], n_frame = self._capture(lambda sl=sl: self._frame_body(sl), sl["stream"])
             if self.rank == 0:
                 sl["state_graph"], n_state = self._capture(lambda sl=sl: self._state_body(sl), self.sim_stream)
-        self.launches_per_frame = n_frame + n_state + ((3 + 4 * int(self.sim.iters)) if self.rank == 0 else 0)
+        self.launches_per_frame = n_frame + n_state + (self.sim.step_launches if self.rank == 0 else 0)
         torch.cuda.synchronize()
         self._barrier()
         self._warm = True

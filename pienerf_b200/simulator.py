@@ -150,6 +150,7 @@ class Simulator:
         self.rhs_gravity = torch.zeros_like(self.dof)
         _qgmls.collect_gravity(self.dx, self.IP_kernel, self.IP_Nx, self.gravity.tolist(), self.IP_rho, self.rhs_gravity)
         self._step_desc = None
+        self._graph = self._graph_key = self._graph_warm = None
         return self
 
     @torch.no_grad()
@@ -175,6 +176,7 @@ class Simulator:
         _qgmls.build_ip_global(self.dx, self.dt, self.IP_kernel, None, None, self.IP_rho, self.IP_Nx, self.IP_dNx, self.IP_ddNx,
                                self.mass_matrix_invt2)
         self._active_u8 = self.kernel_active.to(torch.uint8).contiguous()
+        self._graph = self._graph_key = self._graph_warm = None          # new matrices: any captured step is stale
 
     # ------------------------------------------------------------------ per-frame API
     @torch.no_grad()
@@ -186,30 +188,42 @@ class Simulator:
         return rhs
 
     def _desc(self):
-        if self._step_desc is None:
-            d = QgmlsStepT()
-            d.n_ip, d.n_k, d.iters, d.dt, d.dx = self.n_ip, self.n_k, int(self.iters), float(self.dt), float(self.dx)
-            d.topo, d.mu, d.lam, d.dNx = dptr(self.IP_kernel), dptr(self.IP_mu), dptr(self.IP_lam), dptr(self.IP_dNx)
-            d.adj_bgn, d.adj, d.adj_slices = dptr(self.kernel_bg), dptr(self.buffer), int(self.adj_slices)
-            d.Ainv, d.M, d.A, d.active = dptr(self.global_matrix), dptr(self.mass_matrix_invt2), dptr(self.system_matrix), dptr(self._active_u8)
-            d.pcg_iters = int(self.pcg_iters)
-            d.dof_rest, d.rhs_rest, d.rhs_gravity = dptr(self.dof_rest), dptr(self.rhs_rest), dptr(self.rhs_gravity)
-            d.dof, d.dof_vel, d.scratch = dptr(self.dof), dptr(self.dof_vel), dptr(self._scratch)
-            self._step_desc = d
-        self._step_desc.dof_f = dptr(self.dof_f)
-        self._step_desc.iters = int(self.iters)
-        return self._step_desc
+        """pn_qgmls_step_t over the CURRENT buffers (rebuilt on every call: it is a handful of pointer reads, and a cached copy
+        would keep pointing at freed memory after `sim.dof = ...`, a second build_global() or a changed dt)."""
+        d = QgmlsStepT()
+        d.n_ip, d.n_k, d.iters, d.dt, d.dx = self.n_ip, self.n_k, int(self.iters), float(self.dt), float(self.dx)
+        d.topo, d.mu, d.lam, d.dNx = dptr(self.IP_kernel), dptr(self.IP_mu), dptr(self.IP_lam), dptr(self.IP_dNx)
+        d.adj_bgn, d.adj, d.adj_slices = dptr(self.kernel_bg), dptr(self.buffer), int(self.adj_slices)
+        d.Ainv, d.M, d.A, d.active = dptr(self.global_matrix), dptr(self.mass_matrix_invt2), dptr(self.system_matrix), dptr(self._active_u8)
+        d.pcg_iters = int(self.pcg_iters)
+        d.dof_rest, d.rhs_rest, d.rhs_gravity = dptr(self.dof_rest), dptr(self.rhs_rest), dptr(self.rhs_gravity)
+        d.dof, d.dof_vel, d.scratch = dptr(self.dof, "dof", torchfloat), dptr(self.dof_vel, "dof_vel", torchfloat), dptr(self._scratch)
+        d.dof_f = dptr(self.dof_f, "dof_f", torchfloat)
+        self._step_desc = d
+        return d
+
+    @property
+    def step_launches(self):
+        """kernels one stepforward() enqueues (1 when the whole step runs as the thread-block-cluster kernel)"""
+        from ._lib import lib
+        return int(lib.pn_qgmls_step_launches(self.n_ip, self.n_k, int(self.iters), self.solver, int(self.pcg_iters)))
+
+    def _graph_signature(self):
+        ts = (self.dof, self.dof_vel, self.dof_f, self.dof_rest, self.rhs_rest, self.rhs_gravity, self.global_matrix, self.mass_matrix_invt2,
+              self.system_matrix, self._scratch)
+        return (int(self.iters), int(self.pcg_iters), self.solver, float(self.dt), _qgmls.step_mode_value()) + tuple(t.data_ptr() for t in ts)
 
     @torch.no_grad()
     def stepforward(self, graph=None):
-        """solver.py:595-602: momentum, `iters` local-global iterations, damped velocity — one enqueue-only call.
-        The step is a fixed chain of 3 + 4*iters small kernels over buffers that never move, so after the first call it
-        is replayed as ONE CUDA graph launch (`graph=False` forces the plain enqueue; `self.use_graph` is the default)."""
+        """solver.py:595-602: momentum, `iters` local-global iterations, damped velocity — one enqueue-only call: one
+        thread-block-cluster kernel for systems up to n = 1280, otherwise a fixed chain of 3 + 4*iters kernels replayed as ONE
+        CUDA graph launch after the first call (`graph=False` forces the plain enqueue; `self.use_graph` is the default).
+        The graph is keyed on every buffer address, dt and the iteration counts, so rebinding a tensor re-captures."""
         use = self.use_graph if graph is None else graph
         if not use or not self.dof.is_cuda:
             _qgmls.step(self._desc(), self.solver)
             return
-        key = (int(self.iters), int(self.pcg_iters), self.solver, self.dof.data_ptr(), self.dof_f.data_ptr())
+        key = self._graph_signature()
         if self._graph is None or self._graph_key != key:
             if self._graph_warm != key:                                   # first call with this configuration: plain, warms everything up
                 _qgmls.step(self._desc(), self.solver)

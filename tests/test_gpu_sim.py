@@ -90,6 +90,50 @@ def test_rest_fixed_point_and_determinism():
     assert torch.equal(s2.dof, first)                                       # gather-form rhs: bit-reproducible steps (init assembly uses atomics)
 
 
+@pytest.mark.parametrize("kind", ["block512", "chair2k"])
+def test_cluster_step_kernel_matches_multi_kernel_path(kind):
+    """The one-kernel step (thread-block cluster, barrier.cluster between phases) against the multi-kernel path: same algorithm,
+    different (fixed) summation order in the rhs gather -> fp64 round-off apart; and it is bit-reproducible run to run."""
+    from pienerf_b200 import _qgmls
+    try:
+        _qgmls.step_mode(True)
+        a, _, _ = _pair(kind)
+        for i in range(6):
+            if i == 2:
+                a.update_force(11, torch.tensor([3e4, -2e4, 1e4]))
+            a.stepforward()
+        _qgmls.step_mode(False)
+        b, _, _ = _pair(kind)
+        for i in range(6):
+            if i == 2:
+                b.update_force(11, torch.tensor([3e4, -2e4, 1e4]))
+            b.stepforward()
+        assert b.step_launches == 1 and a.step_launches > 40
+        assert _rel(b.dof.cpu().numpy(), a.dof.cpu().numpy()) < 1e-11 and _rel(b.dof_vel.cpu().numpy(), a.dof_vel.cpu().numpy()) < 1e-9
+        assert float((b.dof - b.dof_rest).abs().max()) > 1e-5                   # the body actually moved
+        c, _, _ = _pair(kind)                                                   # same sequence again: bit-identical (no atomics anywhere)
+        for i in range(6):
+            if i == 2:
+                c.update_force(11, torch.tensor([3e4, -2e4, 1e4]))
+            c.stepforward(graph=(i % 2 == 0))                                   # plain enqueue and graph replay give the same bits
+        assert torch.equal(c.dof, b.dof) and torch.equal(c.dof_vel, b.dof_vel)
+    finally:
+        _qgmls.step_mode(True)
+
+
+def test_rebinding_buffers_recaptures_the_step_graph():
+    """the cached descriptor / graph must follow `sim.dof = ...` and a changed dt."""
+    s, o, b = _pair("block64")
+    for _ in range(3):
+        s.stepforward()
+    ref, _, _ = _pair("block64")
+    for _ in range(3):
+        ref.stepforward()
+    s.dof = s.dof.clone(); s.dof_vel = s.dof_vel.clone()                      # rebinding: new addresses
+    s.stepforward(); s.stepforward(); ref.stepforward(); ref.stepforward()
+    assert torch.equal(s.dof, ref.dof)
+
+
 def test_pcg_matches_dense_inverse():
     """PCG on the assembled system reaches the same fixed point as the pre-inverted matrix."""
     a, _, _ = _pair("block64", solver="inverse")
