@@ -250,6 +250,8 @@ __device__ void svd3x3(const double *F, double *U, double *sg, double *V) {
     double S[9];
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) S[i * 3 + j] = F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j];
     double Q[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    // (warm-starting Q from the previous local-global iteration was measured: no gain once the convergence test below is sane,
+    //  and it costs the exact rest-state fixed point — with F = I the eigenvectors are arbitrary, so a carried Q changes U V^T by a ulp)
     // the three rotations of a sweep are spelled out with constant indices so that S and Q stay in registers
     // (a (p, q) loop indexes them dynamically -> local memory on the serial critical path of every step)
 #define PN_JACOBI(p, q)                                                                                                   \
@@ -266,7 +268,9 @@ __device__ void svd3x3(const double *F, double *U, double *sg, double *V) {
     }
     for (int sweep = 0; sweep < 12; sweep++) {
         const double off = fabs(S[1]) + fabs(S[2]) + fabs(S[5]);
-        if (off <= 1e-30 * (fabs(S[0]) + fabs(S[4]) + fabs(S[8]))) break;
+        // converged when the off-diagonal mass is below fp64 resolution of the diagonal (1e-17 relative: a further sweep cannot
+        // change U V^T or the singular values by a bit that matters; a 1e-30 target is unreachable and costs all 12 sweeps)
+        if (off <= 1e-17 * (fabs(S[0]) + fabs(S[4]) + fabs(S[8]))) break;
         PN_JACOBI(0, 1)
         PN_JACOBI(0, 2)
         PN_JACOBI(1, 2)
@@ -442,6 +446,64 @@ __global__ void __launch_bounds__(256) matvec3_kernel(const double *__restrict__
             if (add1) v += add1[3 * row + c];
             if (add2) v += add2[3 * row + c];
             y[3 * row + c] = v;
+        }
+    }
+}
+
+// Small systems (n <= 512): the vector a mat-vec multiplies is rebuilt by every CTA in shared memory instead of being produced
+// by a launch of its own — 3 launches per local-global iteration instead of 4, and no launch at all for dof_tilde / the final
+// velocity.  Row arithmetic is matvec3_kernel's (same lane partition, same shuffle tree): identical bits.
+//   MODE 0: x = dof + dt vel (solver.py:575); y = mom = M x + dof_f + rhs_gravity (576); CTA 0 also saves dof_last (597)
+//   MODE 1: x = mom + sum_s partial[.][s] - rhs_rest (599); y = dof = dof_rest + Ainv x (600-601);
+//           if vel_out: vel = (dof - dof_last) / dt * 0.998 for the same rows (602)
+template <int MODE>
+__global__ void __launch_bounds__(256) fused_matvec3_kernel(const double *__restrict__ mat, int n, const double *__restrict__ v0,
+                                                            const double *__restrict__ v1, const double *__restrict__ v2, int slices, double dt,
+                                                            const double *__restrict__ add0, const double *__restrict__ add1,
+                                                            double *__restrict__ y, double *__restrict__ last, double *__restrict__ vel_out) {
+    extern __shared__ __align__(16) double xs[];
+    const int n3 = 3 * n;
+    for (int id = threadIdx.x; id < n3; id += blockDim.x) {
+        if (MODE == 0) {
+            const double d = v0[id];
+            xs[id] = d + dt * v1[id];
+            if (blockIdx.x == 0) last[id] = d;
+        } else {
+            const int k = id / 30, i = id % 30;
+            double sum = 0.0;
+            for (int sl = 0; sl < slices; sl++) sum += v0[((size_t)k * slices + sl) * 30 + i];
+            xs[id] = (v1[id] + sum) - v2[id];
+        }
+    }
+    __syncthreads();
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double *m = mat + (size_t)row * n;
+    double a0 = 0, a1 = 0, a2 = 0;
+    if ((n & 1) == 0) {
+        const double2 *m2 = reinterpret_cast<const double2 *>(m);
+        for (int j = lane; j < n / 2; j += 32) {
+            const double2 w = __ldg(m2 + j);
+            const double *xa = xs + 6 * (size_t)j;
+            a0 += w.x * xa[0] + w.y * xa[3]; a1 += w.x * xa[1] + w.y * xa[4]; a2 += w.x * xa[2] + w.y * xa[5];
+        }
+    } else {
+        for (int j = lane; j < n; j += 32) {
+            const double w = __ldg(m + j);
+            a0 += w * xs[3 * j]; a1 += w * xs[3 * j + 1]; a2 += w * xs[3 * j + 2];
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(kFull, a0, o); a1 += __shfl_xor_sync(kFull, a1, o); a2 += __shfl_xor_sync(kFull, a2, o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double v = c == 0 ? a0 : (c == 1 ? a1 : a2);
+            if (add0) v += add0[3 * row + c];
+            if (add1) v += add1[3 * row + c];
+            y[3 * row + c] = v;
+            if (MODE == 1 && vel_out) vel_out[3 * row + c] = (v - last[3 * row + c]) / dt * 0.998;
         }
     }
 }
@@ -948,7 +1010,8 @@ extern "C" int pn_qgmls_matvec3(const double *mat, const double *x, int n, doubl
 }
 
 extern "C" uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k, int adj_slices) {
-    return 9ull * n_ip + 9ull * 30 * n_k + 16 + 30ull * n_k * (adj_slices > 0 ? adj_slices : 1) + 8;   // last 8: phase cycle counters of the cluster kernel
+    // stress | tilde last mom rhs x | pcg | partial | 8 phase cycle counters of the cluster kernel
+    return 9ull * n_ip + 9ull * 30 * n_k + 16 + 30ull * n_k * (adj_slices > 0 ? adj_slices : 1) + 8;
 }
 
 // Cluster size for the one-kernel step: 16 CTAs (non-portable size, one GPC) if the device can co-schedule them, else 8;
@@ -980,6 +1043,7 @@ static int step_cluster_size(int n_ip, int n) {
 
 extern "C" int pn_qgmls_step_launches(int n_ip, int n_k, int iters, int solver, int pcg_iters) {
     if (solver == 0 && !g_step_force_multi && step_cluster_size(n_ip, 10 * n_k) > 0) return 1;
+    if (solver == 0 && 10 * n_k <= 512) return 1 + 3 * iters;
     return 3 + iters * (solver == 0 ? 4 : 6 + 4 * pcg_iters);
 }
 
@@ -1016,12 +1080,23 @@ extern "C" int pn_qgmls_step(const pn_qgmls_step_t *s, int solver, void *stream)
             return PN_OK;
         }
     }
-    axpy_tilde_kernel<<<eb, 256, 0, st>>>(s->dof, s->dof_vel, s->dt, n3, tilde, last);
-    // momentum = M/dt^2 @ dof_tilde + dof_f + rhs_gravity  (solver.py:576)
-    matvec3_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(s->M, tilde, n, s->dof_f, s->rhs_gravity, nullptr, mom);
+    const bool fuse = solver == 0 && n <= 512;                              // small systems: 1 + 3*iters launches (see fused_matvec3_kernel; measured slower at n = 1250)
+    const size_t xs_bytes = sizeof(double) * (size_t)n3;
+    if (fuse) {
+        fused_matvec3_kernel<0><<<div_up(n * 32, 256), 256, xs_bytes, st>>>(s->M, n, s->dof, s->dof_vel, nullptr, 0, s->dt, s->dof_f, s->rhs_gravity, mom, last, nullptr);
+    } else {
+        axpy_tilde_kernel<<<eb, 256, 0, st>>>(s->dof, s->dof_vel, s->dt, n3, tilde, last);
+        // momentum = M/dt^2 @ dof_tilde + dof_f + rhs_gravity  (solver.py:576)
+        matvec3_kernel<<<div_up(n * 32, 256), 256, 0, st>>>(s->M, tilde, n, s->dof_f, s->rhs_gravity, nullptr, mom);
+    }
     for (int it = 0; it < s->iters; it++) {
         ip_stress_kernel<<<div_up(s->n_ip * 8, 128), 128, 0, st>>>(dx3, s->topo, s->mu, s->lam, s->dNx, s->dof, s->n_ip, stress);
         rhs_partial_kernel<<<dim3(s->n_k, s->adj_slices), 128, 0, st>>>(s->adj_bgn, s->adj, stress, s->dNx, s->adj_slices, partial);
+        if (fuse) {
+            fused_matvec3_kernel<1><<<div_up(n * 32, 256), 256, xs_bytes, st>>>(s->Ainv, n, partial, mom, s->rhs_rest, s->adj_slices, s->dt, s->dof_rest, nullptr, s->dof,
+                                                                                 last, it == s->iters - 1 ? s->dof_vel : nullptr);
+            continue;
+        }
         rhs_final_kernel<<<div_up(n3, 256), 256, 0, st>>>(partial, s->n_k, s->adj_slices, mom, s->rhs_rest, rhs);
         if (solver == 0) {
             // dof = dof_rest + Ainv rhs  (solver.py:600-601)
@@ -1039,6 +1114,10 @@ extern "C" int pn_qgmls_step(const pn_qgmls_step_t *s, int solver, void *stream)
             }
             add_rest_kernel<<<eb, 256, 0, st>>>(s->dof_rest, x, n3, s->dof);
         }
+    }
+    if (fuse) {
+        PN_LAUNCH_CHECK("qgmls_step");
+        return PN_OK;
     }
     finish_step_kernel<<<eb, 256, 0, st>>>(s->dof, last, s->dt, n3, s->dof_vel);
     PN_LAUNCH_CHECK("qgmls_step");
