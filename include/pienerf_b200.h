@@ -146,6 +146,7 @@ typedef struct {
     const uint32_t *const *wait_flag; int n_wait;
     uint32_t *const *signal_flag; int n_signal;
     int *status; uint32_t timeout_ms;
+    const float *noises;   /* [N] or NULL: perturb (renderer.py:863): ray n starts at near + noises[n] * dt for its first sample */
 } pn_frame_io_t;
 int pn_render_deformed_ex(const pn_field_t *field_host, const pn_deform_t *deform_host, const float *rays_o,
                           const float *rays_d, uint32_t N, float *image, float *depth, float *depth_0,
@@ -172,6 +173,9 @@ int pn_epoch_wait(uint32_t *epoch, int bump, const uint32_t *const *flags_dev, i
                   uint32_t timeout_ms, void *stream);
 int pn_epoch_signal(const uint32_t *epoch, uint32_t *const *flags_dev, int n_flags, void *stream);
 
+/* Rows of the per-pass sample list of mode 3 (0 = automatic: 24 per ray, 1 Mi .. 32 Mi).  Call before sizing the workspace with
+ * pn_render_workspace_bytes.  A full list defers the remaining rays to the next pass (stats[6]); tests use a small list. */
+int pn_set_wave_capacity(int rows);
 /* Size the persistent march / field grids of mode 3 for (SM count - n_sm) SMs, leaving n_sm SMs' worth of CTA slots to kernels of
  * other streams (the simulator's launches on the GPU that also renders).  0 = use every SM (default).  Process-wide; a CUDA
  * graph captured afterwards keeps the grid sizes it was captured with. */

@@ -61,7 +61,7 @@ class ReferenceRenderer:
     # nerf/renderer.py:755-907
     @torch.no_grad()
     def rund_cuda(self, rays_o, rays_d, p_def, p_ori, F_IP, dF_IP, IP_dx, dt_gamma=0.0, max_steps=1024, T_thresh=1e-2, max_iter_num=1,
-                  hash_grid_size=0.06, cut=False, cut_bounds=(0.0,) * 6, num_seek_IP=1, bg_color=1.0, return_stats=False):
+                  hash_grid_size=0.06, cut=False, cut_bounds=(0.0,) * 6, num_seek_IP=1, bg_color=1.0, return_stats=False, first_noises=None):
         dev = self.dev; rm = self.rm
         rays_o = rays_o.contiguous().view(-1, 3); rays_d = rays_d.contiguous().view(-1, 3)
         N = rays_o.shape[0]
@@ -87,7 +87,7 @@ class ReferenceRenderer:
             M = n_alive * n_step
             M += 128 - (M % 128)
             xyzs = torch.zeros(M, 3, device=dev); dirs = torch.zeros(M, 3, device=dev); deltas = torch.zeros(M, 2, device=dev)
-            noises = torch.zeros(n_alive, device=dev)
+            noises = first_noises if (first_noises is not None and step == 0) else torch.zeros(n_alive, device=dev)   # perturb if step == 0 (renderer.py:863)
             rm.march_rays_quadratic_bending(pig_cnt, pig_bgn, pig_idx, n_vtx, n_grid, p_def, p_ori, F_IP, dF_IP, max_iter_num, bbmin, bbmax,
                                             hash_grid_size, resolution, num_seek_IP, IP_dx, cut, cut_bounds, n_alive, n_step, rays_alive,
                                             rays_t, rays_o, rays_d, self.bound, dt_gamma, max_steps, self.cascade, self.H, self.bits, nears,

@@ -36,7 +36,7 @@ class DeformT(C.Structure):
 
 class FrameIoT(C.Structure):
     _fields_ = [("pix", vp), ("epoch", vp), ("wait_flag", vp), ("n_wait", i32), ("signal_flag", vp), ("n_signal", i32),
-                ("status", vp), ("timeout_ms", u32)]
+                ("status", vp), ("timeout_ms", u32), ("noises", vp)]
 
 
 class QgmlsStepT(C.Structure):
@@ -85,6 +85,7 @@ _PROTOS = {
     "pn_epoch_signal": (i32, [vp, vp, i32, vp]),
     "pn_render_workspace_bytes": (u64, [u32, i32, f32, f32]),
     "pn_set_render_sm_reserve": (i32, [i32]),
+    "pn_set_wave_capacity": (i32, [i32]),
     "pn_set_profile_events": (i32, [vp, vp]),
     "pn_set_profile_event_list": (i32, [vp, i32]),
     "pn_render_pass_count": (i32, [u32]),

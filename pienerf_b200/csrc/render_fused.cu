@@ -240,6 +240,7 @@ struct RenderArgs {
     FrameQueue *queue;
     float *image, *depth, *depth0, *wsum;   // image / depth / depth0 are indexed by pix[ray] when pix != nullptr (frame-sized, maybe peer memory)
     const int *pix;
+    const float *noises;                    // [N] or nullptr: start offset of each ray in units of its first step (perturb, raymarching.cu:1187)
     float density_scale, T_thresh, bg;
     uint32_t max_samples;
 };
@@ -392,7 +393,9 @@ struct WorkspaceLayout {
 };
 
 // rows of the per-pass sample list: 24 per ray (a chair frame keeps ~11 per ray over all passes), whole slabs
+int g_wave_cap_override = 0;   // pn_set_wave_capacity: tests shrink the list to exercise the "list full -> resume next pass" path
 int wave_capacity(uint32_t N) {
+    if (g_wave_cap_override > 0) return g_wave_cap_override / 256 * 256;
     long long c = 24ll * (long long)N;
     if (c < (1ll << 20)) c = 1ll << 20;
     if (c > (32ll << 20)) c = 32ll << 20;
@@ -519,6 +522,11 @@ extern "C" int pn_field_forward(const pn_field_t *f, const float *xyzs, const fl
     return PN_OK;
 }
 
+extern "C" int pn_set_wave_capacity(int rows) {
+    PN_REQUIRE(rows == 0 || rows >= 1024, "rows: 0 (automatic) or >= 1024");
+    g_wave_cap_override = rows;
+    return PN_OK;
+}
 static int g_sm_reserve = 0;
 extern "C" int pn_set_render_sm_reserve(int n_sm) {
     PN_REQUIRE(n_sm >= 0 && n_sm < pn_sm_count_cached(), "reserve must leave SMs for the renderer");
@@ -567,7 +575,7 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
                                      void *workspace, uint64_t workspace_bytes, long long *stats, int mode,
                                      const pn_frame_io_t *io, void *stream) {
     PN_REQUIRE(f && d && rays_o && rays_d && image && depth && depth_0 && weights_sum && workspace, "null pointer");
-    PN_REQUIRE(!io || !io->pix || mode == 3, "a pixel map (scattered / peer frame output) needs the wavefront renderer (mode 3)");
+    PN_REQUIRE(!io || !(io->pix || io->noises) || mode == 3, "a pixel map (scattered / peer frame output) or perturbed ray starts need the wavefront renderer (mode 3)");
     PN_REQUIRE(f->L == pn::kLevels, "fused field expects the 16-level C=2 D=3 grid of nerf/network.py");
     PN_REQUIRE(mode >= 0 && mode <= 3, "render mode: 0 = fused warp-cooperative + tcgen05 MLP, 1 = same with the fp32 SIMT MLP, 2 = one lane per ray, 3 = wavefront (march / field / composite kernels)");
     PN_REQUIRE(d->n_vtx > 0 && d->num_seek_IP >= 1 && d->num_seek_IP <= 3, "need IPs and num_seek_IP in 1..3");
@@ -605,7 +613,7 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
     A.bend.hgs = d->hgs; A.bend.IP_dx = d->IP_dx; A.bend.bound = d->bound; A.bend.cut = d->cut != 0;
     for (int i = 0; i < 6; i++) A.bend.cb[i] = d->cut_bounds[i];
     A.geom = geom; A.rays_o = rays_o; A.rays_d = rays_d; A.nears = nears; A.fars = fars; A.active = active; A.queue = queue;
-    A.image = image; A.depth = depth; A.depth0 = depth_0; A.wsum = weights_sum; A.pix = io ? io->pix : nullptr;
+    A.image = image; A.depth = depth; A.depth0 = depth_0; A.wsum = weights_sum; A.pix = io ? io->pix : nullptr; A.noises = io ? io->noises : nullptr;
     A.density_scale = d->density_scale; A.T_thresh = d->T_thresh; A.bg = d->bg_color; A.max_samples = d->max_steps;
 
     const uint32_t blocks = (uint32_t)pn_sm_count_cached() * 3u;

@@ -76,9 +76,16 @@ __global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const Re
         const float near = A.nears[ray], far = A.fars[ray];
         float t_next = near, skip_until = 0.f;
         int emitted = 0;
+        // perturb (renderer.py:863, raymarching.cu:1187): the reference offsets t by noise * dt for the FIRST march call only, which
+        // emits one sample per ray (n_step = 1 while every ray is alive); composite_rays then stores rays_t = near + (t - t_start),
+        // i.e. the offset is dropped again, and all later calls march the lattice that starts at that rays_t
+        float perturb_off = 0.f;
         if (pass > 0) {
             const float4 s = Wv.rs_march[ray];
             t_next = s.x; skip_until = s.y; emitted = __float_as_int(s.z);
+        } else if (A.noises) {
+            perturb_off = pn::step_size(m, near) * A.noises[ray];
+            t_next = near + perturb_off;
         }
         int pass_emitted = 0, first_idx = -1;
         bool finished = false;
@@ -121,7 +128,15 @@ __global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const Re
                     else { i = 32; carry = tti; }
                 }
             }
-            const bool ray_left = i < 32;
+            bool ray_left = i < 32;
+            float t_restart = 0.f;
+            const bool first_perturbed = perturb_off != 0.f && take != 0u;  // warp-uniform
+            if (first_perturbed) {                                         // keep only the first emitted sample of the perturbed lattice
+                const int l0 = __ffs(take) - 1;
+                take = 1u << l0;
+                t_restart = __shfl_sync(0xffffffffu, t_after, l0) - perturb_off;
+                ray_left = false;
+            }
             int ntake = __popc(take);
             if (emitted + ntake > (int)A.max_samples) {                   // per-ray sample cap
                 int keep = (int)A.max_samples - emitted;
@@ -145,7 +160,7 @@ __global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const Re
             const int idx = rank < room ? cur + rank : nb + (rank - room);
             if ((take >> lane) & 1u) {
                 Wv.xyzdt[idx] = make_float4(x, y, z, dt);
-                Wv.meta[idx] = make_int2(ray, __float_as_int(t_after));
+                Wv.meta[idx] = make_int2(ray, __float_as_int(first_perturbed ? t_restart : t_after));
             }
             if (ntake > 0 && first_idx < 0) first_idx = room > 0 ? cur : nb;
             if (ntake > room) { cur = nb + (ntake - room); end = nb + kSlab; }
@@ -154,6 +169,7 @@ __global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const Re
             if (ray_left || emitted >= (int)A.max_samples) { finished = true; break; }
             t_next = __shfl_sync(0xffffffffu, t_after, 31);
             skip_until = carry;
+            if (first_perturbed) { t_next = t_restart; skip_until = 0.f; perturb_off = 0.f; }
             if (pass_emitted >= pass_cap) break;
         }
         if (lane == 0) {

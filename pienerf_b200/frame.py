@@ -50,18 +50,25 @@ class FrameDriver:
         return self._rays, rH, rW
 
     @torch.no_grad()
-    def test_gui(self, pose, intrinsics, W, H, paused=False, to_host=True, host_out=None):
-        """trainer.py:531-602 with render_def=True, gui_sim=True, spp=1, downscale=1."""
+    def test_gui(self, pose, intrinsics, W, H, paused=False, to_host=True, host_out=None, spp=1, downscale=1):
+        """trainer.py:531-602 with render_def=True, gui_sim=True.  downscale < 1 renders int(H*downscale) x int(W*downscale) rays
+        with scaled intrinsics and upsamples the result with nearest-neighbour interpolation (:537-539,577-586); spp > 1 is the GUI's
+        accumulation index, used only as `perturb` (:565)."""
         self._rays_key = None                                         # the reference regenerates rays every frame
-        rays, rH, rW = self.rays(pose, intrinsics, W, H)
+        rays, rH, rW = self.rays(pose, intrinsics, W, H, downscale)
         if not paused:                                                # trainer.py:299-308
             IP_pos, IP_F, IP_dF = self.sim.get_IP_info()
             self.model.p_def, self.model.IP_F, self.model.IP_dF = IP_pos, IP_F, IP_dF
             self.sim.stepforward()
             self.frame += 1
         render = self.model.render_deformed if self.fused else self.model.rund_cuda
-        outputs = render(rays["rays_o"], rays["rays_d"], staged=True, bg_color=None, perturb=False, **self.opt)
+        outputs = render(rays["rays_o"], rays["rays_d"], staged=True, bg_color=None, perturb=False if spp == 1 else spp, **self.opt)
         image = outputs["image"].reshape(rH, rW, 3); depth = outputs["depth"].reshape(rH, rW); depth_0 = outputs["depth_0"].reshape(rH, rW)
+        if downscale != 1:                                            # trainer.py:577-586
+            import torch.nn.functional as F
+            image = F.interpolate(image.permute(2, 0, 1)[None], size=(H, W), mode="nearest")[0].permute(1, 2, 0).contiguous()
+            depth = F.interpolate(depth[None, None], size=(H, W), mode="nearest")[0, 0]
+            depth_0 = F.interpolate(depth_0[None, None], size=(H, W), mode="nearest")[0, 0]
         if to_host:                                                   # trainer.py:589-593: .cpu().numpy() of the frame
             if host_out is not None:
                 host_out["image"].copy_(image, non_blocking=True); host_out["depth"].copy_(depth, non_blocking=True)

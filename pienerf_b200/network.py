@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import raymarching
-from ._lib import DeformT, FieldT, check, dptr, lib, stream_ptr
+from ._lib import DeformT, FieldT, FrameIoT, check, dptr, lib, stream_ptr
 from .gridencoder import GridEncoder
 from .shencoder import SHEncoder
 
@@ -349,18 +349,25 @@ class NeRFNetwork(nn.Module):
 
     @torch.no_grad()
     def render_deformed(self, rays_o, rays_d, staged=False, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024, T_thresh=1e-2,
-                        mode=None, out=None, workspace=None, stats=None, io=None, embeddings=None, ip_state=None, **kwargs):
+                        mode=None, out=None, workspace=None, stats=None, io=None, embeddings=None, ip_state=None, noises=None, **kwargs):
         """renderer.py:587-599 -> rund_cuda semantics in one device-resident call.  Returns the same dict.
         mode 3: wavefront (default); 0: fused warp-cooperative kernel + tcgen05 MLP; 1: same with the fp32 SIMT MLP; 2: one lane
         per ray.  `workspace` / `stats` / `embeddings` / `ip_state` / `io` (_lib.FrameIoT) let a frame pipeline keep several
         frames in flight (pipeline.py); by default the module's own single workspace is used."""
         if mode is None:
             mode = DEFAULT_RENDER_MODE
-        if perturb:
-            raise NotImplementedError("perturb is only used with spp>1 accumulation, which the sim GUI never does (gui.py:620-622)")
         prefix = rays_o.shape[:-1]
         rays_o = rays_o.to(torch.float32).contiguous().view(-1, 3); rays_d = rays_d.to(torch.float32).contiguous().view(-1, 3)
         N = rays_o.shape[0]; device = rays_o.device
+        if perturb and noises is None:                                        # raymarching.py:407-409: torch.rand per ray (spp > 1 accumulation)
+            noises = torch.rand(N, dtype=torch.float32, device=device)
+        if noises is not None:
+            if mode != 3:
+                raise NotImplementedError("perturbed ray starts are implemented by the wavefront renderer (mode 3)")
+            noises = noises.to(torch.float32).contiguous().view(-1)
+            if io is None:
+                io = FrameIoT()
+            io.noises = dptr(noises, "noises", torch.float32)
         d, keep = self.deform_struct(ip_state, dt_gamma=dt_gamma, bg_color=bg_color, max_steps=max_steps, T_thresh=T_thresh, **kwargs)
         need = self.workspace_bytes(N, d.n_vtx, **kwargs)
         if workspace is None:

@@ -170,6 +170,10 @@ CONFIGS = {
     "step512": dict(body="block512", bound=1.0, W=0, H=0),
     "chair": dict(body="chair2k", bound=1.0, W=800, H=800, max_steps=1024, T_thresh=1e-2, dt_gamma=0.0,
                   min_near=0.2, max_iter_num=1, num_seek_IP=3, sim_dx=0.05, radius=2.5, fovy=50.0, cut=False),
+    # one GPU's share of the chair frame at 8 GPUs (1/8 of the rays, same body / field): single-GPU stand-in for tuning the
+    # coexistence of the simulator and a small render on the simulating rank
+    "chair8": dict(body="chair2k", bound=1.0, W=283, H=283, max_steps=1024, T_thresh=1e-2, dt_gamma=0.0,
+                   min_near=0.2, max_iter_num=1, num_seek_IP=3, sim_dx=0.05, radius=2.5, fovy=50.0, cut=False),
     "chairlike": dict(body="chairlike", bound=1.0, W=800, H=800, max_steps=1024, T_thresh=1e-2, dt_gamma=0.0,
                       min_near=0.2, max_iter_num=1, num_seek_IP=3, sim_dx=0.05, radius=2.5, fovy=50.0, cut=False),
     "trex": dict(body="block8k", bound=2.0, W=1008, H=756, max_steps=300, T_thresh=5e-2, dt_gamma=1.0 / 128,

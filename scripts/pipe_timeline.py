@@ -15,6 +15,8 @@ import torch.distributed as dist
 config = sys.argv[1] if len(sys.argv) > 1 else "chair"
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 slots = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+paused = len(sys.argv) > 4 and sys.argv[4] == "paused"
+reserve = int(sys.argv[5]) if len(sys.argv) > 5 else None
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -24,10 +26,10 @@ from pienerf_b200.frame import build_scene
 from pienerf_b200.pipeline import FramePipeline
 
 model, sim, opt, pose, intr, body, field = build_scene(config, device=dev)
-pipe = FramePipeline(model, sim, opt, slots=slots)
+pipe = FramePipeline(model, sim, opt, slots=slots, sim_sm_reserve=reserve)
 pipe.build(pose, intr)
 for _ in range(6):
-    pipe.frame(pose, intr, to_host=False)
+    pipe.frame(pose, intr, to_host=False, paused=paused)
 pipe.drain(); torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -35,6 +37,7 @@ if world > 1:
 ev = lambda: torch.cuda.Event(enable_timing=True)
 rec = []
 orig_frame_replay = {}
+torch.cuda.profiler.start()
 t0 = ev(); t0.record()
 # instrument: wrap graph replays with events on their streams
 for k in range(K):
@@ -62,7 +65,7 @@ for k in range(K):
             a.record(torch.cuda.current_stream()); old_step(); b.record(torch.cuda.current_stream())
             e["step"] = (a, b)
         sim.stepforward = stepf
-    pipe.frame(pose, intr, to_host=False)
+    pipe.frame(pose, intr, to_host=False, paused=paused)
     sl["graph"] = g
     if sg is not None:
         sl["state_graph"] = sg
@@ -72,10 +75,11 @@ for k in range(K):
 pipe.drain()
 t1 = ev(); t1.record()
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 if world > 1:
     dist.barrier()
 total = t0.elapsed_time(t1)
-lines = [f"rank {rank}/{world} {config}: {K} frames in {total:.3f} ms = {total / K:.3f} ms/frame ({1e3 * K / total:.1f} fps), {slots} slots"]
+lines = [f"rank {rank}/{world} {config}: {K} frames in {total:.3f} ms = {total / K:.3f} ms/frame ({1e3 * K / total:.1f} fps), {slots} slots, paused={paused}, reserve={pipe.sim_sm_reserve}"]
 for k, e in enumerate(rec):
     parts = [f"frame {k:2d} slot {e['slot']}"]
     for tag in ("state", "step", "frame"):
