@@ -52,9 +52,44 @@ def test_argument_validation_without_gpu():
         _shencoder.sh_encode_forward(x, x, 4, 3, 4, None)
 
 
-def test_dropin_names_and_reference_wrappers_import():
+def test_compiled_extension_modules_mirror_the_reference_bindings():
+    """The pybind11 modules (csrc/bindings.cpp) export the entry points of the reference's bindings.cpp files and raise the
+    same exception types; no compute without a GPU."""
+    import torch
+    from pienerf_b200.build_ext import load_ext
+    want = {"_gridencoder": ["grid_encode_forward", "grid_encode_backward", "grad_total_variation"],          # gridencoder/src/bindings.cpp:5-9
+            "_shencoder": ["sh_encode_forward", "sh_encode_backward"],                                         # shencoder/src/bindings.cpp:5-8
+            "_raymarching": ["near_far_from_aabb", "sph_from_ray", "morton3D", "morton3D_invert", "packbits", "march_rays_train",
+                             "composite_rays_train_forward", "composite_rays_train_backward", "march_rays", "march_rays_quadratic_bending",
+                             "composite_rays"],                                                                # raymarching/src/bindings.cpp:5-19
+            "_qgmls": ["shape_functions", "collect_param", "build_ip_global", "build_pin_global", "collect_gravity", "build_rhs", "matvec3", "step",
+                       "ip_info", "update_pos", "update_force"]}
+    mods = {n: load_ext(n) for n in want}
+    if any(m is None for m in mods.values()):
+        pytest.skip("compiled modules not built (python -m pienerf_b200.build_ext)")
+    for n, fns in want.items():
+        for f in fns:
+            assert callable(getattr(mods[n], f)), (n, f)
+    with pytest.raises(NotImplementedError, match="training-only"):
+        mods["_raymarching"].march_rays_train()
+    with pytest.raises(NotImplementedError, match="training-only"):
+        mods["_gridencoder"].grid_encode_backward(1, 2, 3)
+    x = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        mods["_gridencoder"].grid_encode_forward(x, x, x.int(), x, 4, 3, 2, 1, 1.0, 16, None, 0, False, 0)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        mods["_shencoder"].sh_encode_forward(x, x, 4, 3, 4, None)
+    with pytest.raises(TypeError):
+        mods["_raymarching"].composite_rays(1, 2)                                                              # positional signature enforced by pybind11
+
+
+@pytest.mark.parametrize("compiled", [False, None])
+def test_dropin_names_and_reference_wrappers_import(compiled):
+    """compiled=None picks the pybind11 modules when pienerf_b200/ext is built (otherwise ctypes); False forces ctypes."""
     from pienerf_b200 import dropin
-    names = dropin.install()
+    names = dropin.install(compiled=compiled)
+    if compiled is False:
+        assert set(dropin.installed.values()) == {"ctypes"}
     assert names == ("_gridencoder", "_shencoder", "_raymarching", "_qgmls")
     import _gridencoder
     import _raymarching

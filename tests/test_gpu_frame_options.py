@@ -65,7 +65,7 @@ def test_full_sample_list_defers_rays_and_reports_truncation():
     ro_, rd_ = _gpu(rays_o)[None], _gpu(rays_d)[None]
     base = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in model.render_deformed(ro_, rd_, mode=3, **KW, **OPT).items()}
     st0 = model.check_stats(base["stats"])
-    assert st0[6] == 0 and st0[0] > 50000
+    assert st0[6] == 0 and st0[0] > 5000
     try:
         # (a) a list that fills up in the first passes: chunks are deferred, the rays resume later, same frame bit for bit
         check(lib.pn_set_wave_capacity(max(1024, (st0[0] // 3) // 256 * 256)))

@@ -112,12 +112,16 @@ def test_cluster_step_kernel_matches_multi_kernel_path(kind):
         assert b.step_launches == 1
         assert _rel(b.dof.cpu().numpy(), a.dof.cpu().numpy()) < 1e-9 and _rel(b.dof_vel.cpu().numpy(), a.dof_vel.cpu().numpy()) < 1e-7   # measured 4e-11 / 1e-9
         assert float((b.dof - b.dof_rest).abs().max()) > 1e-5                   # the body actually moved
-        c, _, _ = _pair(kind)                                                   # same sequence again: bit-identical (no atomics anywhere)
-        for i in range(6):
-            if i == 2:
-                c.update_force(11, torch.tensor([3e4, -2e4, 1e4]))
-            c.stepforward(graph=(i % 2 == 0))                                   # plain enqueue and graph replay give the same bits
-        assert torch.equal(c.dof, b.dof) and torch.equal(c.dof_vel, b.dof_vel)
+        # bit-reproducible: the same instance (init assembly uses fp64 atomics, so two instances differ by round-off) run again
+        # from a saved state, alternating plain enqueue and graph replay
+        dof0, vel0 = b.dof.clone(), b.dof_vel.clone()
+        for _ in range(3):
+            b.stepforward()
+        first = (b.dof.clone(), b.dof_vel.clone())
+        b.dof.copy_(dof0); b.dof_vel.copy_(vel0)
+        for i in range(3):
+            b.stepforward(graph=(i % 2 == 0))
+        assert torch.equal(b.dof, first[0]) and torch.equal(b.dof_vel, first[1])
     finally:
         _qgmls.step_mode(True)
 
@@ -127,12 +131,16 @@ def test_rebinding_buffers_recaptures_the_step_graph():
     s, o, b = _pair("block64")
     for _ in range(3):
         s.stepforward()
-    ref, _, _ = _pair("block64")
-    for _ in range(3):
-        ref.stepforward()
-    s.dof = s.dof.clone(); s.dof_vel = s.dof_vel.clone()                      # rebinding: new addresses
-    s.stepforward(); s.stepforward(); ref.stepforward(); ref.stepforward()
-    assert torch.equal(s.dof, ref.dof)
+    dof0, vel0 = s.dof.clone(), s.dof_vel.clone()
+    s.stepforward(); s.stepforward()
+    want = s.dof.clone()
+    s.dof = dof0.clone(); s.dof_vel = vel0.clone()                            # rebinding: new addresses (a reset)
+    s.stepforward(); s.stepforward()
+    assert torch.equal(s.dof, want)
+    s.dof = dof0.clone(); s.dof_vel = vel0.clone()
+    s.dt = 5e-3                                                               # a changed dt must not replay the old graph
+    s.stepforward(); s.stepforward()
+    assert not torch.equal(s.dof, want)
 
 
 def test_pcg_matches_dense_inverse():
