@@ -114,6 +114,14 @@ typedef struct {
 int pn_field_forward(const pn_field_t *field_host, const float *xyzs, const float *dirs, uint32_t M, float *sigmas,
                      float *rgbs, int mode, void *stream);
 
+/* nerf/network.py:105-127 alone (sigma_net 32-64-16, trunc_exp, SH(4) of dirs || geo, color_net 31-64-64-3, sigmoid) on the
+ * tcgen05 pipeline of the frame renderer, hash-grid gather replaced by a load of pre-encoded features enc [M,32] f32 (the
+ * [B, L*C] layout grid.py:57 hands to the MLP).  For measuring the MLP pass by itself; pn_set_profile_event_list events [0], [1]
+ * bracket the tensor-core kernel. */
+uint64_t pn_mlp_workspace_bytes(uint32_t M);
+int pn_mlp_forward(const pn_field_t *field_host, const float *enc, const float *dirs, uint32_t M, float *sigmas, float *rgbs,
+                   void *workspace, uint64_t workspace_bytes, void *stream);
+
 /* nerf/renderer.py:755-907 rund_cuda as a device-resident frame (enqueue-only, no host sync): near/far, IP bbox +
  * grid, then the render itself.  mode 3 (product path) = wavefront: per pass a march kernel (lattice march +
  * inverse warp, samples appended to a compact list), the field kernel (hash-grid gather + tcgen05 MLP over 128-row

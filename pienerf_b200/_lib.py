@@ -72,6 +72,8 @@ _PROTOS = {
     "pn_build_ip_grid": (i32, [vp, i32, vp, f32, vp, i32, vp, vp, vp, vp]),
     "pn_ip_bbox": (i32, [vp, i32, f32, i32, f32, vp, vp, vp, vp]),
     "pn_field_forward": (i32, [C.POINTER(FieldT), vp, vp, u32, vp, vp, i32, vp]),
+    "pn_mlp_workspace_bytes": (u64, [u32]),
+    "pn_mlp_forward": (i32, [C.POINTER(FieldT), vp, vp, u32, vp, vp, vp, u64, vp]),
     "pn_render_deformed": (i32, [C.POINTER(FieldT), C.POINTER(DeformT), vp, vp, u32, vp, vp, vp, vp, vp, u64, vp, i32, vp]),
     "pn_render_deformed_ex": (i32, [C.POINTER(FieldT), C.POINTER(DeformT), vp, vp, u32, vp, vp, vp, vp, vp, u64, vp, i32, C.POINTER(FrameIoT), vp]),
     "pn_get_rays_pix": (i32, [vp, u32, u32, vp, u32, vp, vp, vp]),

@@ -15,7 +15,8 @@
 
 namespace {
 
-void *cur_stream() { return (void *)at::cuda::getCurrentCUDAStream().stream(); }
+// (argument evaluation order is unspecified: this may run before the tensor checks, so it must not throw on a GPU-less host)
+void *cur_stream() { return at::cuda::is_available() ? (void *)at::cuda::getCurrentCUDAStream().stream() : nullptr; }
 
 void pn_check(int rc) {
     if (rc == PN_OK) return;

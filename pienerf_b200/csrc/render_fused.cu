@@ -547,6 +547,45 @@ extern "C" int pn_set_profile_events(void *start, void *stop) {
     return PN_OK;
 }
 
+extern "C" uint64_t pn_mlp_workspace_bytes(uint32_t M) {
+    const uint64_t rows = ((uint64_t)M + 127) / 128 * 128;
+    return 4096 + kWeightsImageBytes + rows * (8 + 16 + 16);
+}
+
+// nerf/network.py:105-127 (sigma_net + color_net) alone, on the product's tensor-core pipeline: the wavefront field kernel with
+// its hash-grid gather replaced by a coalesced load of pre-encoded features.  Exists to measure what the tcgen05 / TMEM MLP
+// sustains by itself (bench.py "mlp_pass"); the profiling event list of pn_set_profile_event_list brackets the field kernel.
+extern "C" int pn_mlp_forward(const pn_field_t *f, const float *enc, const float *dirs, uint32_t M, float *sigmas, float *rgbs, void *workspace,
+                              uint64_t workspace_bytes, void *stream) {
+    PN_REQUIRE(f && enc && dirs && sigmas && rgbs && workspace, "null pointer");
+    PN_REQUIRE(workspace_bytes >= pn_mlp_workspace_bytes(M), "workspace too small (see pn_mlp_workspace_bytes)");
+    if (M == 0) return PN_OK;
+    cudaStream_t st = PN_STREAM(stream);
+    const uint64_t rows = ((uint64_t)M + 127) / 128 * 128;
+    unsigned char *base = (unsigned char *)workspace;
+    WaveArgs Wv{};
+    Wv.ctl = (PassCtl *)base;
+    pn::tc::Weights *wimg = (pn::tc::Weights *)(base + 4096);
+    Wv.weights_img = wimg;
+    Wv.meta = (int2 *)(base + 4096 + kWeightsImageBytes);
+    Wv.xyzdt = (float4 *)((unsigned char *)Wv.meta + rows * 8);
+    Wv.out = (float4 *)((unsigned char *)Wv.xyzdt + rows * 16);
+    Wv.enc = enc; Wv.cap = (int)rows;
+    RenderArgs A{};
+    A.field = *f; A.rays_d = dirs; A.density_scale = 1.0f;
+    PN_CUDA(cudaMemsetAsync(base, 0, 4096, st));
+    mlp_rows_kernel<<<div_up(M, 256u), 256, 0, st>>>(M, Wv.meta, Wv.xyzdt, Wv.ctl);
+    field_weights_kernel<<<1, 256, 0, st>>>(A.field, wimg);
+    const size_t smem = sizeof(WaveWsSmem) + 128;
+    if (int rc = set_smem(wave_field_ws_kernel, smem)) return rc;
+    if (g_prof_list && g_prof_n >= 2) PN_CUDA(cudaEventRecord(g_prof_list[0], st));
+    wave_field_ws_kernel<<<(uint32_t)pn_sm_count_cached(), (kWsProd + kWsCons) * 128, smem, st>>>(A, Wv, 0);
+    if (g_prof_list && g_prof_n >= 2) PN_CUDA(cudaEventRecord(g_prof_list[1], st));
+    mlp_unpack_kernel<<<div_up(M, 256u), 256, 0, st>>>(M, Wv.out, sigmas, rgbs);
+    PN_LAUNCH_CHECK("pn_mlp_forward");
+    return PN_OK;
+}
+
 #ifndef PN_WAVE_FIRST_CAP
 #define PN_WAVE_FIRST_CAP 32   // samples per ray in the first pass (doubles every pass): saturating rays waste <= one 32-sample chunk
 #endif

@@ -42,6 +42,7 @@ struct WaveArgs {
     int *slab_next;        // [cap / kSlab] row at which a warp's sample stream continues after this slab
     long long *counters;   // [0] composited samples, [1] emitted samples, [2] rays cut short by the last pass, [3] chunks deferred by a full sample list
     const pn::tc::Weights *weights_img;   // bf16 hi/lo weight images + level geometry, built once per frame (field_weights_kernel)
+    const float *enc;      // MLP-only measurement (pn_mlp_forward): pre-encoded [rows,32] features replace the hash-grid gather
     int cap;               // rows available per pass
 };
 
@@ -276,7 +277,20 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
             if (valid) sm = Wv.xyzdt[i];
             pn::tc::mbar_wait(&S.empty[st], (use & 1) ^ 1);               // stage free (a fresh barrier passes at once)
             char *hi = reinterpret_cast<char *>(S.stage[st].a[0]) + row * 16, *lo = reinterpret_cast<char *>(S.stage[st].a[1]) + row * 16;
-            if (S.w.fast) {
+            if (Wv.enc) {
+                // features in, sigma / rgb out: the same ring, barriers and tensor-core pipeline fed by a plain 128-byte row load
+                const float4 *e4 = reinterpret_cast<const float4 *>(Wv.enc + 32 * (size_t)i);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                    if (valid) { a = __ldg(e4 + 2 * c); b = __ldg(e4 + 2 * c + 1); }
+                    uint4 h, l;
+                    pn::tc::split_pair(a.x, a.y, h.x, l.x); pn::tc::split_pair(a.z, a.w, h.y, l.y);
+                    pn::tc::split_pair(b.x, b.y, h.z, l.z); pn::tc::split_pair(b.z, b.w, h.w, l.w);
+                    *reinterpret_cast<uint4 *>(hi + c * 2048) = h;
+                    *reinterpret_cast<uint4 *>(lo + c * 2048) = l;
+                }
+            } else if (S.w.fast) {
                 pn::tc::encode_rows_ilp(hi, lo, S.w, table, A.field.bound, valid, sm.x, sm.y, sm.z, lvl0);
             } else {
                 // generic table shapes: per-level path (tiled grids, non power-of-two hash sizes)
@@ -326,7 +340,7 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
 #endif
             if (valid) {
                 sigma = A.density_scale * sigma;
-                Wv.out[i] = make_float4(1.0f - __expf(-sigma * dt), r, g, b);
+                Wv.out[i] = make_float4(Wv.enc ? sigma : 1.0f - __expf(-sigma * dt), r, g, b);
             }
         }
     }
@@ -409,6 +423,19 @@ __global__ void __launch_bounds__(256) wave_composite_kernel(const RenderArgs A,
     }
     for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
     if (lane == 0 && kept) atomicAdd((unsigned long long *)&Wv.counters[0], (unsigned long long)kept);
+}
+
+// pn_mlp_forward: a one-pass "sample list" whose row i is (ray i, dt 1), and the unpacking of its results
+__global__ void __launch_bounds__(256) mlp_rows_kernel(uint32_t M, int2 *__restrict__ meta, float4 *__restrict__ xyzdt, PassCtl *__restrict__ ctl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) ctl[0].n_reserved = (int)M;
+    if (i < M) { meta[i] = make_int2((int)i, 0); xyzdt[i] = make_float4(0.f, 0.f, 0.f, 1.f); }
+}
+__global__ void __launch_bounds__(256) mlp_unpack_kernel(uint32_t M, const float4 *__restrict__ out, float *__restrict__ sigmas, float *__restrict__ rgbs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float4 o = out[i];
+    sigmas[i] = o.x; rgbs[3 * i] = o.y; rgbs[3 * i + 1] = o.z; rgbs[3 * i + 2] = o.w;
 }
 
 __global__ void wave_stats_kernel(const FrameQueue *q, const FrameGeom *g, const WaveArgs Wv, int n_pass, long long *stats) {

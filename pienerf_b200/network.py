@@ -224,6 +224,21 @@ class NeRFNetwork(nn.Module):
         check(lib.pn_field_forward(C.byref(f), dptr(x), dptr(d), M, dptr(sigmas), dptr(rgbs), int(mode), stream_ptr()))
         return sigmas, rgbs
 
+    @torch.no_grad()
+    def mlp_only(self, enc, d):
+        """sigma_net + color_net on pre-encoded features `enc` [M,32] and directions `d` [M,3] (network.py:105-127) through the
+        frame renderer's tcgen05 pipeline (pn_mlp_forward) — the MLP pass measured by itself."""
+        enc = enc.to(torch.float32).contiguous().view(-1, 32); d = d.to(torch.float32).contiguous().view(-1, 3)
+        M = enc.shape[0]
+        need = int(lib.pn_mlp_workspace_bytes(M))
+        if getattr(self, "_mlp_ws", None) is None or self._mlp_ws.numel() < need or self._mlp_ws.device != enc.device:
+            self._mlp_ws = torch.empty(need, dtype=torch.uint8, device=enc.device)
+        sigmas = torch.empty(M, dtype=torch.float32, device=enc.device)
+        rgbs = torch.empty(M, 3, dtype=torch.float32, device=enc.device)
+        f = self._field_struct()
+        check(lib.pn_mlp_forward(C.byref(f), dptr(enc), dptr(d), M, dptr(sigmas), dptr(rgbs), dptr(self._mlp_ws), need, stream_ptr()))
+        return sigmas, rgbs
+
     # ------------------------------------------------------------------ nerf/renderer.py:332-388
     @torch.no_grad()
     def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024, T_thresh=1e-2, fused_field=False, **kwargs):

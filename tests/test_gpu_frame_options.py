@@ -112,3 +112,27 @@ def test_non_default_architecture_is_refused_by_the_fused_kernels():
         m.forward_fused(x, d)
     s, c = m.forward(x, d)                                                   # the per-op path handles any shape
     assert s.shape == (8,) and c.shape == (8, 3)
+
+
+def test_mlp_only_pass_matches_torch_fp32():
+    """pn_mlp_forward (features in, sigma / rgb out; the kernel bench.py's `mlp_pass` times) vs the fp32 torch layers of network.py:105-127.
+    Tolerance: the bf16x3 split keeps fp32-level accuracy (2e-4 relative on sigma, 1e-4 absolute on rgb, as for the fused field)."""
+    import torch.nn.functional as F
+    from pienerf_b200.network import NeRFNetwork
+    from pienerf_b200.synthetic import make_field
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = NeRFNetwork(bound=1).cuda().load_field(make_field())
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M = 100003
+    enc = torch.randn(M, 32, device="cuda", generator=g) * 0.5
+    d = F.normalize(torch.randn(M, 3, device="cuda", generator=g), dim=-1)
+    sig, rgb = model.mlp_only(enc, d)
+    h = F.relu(F.linear(enc.double(), model.sigma_net[0].weight.double()))
+    h = F.linear(h, model.sigma_net[1].weight.double())
+    want_sig = torch.exp(h[:, 0])
+    sh = model.encoder_dir(d).double()
+    c = torch.cat([sh, h[:, 1:]], dim=-1)
+    c = F.relu(F.linear(c, model.color_net[0].weight.double())); c = F.relu(F.linear(c, model.color_net[1].weight.double()))
+    want_rgb = torch.sigmoid(F.linear(c, model.color_net[2].weight.double()))
+    assert float(((sig.double() - want_sig).abs() / want_sig.abs().clamp_min(1e-6)).max()) < 2e-4
+    assert float((rgb.double() - want_rgb).abs().max()) < 1e-4
