@@ -489,6 +489,9 @@ def run_reference(args):
 def main():
     # the contract is ONE JSON line on stdout: libraries (NCCL's version banner, torch warnings) write to fd 1 too, so
     # everything goes to stderr while the run lasts and the line is printed on the real stdout at the end
+    # watchdog: a hang (a wedged kernel, a lost rank) must not eat the box: dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("PN_BENCH_WATCHDOG_S", "480")), exit=True)
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     sys.stdout = os.fdopen(real_stdout, "w", buffering=1)

@@ -130,7 +130,7 @@ int pn_mlp_forward(const pn_field_t *field_host, const float *enc, const float *
  * stats (optional, device int64[8]): [0] composited samples, [1] rays that hit the aabb, [2] field evaluations,
  * [3] rows the field kernel processed (mode 3; samples + slab padding), [4] error bits (1: the deformed IP bbox needed more
  * grid cells than the workspace holds and was clamped — diverged body; 2: rays were cut short because the sample list and
- * the passes ran out), [5] number of such rays, [6] chunks a full sample list deferred to a later pass, [7] 0. */
+ * the passes ran out), [5] number of such rays, [6] chunks a full sample list deferred to a later pass, [7] passes that had rays. */
 typedef struct {
     const float *p_def, *p_ori, *F_IP, *dF_IP; int n_vtx; float IP_dx;
     const uint8_t *density_bitfield; float bound; uint32_t cascade; uint32_t grid_size;
@@ -155,7 +155,10 @@ typedef struct {
     uint32_t *const *signal_flag; int n_signal;
     int *status; uint32_t timeout_ms;
     const float *noises;   /* [N] or NULL: perturb (renderer.py:863): ray n starts at near + noises[n] * dt for its first sample */
+    int max_passes;        /* > 0: at most this many wavefront passes, the last one unbounded (stats[7] of earlier frames tells how many are used) */
+    uint32_t flags;        /* PN_IO_* */
 } pn_frame_io_t;
+#define PN_IO_WEIGHTS_READY 1u   /* the workspace already holds the weight image of these weights (an earlier call with the same workspace) */
 int pn_render_deformed_ex(const pn_field_t *field_host, const pn_deform_t *deform_host, const float *rays_o,
                           const float *rays_d, uint32_t N, float *image, float *depth, float *depth_0,
                           float *weights_sum, void *workspace, uint64_t workspace_bytes, long long *stats, int mode,

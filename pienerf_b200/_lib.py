@@ -36,7 +36,7 @@ class DeformT(C.Structure):
 
 class FrameIoT(C.Structure):
     _fields_ = [("pix", vp), ("epoch", vp), ("wait_flag", vp), ("n_wait", i32), ("signal_flag", vp), ("n_signal", i32),
-                ("status", vp), ("timeout_ms", u32), ("noises", vp)]
+                ("status", vp), ("timeout_ms", u32), ("noises", vp), ("max_passes", i32), ("flags", u32)]
 
 
 class QgmlsStepT(C.Structure):
@@ -115,6 +115,7 @@ for _name, (_res, _args) in _PROTOS.items():
     _fn.argtypes = _args
 
 PN_ENOTIMPL = -3
+PN_IO_WEIGHTS_READY = 1
 
 
 def last_error():

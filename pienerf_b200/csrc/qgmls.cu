@@ -523,25 +523,33 @@ __global__ void finish_step_kernel(const double *__restrict__ dof, const double 
 
 // ---------------------------------------------------------------- the whole step as ONE thread-block-cluster kernel
 // stepforward (solver.py:574-602) is a strictly sequential chain — per local-global iteration: per-IP F + SVD, rhs gather,
-// one dense mat-vec — over a few thousand IPs and a few hundred DOFs: as 3 + 4*iters launches it is pure launch latency
-// (43 graph nodes, 0.31 ms), and on the GPU that also renders, every one of those launches queues behind persistent render
-// CTAs.  Here one cluster of kStepCluster CTAs (one GPC) runs the entire step: phases are separated by the hardware
-// cluster barrier (barrier.cluster, release/acquire), DOFs and the rhs live in shared memory, everything that crosses CTAs
-// goes through L2 (written with plain stores, read back with ld.global.cg after the barrier).  Each phase repeats the
-// arithmetic of the stand-alone kernels above operation for operation (same lane mapping, same reduction trees), so the
-// result is bit-identical to the multi-kernel path (tested) and steps stay bit-reproducible.
+// one dense mat-vec — over a few thousand IPs and a few hundred DOFs.  As 1 + 3*iters launches it is latency-bound, and on the
+// GPU that also renders every one of those launches queues behind persistent render CTAs (0.21 ms alone, 0.5 ms beside the
+// renderer).  Here ONE cluster of 16 (or 8) CTAs — one GPC — runs the entire step:
+//   * every CTA owns a contiguous run of IPs and a contiguous run of DOF rows for the whole step;
+//   * the IPs' gradient blocks dNx (the only large operand, 1920 B / IP, constant) are streamed through a per-warp shared-memory
+//     stage by TMA bulk copies (cp.async.bulk on an mbarrier), the next block being fetched while the current one is used —
+//     the block for the first round of iteration i+1 is already in flight during the SVDs of iteration i;
+//   * the rhs is gathered IP-centrically: each CTA sums the contributions of ITS IPs per kernel in a fixed order (a CTA-local
+//     kernel -> (ip, corner) CSR built once in shared memory), the C partial vectors are added in rank order: deterministic,
+//     no atomics, and the stresses never leave shared memory;
+//   * the CTA's rows of the pre-inverted matrix stay in shared memory for all iterations when they fit (n <= ~400);
+//   * two hardware cluster barriers (barrier.cluster, release / acquire) per iteration; what crosses CTAs goes through L2
+//     (plain stores, ld.global.cg after the barrier).
+// Same algorithm and per-IP / per-row arithmetic as the kernels above; only the rhs summation order differs (fp64 round-off).
 struct StepClusterArgs {
-    int n_ip, n_k, n, iters, slices;
+    int n_ip, n_k, n, iters;
     double dt, dx3;
     const int *topo; const double *mu, *lam, *dNx;
-    const int *adj_bgn, *adj;
     const double *Ainv, *M, *dof_rest, *dof_f, *rhs_rest, *rhs_gravity;
     double *dof, *dof_vel;
-    double *stress, *last, *mom, *partial;     // scratch in global memory (L2)
+    double *mom, *partialC;                    // scratch in global memory (L2): [n3], [C][n3]
     long long *prof;                           // [8] cycles of CTA 0 per phase, summed over the iterations (diagnostics)
+    int ainv_in_smem;
 };
 constexpr int kStepThreads = 512;
-constexpr int kGatherUnroll = 2;           // entries in flight per lane group in the rhs gather
+constexpr int kStepWarps = kStepThreads / 32;
+constexpr int kGatherUnroll = 4;           // entries in flight per lane group in the rhs gather
 
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -549,97 +557,174 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init1(uint64_t *bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar))); }
+__device__ __forceinline__ void mbar_expect(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {   // TMA 1-D bulk copy, 16-byte multiples
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
 
-// y[row] = (Mat x)[row] (+ add0 + add1) for the rows of this cluster-wide warp; x in shared memory.  Lane j takes the
-// element pairs j, j + 32, ... of the row (matvec3_kernel's partition), four 128-bit row loads in flight per lane.
-__device__ __forceinline__ void cluster_matvec_rows(const double *__restrict__ mat, const double *x_s, int n, int gwarp, int nwarps, int lane,
-                                                    const double *__restrict__ add0, const double *__restrict__ add1, double *__restrict__ y) {
-    for (int row = gwarp; row < n; row += nwarps) {
-        const double *m = mat + (size_t)row * n;
-        double a0 = 0, a1 = 0, a2 = 0;
-        if ((n & 1) == 0) {
-            const double2 *m2 = reinterpret_cast<const double2 *>(m);
-            const int h = n / 2;
-            for (int j0 = lane; j0 < h; j0 += 128) {
-                double2 w[4];
+// one row of y = Mat x (+ add0 + add1): matvec3_kernel's lane partition and shuffle tree; `m` may point to shared or global memory
+__device__ __forceinline__ void cluster_row(const double *m, const double *x_s, int n, int lane, double &a0, double &a1, double &a2) {
+    a0 = a1 = a2 = 0;
+    if ((n & 1) == 0) {
+        const double2 *m2 = reinterpret_cast<const double2 *>(m);
+        const int h = n / 2;
+        for (int j0 = lane; j0 < h; j0 += 128) {
+            double2 w[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) w[u] = (j0 + 32 * u < h) ? __ldg(m2 + j0 + 32 * u) : make_double2(0.0, 0.0);
+            for (int u = 0; u < 4; u++) w[u] = (j0 + 32 * u < h) ? m2[j0 + 32 * u] : make_double2(0.0, 0.0);
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (j0 + 32 * u < h) {
-                        const double *xa = x_s + 6 * (size_t)(j0 + 32 * u);
-                        a0 += w[u].x * xa[0] + w[u].y * xa[3]; a1 += w[u].x * xa[1] + w[u].y * xa[4]; a2 += w[u].x * xa[2] + w[u].y * xa[5];
-                    }
+            for (int u = 0; u < 4; u++) {
+                if (j0 + 32 * u < h) {
+                    const double *xa = x_s + 6 * (size_t)(j0 + 32 * u);
+                    a0 += w[u].x * xa[0] + w[u].y * xa[3]; a1 += w[u].x * xa[1] + w[u].y * xa[4]; a2 += w[u].x * xa[2] + w[u].y * xa[5];
                 }
             }
-        } else {
-            for (int j = lane; j < n; j += 32) {
-                const double w = __ldg(m + j);
-                a0 += w * x_s[3 * j]; a1 += w * x_s[3 * j + 1]; a2 += w * x_s[3 * j + 2];
-            }
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            a0 += __shfl_xor_sync(kFull, a0, o); a1 += __shfl_xor_sync(kFull, a1, o); a2 += __shfl_xor_sync(kFull, a2, o);
+    } else {
+        for (int j = lane; j < n; j += 32) {
+            const double w = m[j];
+            a0 += w * x_s[3 * j]; a1 += w * x_s[3 * j + 1]; a2 += w * x_s[3 * j + 2];
         }
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                double v = c == 0 ? a0 : (c == 1 ? a1 : a2);
-                if (add0) v += add0[3 * row + c];
-                if (add1) v += add1[3 * row + c];
-                y[3 * row + c] = v;
-            }
-        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(kFull, a0, o); a1 += __shfl_xor_sync(kFull, a1, o); a2 += __shfl_xor_sync(kFull, a2, o);
     }
 }
 
-__global__ void __launch_bounds__(kStepThreads, 1) qgmls_step_cluster_kernel(const StepClusterArgs a) {
-    extern __shared__ __align__(16) double step_smem[];
-    const int n3 = 3 * a.n;
-    double *dof_s = step_smem;                 // [n3] current DOFs (every CTA holds a copy)
-    double *vec_s = dof_s + n3;                // [n3] dof_tilde, then the rhs of each iteration
-    double *F_s = vec_s + n3;                  // [ips_per_cta][9]
-    double *stage_s = nullptr;                 // [warps][960] gradient staging (7680 B per warp), placed after F_s below
-    const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int gwarp = rank * (kStepThreads / 32) + wid, nwarps = C * (kStepThreads / 32);
-    const int ips_per_cta = ((a.n_ip + C - 1) / C + 3) & ~3;                  // multiple of 4: a warp's 4 IPs never straddle CTAs
-    stage_s = F_s + 9 * (size_t)ips_per_cta;
-    stage_s = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(stage_s) + 15) & ~uintptr_t(15));
-    const int ip0 = rank * ips_per_cta, ip1 = min(a.n_ip, ip0 + ips_per_cta);
+struct StepSmemLayout { size_t dof, vec, last, F, S, ainv, stage, bars, off, ent, total; };
+__host__ __device__ inline StepSmemLayout step_smem_layout(int n_ip, int n, int n_k, int C, int ainv_in_smem) {
+    const int ips = (((n_ip + C - 1) / C) + 3) & ~3, rows = (n + C - 1) / C;
+    StepSmemLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t r = o; o += (bytes + 15) & ~size_t(15); return r; };
+    L.dof = take(8 * 3 * (size_t)n); L.vec = take(8 * 3 * (size_t)n); L.last = take(8 * 3 * (size_t)rows);
+    L.F = take(8 * 9 * (size_t)ips); L.S = take(8 * 9 * (size_t)ips);
+    L.ainv = take(ainv_in_smem ? 8 * (size_t)rows * n : 0);
+    L.stage = take(8 * 960 * (size_t)kStepWarps);
+    L.bars = take(8 * kStepWarps);
+    L.off = take(4 * (2 * (size_t)n_k + 2));
+    L.ent = take(2 * 8 * (size_t)ips);
+    L.total = o;
+    return L;
+}
 
+__global__ void __launch_bounds__(kStepThreads, 1) qgmls_step_cluster_kernel(const StepClusterArgs a) {
+    extern __shared__ __align__(16) unsigned char step_smem[];
+    const int n = a.n, n3 = 3 * a.n;
+    const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+    const StepSmemLayout L = step_smem_layout(a.n_ip, n, a.n_k, C, a.ainv_in_smem);
+    double *dof_s = reinterpret_cast<double *>(step_smem + L.dof);      // [n3] current DOFs (every CTA holds a copy)
+    double *vec_s = reinterpret_cast<double *>(step_smem + L.vec);      // [n3] dof_tilde, then the rhs of each iteration
+    double *last_s = reinterpret_cast<double *>(step_smem + L.last);    // [rows,3] DOFs of this CTA's rows at the start of the step
+    double *F_s = reinterpret_cast<double *>(step_smem + L.F);          // [ips,9]
+    double *S_s = reinterpret_cast<double *>(step_smem + L.S);          // [ips,9] stresses dx^3 (mu R + lam V)
+    double *ainv_s = reinterpret_cast<double *>(step_smem + L.ainv);    // [rows,n] this CTA's rows of the pre-inverted matrix
+    double *stage_s = reinterpret_cast<double *>(step_smem + L.stage);  // [warps][960] gradient blocks of 4 IPs (7680 B per warp)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(step_smem + L.bars);  // one mbarrier per warp
+    int *off_s = reinterpret_cast<int *>(step_smem + L.off);            // [n_k+1] CSR offsets, then [n_k+1] counters
+    int *cnt_s = off_s + a.n_k + 1;
+    unsigned short *ent_s = reinterpret_cast<unsigned short *>(step_smem + L.ent);   // local (ip, corner) codes grouped by kernel
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ips_per_cta = (((a.n_ip + C - 1) / C) + 3) & ~3;
+    const int ip0 = min(a.n_ip, rank * ips_per_cta), ip1 = min(a.n_ip, ip0 + ips_per_cta), nloc = ip1 - ip0;
+    const int rows_per_cta = (n + C - 1) / C, row0 = min(n, rank * rows_per_cta), row1 = min(n, row0 + rows_per_cta);
+    const int n_rounds = (ips_per_cta / 4 + kStepWarps - 1) / kStepWarps;     // gradient blocks (4 IPs) per warp and iteration
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
 #define PN_STEP_TICK(k) { const long long t_ = clock64(); pc[k] += t_ - tc; tc = t_; }
-    // ---- dof_tilde = dof + dt vel, last = dof (solver.py:575,597); momentum = M/dt^2 tilde + f + g (solver.py:576)
+
+    // this warp's gradient block of round r: IPs ip0 + 4 * (r * warps + wid) ..+3; bytes = what exists of it
+    auto block_bytes = [&](int r) -> uint32_t {
+        const int v = ip0 + 4 * (r * kStepWarps + wid);
+        return (r < n_rounds && v < ip1) ? (uint32_t)(min(4, ip1 - v) * 1920) : 0u;
+    };
+    auto fetch = [&](int r) {                                           // whole warp calls; lane 0 issues
+        const uint32_t bytes = block_bytes(r);
+        if (lane == 0 && bytes) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage's previous readers (generic proxy) come first
+            mbar_expect(&bars[wid], bytes);
+            bulk_load(stage_s + (size_t)wid * 960, a.dNx + (size_t)(ip0 + 4 * (r * kStepWarps + wid)) * 240, bytes, &bars[wid]);
+        }
+    };
+    if (lane == 0) mbar_init1(&bars[wid]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t stage_phase = 0;
+    int my_rounds = 0;
+    for (int r = 0; r < n_rounds; r++) my_rounds += block_bytes(r) != 0;
+    fetch(0);
+
+    // ---- dof_tilde = dof + dt vel (solver.py:575), dof_last (597); CTA-local kernel -> (ip, corner) lists; resident matrix rows
     for (int i = tid; i < n3; i += kStepThreads) {
         const double d = a.dof[i];
         dof_s[i] = d;
         vec_s[i] = d + a.dt * a.dof_vel[i];
-        if (rank == 0) a.last[i] = d;
+    }
+    for (int i = tid; i < a.n_k + 1; i += kStepThreads) { off_s[i] = 0; cnt_s[i] = 0; }
+    if (a.ainv_in_smem) {
+        const double2 *src = reinterpret_cast<const double2 *>(a.Ainv + (size_t)row0 * n);
+        double2 *dst = reinterpret_cast<double2 *>(ainv_s);
+        const int tot2 = (row1 - row0) * n / 2;                         // n is even when ainv_in_smem (checked on the host)
+        for (int i = tid; i < tot2; i += kStepThreads) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    cluster_matvec_rows(a.M, vec_s, a.n, gwarp, nwarps, lane, a.dof_f, a.rhs_gravity, a.mom);
-    cluster_sync_all();
+    for (int i = tid; i < 3 * (row1 - row0); i += kStepThreads) last_s[i] = dof_s[3 * row0 + i];
+    for (int e = tid; e < nloc * 8; e += kStepThreads) atomicAdd(&cnt_s[a.topo[8 * (size_t)ip0 + e]], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int k = 0; k < a.n_k; k++) { off_s[k] = run; run += cnt_s[k]; cnt_s[k] = 0; }
+        off_s[a.n_k] = run;
+    }
+    __syncthreads();
+    for (int e = tid; e < nloc * 8; e += kStepThreads) {
+        const int k = a.topo[8 * (size_t)ip0 + e];
+        ent_s[off_s[k] + atomicAdd(&cnt_s[k], 1)] = (unsigned short)e;
+    }
+    __syncthreads();
+    for (int k = tid; k < a.n_k; k += kStepThreads) {                     // ascending (ip, corner) inside a kernel: a fixed summation order
+        unsigned short *l = ent_s + off_s[k];
+        const int m = off_s[k + 1] - off_s[k];
+        for (int i = 1; i < m; i++) {
+            const unsigned short v = l[i];
+            int j = i - 1;
+            while (j >= 0 && l[j] > v) { l[j + 1] = l[j]; j--; }
+            l[j + 1] = v;
+        }
+    }
+    // ---- momentum = M/dt^2 dof_tilde + dof_f + rhs_gravity (solver.py:576) for this CTA's rows
+    for (int row = row0 + wid; row < row1; row += kStepWarps) {
+        double a0, a1, a2;
+        cluster_row(a.M + (size_t)row * n, vec_s, n, lane, a0, a1, a2);
+        if (lane == 0) {
+            a.mom[3 * row] = (a0 + a.dof_f[3 * row]) + a.rhs_gravity[3 * row];
+            a.mom[3 * row + 1] = (a1 + a.dof_f[3 * row + 1]) + a.rhs_gravity[3 * row + 1];
+            a.mom[3 * row + 2] = (a2 + a.dof_f[3 * row + 2]) + a.rhs_gravity[3 * row + 2];
+        }
+    }
+    __syncthreads();
     PN_STEP_TICK(0)
 
     for (int it = 0; it < a.iters; it++) {
-        // ---- calc_elastic, part 1: F per IP, 8 lanes per IP (ip_stress_kernel's mapping and shuffle tree).  A warp's 4 IPs x 8
-        // corners x [3][10] gradients are ONE contiguous 7680-byte run of dNx: it is staged into shared memory with fifteen
-        // coalesced 128-bit loads per lane (per-lane 240-byte blocks read straight from global cost 32 sectors per instruction)
-        for (int t = tid; t < ips_per_cta * 8; t += kStepThreads) {
-            const int lv = t >> 3, v = ip0 + lv, i = t & 7;
+        // ---- calc_elastic, part 1: F per IP, 8 lanes per IP (ip_stress_kernel's mapping and shuffle tree), gradients from the stage
+        for (int r = 0; r < n_rounds; r++) {
+            if (block_bytes(r) == 0) continue;                              // warp-uniform
+            if (my_rounds > 1 || (it == 0 && r == 0)) { mbar_wait_parity(&bars[wid], stage_phase); stage_phase ^= 1; }
+            const int lv = 4 * (r * kStepWarps + wid) + (lane >> 3), v = ip0 + lv, i = lane & 7;
             const bool live = v < ip1;
-            const int v_warp = ip0 + ((t & ~31) >> 3);                         // first IP of this warp's run
-            double2 *st2 = reinterpret_cast<double2 *>(stage_s + (size_t)wid * 960);
-            const double2 *src2 = reinterpret_cast<const double2 *>(a.dNx + (size_t)v_warp * 240);
-            const int n2 = max(0, min(4, a.n_ip - v_warp)) * 120;             // double2 elements that exist
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < 15; u++) { const int e = lane + 32 * u; if (e < n2) st2[e] = __ldg(src2 + e); }
-            __syncwarp();
             double F[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (live) {
-                const double *dN = stage_s + (size_t)wid * 960 + (size_t)(t & 31) * 30;
+                const double *dN = stage_s + (size_t)wid * 960 + (size_t)lane * 30;
                 const double *d = dof_s + 3 * (size_t)(a.topo[8 * v + i] * 10);
 #pragma unroll
                 for (int x = 0; x < 10; x++) {
@@ -657,11 +742,18 @@ __global__ void __launch_bounds__(kStepThreads, 1) qgmls_step_cluster_kernel(con
 #pragma unroll
                 for (int k = 0; k < 9; k++) F_s[9 * lv + k] = F[k];
             }
+            __syncwarp();
+            if (my_rounds > 1) {                                             // next block (of the next iteration after the last round)
+                int nr = r + 1;
+                while (nr < n_rounds && block_bytes(nr) == 0) nr++;
+                if (nr < n_rounds) fetch(nr);
+                else if (it + 1 < a.iters) fetch(0);
+            }
         }
         __syncthreads();
         PN_STEP_TICK(1)
-        // ---- part 2: one thread per IP: SVD, R = U V^T, V = U proj(sigma) V^T, stress = dx^3 (mu R + lam V)
-        for (int lv = tid; lv < ip1 - ip0; lv += kStepThreads) {
+        // ---- part 2: one thread per IP: SVD, R = U V^T, V = U proj(sigma) V^T, stress = dx^3 (mu R + lam V) -> shared memory
+        for (int lv = tid; lv < nloc; lv += kStepThreads) {
             const int v = ip0 + lv;
             double F[9], U[9], sg[3], V[9], sp[3];
 #pragma unroll
@@ -673,93 +765,90 @@ __global__ void __launch_bounds__(kStepThreads, 1) qgmls_step_cluster_kernel(con
                 for (int c = 0; c < 3; c++) {
                     double x = 0, y = 0;
                     for (int k = 0; k < 3; k++) { x += U[r * 3 + k] * V[c * 3 + k]; y += U[r * 3 + k] * sp[k] * V[c * 3 + k]; }
-                    a.stress[(size_t)v * 9 + r * 3 + c] = a.dx3 * (m * x + l * y);
+                    S_s[9 * lv + r * 3 + c] = a.dx3 * (m * x + l * y);
                 }
         }
+        __syncthreads();
         PN_STEP_TICK(2)
-        cluster_sync_all();
-        PN_STEP_TICK(3)
-        // ---- collect_rhs_IP as a gather: one warp per (kernel, 128-entry slice).  Lane group g = lane / 10 (three groups, lanes
-        // 30-31 idle) walks the slice's entries g, g + 3, ... in order; lane x = lane % 10 of a group owns DOF slot x and reads the
-        // entry's three gradient rows with coalesced 80-byte loads; the 3x3 stress is a broadcast load.  Sums run in a fixed order
-        // (entry order within a group, then (g0 + g1) + g2): deterministic, no atomics, no 30 x 5 shuffle trees.
-        for (int item = gwarp; item < a.n_k * a.slices; item += nwarps) {
-            const int k = item / a.slices, sl = item % a.slices;
-            const int e0 = a.adj_bgn[k] + sl * 128, cnt = max(0, min(128, a.adj_bgn[k + 1] - e0));
-            int codes[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) codes[u] = (lane + 32 * u < cnt) ? a.adj[e0 + lane + 32 * u] : -1;
+        // ---- collect_rhs_IP, IP-centric: a warp per kernel; lane group g = lane / 10 walks the kernel's local entries g, g + 3, ...
+        // in order, lane x = lane % 10 owns DOF slot x (coalesced 80-byte gradient rows); (g0 + g1) + g2; no atomics
+        for (int k = wid; k < a.n_k; k += kStepWarps) {
+            const int b = off_s[k], cnt = off_s[k + 1] - b;
             const int g = lane / 10, x = lane - 10 * g;
             double r0 = 0, r1 = 0, r2 = 0;
-            for (int base = 0; base < cnt; base += 3 * kGatherUnroll) {       // warp-uniform trip count: every lane joins the shuffles
-                double S[kGatherUnroll][9], G[kGatherUnroll][3];
-                bool ok[kGatherUnroll];
+            if (g < 3) {
+                for (int j0 = g; j0 < cnt; j0 += 3 * kGatherUnroll) {
+                    double G[kGatherUnroll][3];
+                    int lvs[kGatherUnroll];
 #pragma unroll
-                for (int u = 0; u < kGatherUnroll; u++) {
-                    const int j = base + 3 * u + g;
-                    ok[u] = g < 3 && j < cnt;
-                    // entry j's code sits in register codes[j / 32] of lane j % 32
-                    const int c0 = __shfl_sync(kFull, codes[0], j & 31), c1 = __shfl_sync(kFull, codes[1], j & 31);
-                    const int c2 = __shfl_sync(kFull, codes[2], j & 31), c3 = __shfl_sync(kFull, codes[3], j & 31);
-                    const int code = (j >> 5) == 0 ? c0 : ((j >> 5) == 1 ? c1 : ((j >> 5) == 2 ? c2 : c3));
-                    if (ok[u]) {
-                        const int v = code >> 3, i = code & 7;
-                        const double *Sp = a.stress + (size_t)v * 9;
-                        const double *dN = a.dNx + (size_t)v * 240 + i * 30 + x;
-#pragma unroll
-                        for (int q = 0; q < 9; q++) S[u][q] = __ldcg(Sp + q);
-                        G[u][0] = __ldg(dN); G[u][1] = __ldg(dN + 10); G[u][2] = __ldg(dN + 20);
+                    for (int u = 0; u < kGatherUnroll; u++) {
+                        const int j = j0 + 3 * u;
+                        lvs[u] = -1;
+                        if (j < cnt) {
+                            const int e = ent_s[b + j];
+                            lvs[u] = e >> 3;
+                            const double *dN = a.dNx + (size_t)(ip0 + (e >> 3)) * 240 + (e & 7) * 30 + x;
+                            G[u][0] = __ldg(dN); G[u][1] = __ldg(dN + 10); G[u][2] = __ldg(dN + 20);
+                        }
                     }
-                }
 #pragma unroll
-                for (int u = 0; u < kGatherUnroll; u++) {
-                    if (ok[u]) {
-                        r0 += S[u][0] * G[u][0] + S[u][1] * G[u][1] + S[u][2] * G[u][2];
-                        r1 += S[u][3] * G[u][0] + S[u][4] * G[u][1] + S[u][5] * G[u][2];
-                        r2 += S[u][6] * G[u][0] + S[u][7] * G[u][1] + S[u][8] * G[u][2];
+                    for (int u = 0; u < kGatherUnroll; u++) {
+                        if (lvs[u] >= 0) {
+                            const double *S = S_s + 9 * lvs[u];
+                            r0 += S[0] * G[u][0] + S[1] * G[u][1] + S[2] * G[u][2];
+                            r1 += S[3] * G[u][0] + S[4] * G[u][1] + S[5] * G[u][2];
+                            r2 += S[6] * G[u][0] + S[7] * G[u][1] + S[8] * G[u][2];
+                        }
                     }
                 }
             }
-            // (group 0 + group 1) + group 2, lanes 0-9 write slot x
             const double b0 = __shfl_sync(kFull, r0, (lane + 10) & 31), b1 = __shfl_sync(kFull, r1, (lane + 10) & 31), b2 = __shfl_sync(kFull, r2, (lane + 10) & 31);
             const double c0 = __shfl_sync(kFull, r0, (lane + 20) & 31), c1 = __shfl_sync(kFull, r1, (lane + 20) & 31), c2 = __shfl_sync(kFull, r2, (lane + 20) & 31);
             if (lane < 10) {
-                double *o = a.partial + (size_t)item * 30 + 3 * lane;
+                double *o = a.partialC + (size_t)rank * n3 + (size_t)k * 30 + 3 * lane;
                 o[0] = (r0 + b0) + c0; o[1] = (r1 + b1) + c1; o[2] = (r2 + b2) + c2;
             }
         }
         PN_STEP_TICK(4)
         cluster_sync_all();
         PN_STEP_TICK(3)
-        // ---- rhs = momentum + gathered - rhs_rest (solver.py:599; rhs_final_kernel), every CTA its own copy in shared memory
+        // ---- rhs = momentum + gathered - rhs_rest (solver.py:599): the C partial vectors in rank order, every CTA its own copy
         for (int id = tid; id < n3; id += kStepThreads) {
-            const int k = id / 30, i = id % 30;
             double sum = 0.0;
-            for (int sl = 0; sl < a.slices; sl++) sum += __ldcg(a.partial + ((size_t)k * a.slices + sl) * 30 + i);
+            for (int c = 0; c < C; c++) sum += __ldcg(a.partialC + (size_t)c * n3 + id);
             vec_s[id] = (__ldcg(a.mom + id) + sum) - a.rhs_rest[id];
         }
         __syncthreads();
-        // ---- dof = dof_rest + Ainv rhs (solver.py:600-601)
-        cluster_matvec_rows(a.Ainv, vec_s, a.n, gwarp, nwarps, lane, a.dof_rest, nullptr, a.dof);
+        // ---- dof = dof_rest + Ainv rhs (solver.py:600-601) for this CTA's rows; the last iteration also writes the velocity (602)
+        for (int row = row0 + wid; row < row1; row += kStepWarps) {
+            double a0, a1, a2;
+            cluster_row(a.ainv_in_smem ? ainv_s + (size_t)(row - row0) * n : a.Ainv + (size_t)row * n, vec_s, n, lane, a0, a1, a2);
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const double v = (c == 0 ? a0 : (c == 1 ? a1 : a2)) + a.dof_rest[3 * row + c];
+                    a.dof[3 * row + c] = v;
+                    if (it == a.iters - 1) a.dof_vel[3 * row + c] = (v - last_s[3 * (row - row0) + c]) / a.dt * 0.998;
+                }
+            }
+        }
         PN_STEP_TICK(5)
-        cluster_sync_all();
-        PN_STEP_TICK(3)
-        for (int i = tid; i < n3; i += kStepThreads) dof_s[i] = __ldcg(a.dof + i);
-        __syncthreads();
-        PN_STEP_TICK(6)
+        if (it + 1 < a.iters) {
+            cluster_sync_all();
+            PN_STEP_TICK(3)
+            for (int i = tid; i < n3; i += kStepThreads) dof_s[i] = __ldcg(a.dof + i);
+            __syncthreads();
+            PN_STEP_TICK(6)
+        }
     }
-    // ---- dof_vel = (dof - dof_last) / dt * 0.998 (solver.py:602)
-    for (int i = rank * kStepThreads + tid; i < n3; i += C * kStepThreads) a.dof_vel[i] = (dof_s[i] - __ldcg(a.last + i)) / a.dt * 0.998;
-    PN_STEP_TICK(7)
+    cluster_sync_all();        // nobody leaves (and frees its shared memory / lets the next launch overwrite scratch) before everyone is done
 #undef PN_STEP_TICK
     if (a.prof && rank == 0 && tid == 0)
         for (int k = 0; k < 8; k++) a.prof[k] = pc[k];
 }
 
-size_t step_cluster_smem(int n_ip, int n, int C) {
-    const int ips_per_cta = ((n_ip + C - 1) / C + 3) & ~3;
-    return sizeof(double) * (2 * 3 * (size_t)n + 9 * (size_t)ips_per_cta + (kStepThreads / 32) * 960) + 32;
-}
+size_t step_cluster_smem(int n_ip, int n, int n_k, int C, int ainv_in_smem) { return step_smem_layout(n_ip, n, n_k, C, ainv_in_smem).total + 16; }
+int step_ainv_fits(int n, int C) { return (n % 2 == 0) && (size_t)((n + C - 1) / C) * n * 8 <= 48 * 1024; }
 
 // ---------------------------------------------------------------- PCG on (A + 1e-3 I) x = b, 3 right-hand sides
 // Jacobi-preconditioned CG over the active rows; one cooperative single-block driver per iteration would serialise,
@@ -1010,22 +1099,22 @@ extern "C" int pn_qgmls_matvec3(const double *mat, const double *x, int n, doubl
 }
 
 extern "C" uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k, int adj_slices) {
-    // stress | tilde last mom rhs x | pcg | partial | 8 phase cycle counters of the cluster kernel
-    return 9ull * n_ip + 9ull * 30 * n_k + 16 + 30ull * n_k * (adj_slices > 0 ? adj_slices : 1) + 8;
+    // stress | tilde last mom rhs x | pcg | partial | 8 phase cycle counters of the cluster kernel | its 16 per-CTA partial rhs vectors
+    return 9ull * n_ip + 9ull * 30 * n_k + 16 + 30ull * n_k * (adj_slices > 0 ? adj_slices : 1) + 8 + 16ull * 30 * n_k;
 }
 
 // Cluster size for the one-kernel step: 16 CTAs (non-portable size, one GPC) if the device can co-schedule them, else 8;
 // 0 = use the multi-kernel path (big systems: the dense mat-vec wants the whole GPU's bandwidth, not one GPC's).
 static int g_step_force_multi = 1;   // measured on B200: the cluster kernel is slower (469 vs 219 us, chair body) -> opt-in
 extern "C" int pn_qgmls_step_mode(int force_multi_kernel) { g_step_force_multi = force_multi_kernel; return PN_OK; }
-static int step_cluster_size(int n_ip, int n) {
+static int step_cluster_size(int n_ip, int n, int n_k) {
     static int cached_key_n = -1, cached_key_ip = -1, cached = 0;
-    if (n > 1280) return 0;                                  // matrix > 13 MB (x (1 + iters) reads per step)
+    if (n > 1280 || n_ip > 16 * 1024) return 0;              // matrix > 13 MB (x (1 + iters) reads per step) / 16-bit local entry codes
     if (cached_key_n == n && cached_key_ip == n_ip) return cached;
     int best = 0;
     for (int C : {16, 8}) {
-        const size_t smem = step_cluster_smem(n_ip, n, C);
-        if (smem > 200 * 1024) continue;
+        const size_t smem = step_cluster_smem(n_ip, n, n_k, C, step_ainv_fits(n, C));
+        if (smem > 220 * 1024) continue;
         if (cudaFuncSetAttribute(qgmls_step_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
         if (C > 8 && cudaFuncSetAttribute(qgmls_step_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
         cudaLaunchConfig_t cfg{};
@@ -1042,7 +1131,7 @@ static int step_cluster_size(int n_ip, int n) {
 }
 
 extern "C" int pn_qgmls_step_launches(int n_ip, int n_k, int iters, int solver, int pcg_iters) {
-    if (solver == 0 && !g_step_force_multi && step_cluster_size(n_ip, 10 * n_k) > 0) return 1;
+    if (solver == 0 && !g_step_force_multi && step_cluster_size(n_ip, 10 * n_k, n_k) > 0) return 1;
     if (solver == 0 && 10 * n_k <= 512) return 1 + 3 * iters;
     return 3 + iters * (solver == 0 ? 4 : 6 + 4 * pcg_iters);
 }
@@ -1063,16 +1152,18 @@ extern "C" int pn_qgmls_step(const pn_qgmls_step_t *s, int solver, void *stream)
     const double dx3 = s->dx * s->dx * s->dx;
     const int eb = div_up(n3, 256);
     if (solver == 0 && !g_step_force_multi) {
-        const int C = step_cluster_size(s->n_ip, n);
+        const int C = step_cluster_size(s->n_ip, n, s->n_k);
         if (C > 0) {
             StepClusterArgs a{};
-            a.n_ip = s->n_ip; a.n_k = s->n_k; a.n = n; a.iters = s->iters; a.slices = s->adj_slices; a.dt = s->dt; a.dx3 = dx3;
-            a.topo = s->topo; a.mu = s->mu; a.lam = s->lam; a.dNx = s->dNx; a.adj_bgn = s->adj_bgn; a.adj = s->adj;
+            a.n_ip = s->n_ip; a.n_k = s->n_k; a.n = n; a.iters = s->iters; a.dt = s->dt; a.dx3 = dx3;
+            a.topo = s->topo; a.mu = s->mu; a.lam = s->lam; a.dNx = s->dNx;
             a.Ainv = s->Ainv; a.M = s->M; a.dof_rest = s->dof_rest; a.dof_f = s->dof_f; a.rhs_rest = s->rhs_rest; a.rhs_gravity = s->rhs_gravity;
-            a.dof = s->dof; a.dof_vel = s->dof_vel; a.stress = stress; a.last = last; a.mom = mom; a.partial = partial;
+            a.dof = s->dof; a.dof_vel = s->dof_vel; a.mom = mom;
             a.prof = reinterpret_cast<long long *>(partial + 30 * (size_t)s->n_k * s->adj_slices);
+            a.partialC = partial + 30 * (size_t)s->n_k * s->adj_slices + 8;
+            a.ainv_in_smem = step_ainv_fits(n, C);
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(C); cfg.blockDim = dim3(kStepThreads); cfg.dynamicSmemBytes = step_cluster_smem(s->n_ip, n, C); cfg.stream = st;
+            cfg.gridDim = dim3(C); cfg.blockDim = dim3(kStepThreads); cfg.dynamicSmemBytes = step_cluster_smem(s->n_ip, n, s->n_k, C, a.ainv_in_smem); cfg.stream = st;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;

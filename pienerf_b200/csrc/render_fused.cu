@@ -674,7 +674,8 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
         Wv.xyzdt = (float4 *)(base + w.xyzdt); Wv.meta = (int2 *)(base + w.meta); Wv.out = (float4 *)(base + w.out);
         Wv.slab_next = (int *)(base + w.slab_next); Wv.cap = w.cap;
         Wv.weights_img = (const pn::tc::Weights *)(base + w.weights_img);
-        field_weights_kernel<<<1, 256, 0, st>>>(A.field, (pn::tc::Weights *)(base + w.weights_img));
+        // the bf16 hi / lo weight image only changes with the weights: a caller that renders frame after frame builds it once
+        if (!(io && (io->flags & PN_IO_WEIGHTS_READY))) field_weights_kernel<<<1, 256, 0, st>>>(A.field, (pn::tc::Weights *)(base + w.weights_img));
         PN_CUDA(cudaMemsetAsync(base + w.ctl, 0, 16 * 16 + 256, st));       // ctl + counters (adjacent, 256-byte aligned blocks)
         const size_t smem = sizeof(WaveWsSmem) + 128;
         if (int rc = set_smem(wave_field_ws_kernel, smem)) return rc;
@@ -682,15 +683,20 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
         // another stream (pn_set_render_sm_reserve: on the GPU that also runs the simulator, its many tiny launches otherwise queue
         // behind render CTAs that hold every SM until their kernel ends)
         const uint32_t sms = (uint32_t)max(8, pn_sm_count_cached() - g_sm_reserve);
-        // pass caps 32, 64, ... until the per-ray cap is covered; one spare pass absorbs the <32-sample overshoot per pass
-        const int n_pass = pn_render_pass_count(d->max_steps);
+        // pass caps 32, 64, ... until the per-ray cap is covered; one spare pass absorbs the <32-sample overshoot per pass.
+        // io->max_passes < that: fewer launches, the LAST pass marches every remaining sample (cap = max_steps) — rays are then
+        // cut short only if the sample list itself overflows, which stats[4..5] report.
+        int n_pass = pn_render_pass_count(d->max_steps);
+        const bool limited = io && io->max_passes > 0 && io->max_passes < n_pass;
+        if (limited) n_pass = io->max_passes;
         int cap_p = PN_WAVE_FIRST_CAP, fk = 0;
         if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
         for (int p = 0; p < n_pass; p++, cap_p *= 2) {
+            const int cap_now = (limited && p == n_pass - 1) ? (int)d->max_steps : cap_p;
             switch (d->num_seek_IP) {
-                case 1: wave_march_kernel<1><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
-                case 2: wave_march_kernel<2><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
-                default: wave_march_kernel<3><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_p); break;
+                case 1: wave_march_kernel<1><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_now); break;
+                case 2: wave_march_kernel<2><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_now); break;
+                default: wave_march_kernel<3><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_now); break;
             }
             if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk], st));
             wave_field_ws_kernel<<<sms, (kWsProd + kWsCons) * 128, smem, st>>>(A, Wv, p);

@@ -224,6 +224,7 @@ struct __align__(128) WaveWsSmem {
     WsTile tile[kWsCons];
     WsStage stage[kWsStages];
     uint64_t full[kWsStages], empty[kWsStages];
+    int released[kWsStages];   // uses of a stage whose tile is completely done (software count next to the parity-only mbarriers, see below)
     uint32_t tmem_base;
 };
 
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
     if (n_rows == 0) return;
     const float2 *table = reinterpret_cast<const float2 *>(A.field.embeddings);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kWsStages; s++) { pn::tc::mbar_init(&S.full[s], 4); pn::tc::mbar_init(&S.empty[s], 1); }
+        for (int s = 0; s < kWsStages; s++) { pn::tc::mbar_init(&S.full[s], 4); pn::tc::mbar_init(&S.empty[s], 1); S.released[s] = 0; }
         for (int g = 0; g < kWsCons; g++) pn::tc::mbar_init(&S.tile[g].bar, 1);
         pn::tc::mbar_init(&S.wbar, 1);
         pn::tc::fence_barrier_init();
@@ -275,6 +276,11 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
             const bool valid = mt.x >= 0;
             float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) sm = Wv.xyzdt[i];
+            // A stage is shared by the producer groups (4 stages, 3 groups), and an mbarrier wait only sees the PARITY of the phase:
+            // a group that got two uses ahead of a slow neighbour would read the parity of `use - 2` as "free" and overwrite a
+            // stage that was never filled.  The consumers' software count keeps everybody within one use (never seen with the
+            // gather, whose groups run at the same pace; reproducible with the fast feature-load producers of pn_mlp_forward).
+            if (use >= 2) { while (*reinterpret_cast<volatile int *>(&S.released[st]) < use - 1) __nanosleep(20); }
             pn::tc::mbar_wait(&S.empty[st], (use & 1) ^ 1);               // stage free (a fresh barrier passes at once)
             char *hi = reinterpret_cast<char *>(S.stage[st].a[0]) + row * 16, *lo = reinterpret_cast<char *>(S.stage[st].a[1]) + row * 16;
             if (Wv.enc) {
@@ -338,6 +344,7 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
 #else
             pn::tc::mlp_tile_ts(T, S.w, cg, row, sh, phase, sigma, r, g, b, S.stage[st].a[0], S.stage[st].a[1], &S.empty[st]);
 #endif
+            if (row == 0) *reinterpret_cast<volatile int *>(&S.released[st]) = use + 1;
             if (valid) {
                 sigma = A.density_scale * sigma;
                 Wv.out[i] = make_float4(Wv.enc ? sigma : 1.0f - __expf(-sigma * dt), r, g, b);
@@ -350,6 +357,10 @@ __global__ void __launch_bounds__((kWsProd + kWsCons) * 128, 1) wave_field_ws_ke
 }
 
 // --------------------------------------------------------------------------------------------- composite
+#ifndef PN_COMP_BATCH
+#define PN_COMP_BATCH 16     // sample rows in flight per ray: the walk is a chain of L2 round trips, 16 halves their number vs 8
+#endif
+constexpr int kCompBatch = PN_COMP_BATCH;
 __global__ void __launch_bounds__(256) wave_composite_kernel(const RenderArgs A, const WaveArgs Wv, int pass, int last_pass) {
     const int n_alive = pass == 0 ? A.queue->n_active : Wv.ctl[pass].n_alive;
     const int *alive = pass == 0 ? A.active : Wv.alive[(pass - 1) & 1];
@@ -374,16 +385,19 @@ __global__ void __launch_bounds__(256) wave_composite_kernel(const RenderArgs A,
             bool terminated = false;
             int idx = lk.x, rem = lk.y;
             while (rem > 0 && !terminated) {
-                // rows of a ray are contiguous up to the end of a slab: 8 independent loads per step, then the recurrence
+                // rows of a ray are contiguous up to the end of a slab: kCompBatch independent loads per step, then the recurrence;
+                // the row at which the ray continues after this slab is fetched first (the only dependent load of the walk)
                 const int seg = min(rem, kSlab - (idx & (kSlab - 1)));
-                for (int s = 0; s < seg && !terminated; s += 8) {
-                    float4 o[8];
-                    float ta[8];
+                int next_idx = 0;
+                if (rem > seg) next_idx = Wv.slab_next[(idx + seg) / kSlab - 1];
+                for (int s = 0; s < seg && !terminated; s += kCompBatch) {
+                    float4 o[kCompBatch];
+                    float ta[kCompBatch];
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
+                    for (int j = 0; j < kCompBatch; j++)
                         if (s + j < seg) { o[j] = Wv.out[idx + s + j]; ta[j] = __int_as_float(Wv.meta[idx + s + j].y); }
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
+                    for (int j = 0; j < kCompBatch; j++) {
                         if (s + j < seg && !terminated) {
                             const float T = 1 - ws;                             // raymarching.cu:890-906
                             const float w = o[j].x * T;
@@ -397,8 +411,7 @@ __global__ void __launch_bounds__(256) wave_composite_kernel(const RenderArgs A,
                         }
                     }
                 }
-                rem -= seg; idx += seg;
-                if (rem > 0 && !terminated) idx = Wv.slab_next[idx / kSlab - 1];   // idx sits on a slab boundary here
+                rem -= seg; idx = next_idx;
             }
             if (terminated || finished || last_pass) {
                 const size_t o = A.pix ? (size_t)A.pix[ray] : (size_t)ray;   // this ray's pixel in the (possibly remote) frame
@@ -448,7 +461,9 @@ __global__ void wave_stats_kernel(const FrameQueue *q, const FrameGeom *g, const
     stats[4] = (g->overflow ? 1 : 0) | (Wv.counters[2] ? 2 : 0);   // bit 0: IP grid clamped; bit 1: rays cut short (sample list + passes exhausted)
     stats[5] = Wv.counters[2];   // rays finalised by the last pass before they finished or terminated
     stats[6] = Wv.counters[3];   // 32-lattice-point chunks a full sample list deferred to the next pass (harmless unless [5] > 0)
-    stats[7] = 0;
+    int used = 0;
+    for (int p = 0; p < n_pass; p++) used += (p == 0 ? q->n_active : Wv.ctl[p].n_alive) > 0;
+    stats[7] = used;             // passes that had rays to march (a frame pipeline sizes its graphs with this, io->max_passes)
 }
 
 }  // namespace

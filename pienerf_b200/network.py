@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import raymarching
-from ._lib import DeformT, FieldT, FrameIoT, check, dptr, lib, stream_ptr
+from ._lib import PN_IO_WEIGHTS_READY, DeformT, FieldT, FrameIoT, check, dptr, lib, stream_ptr
 from .gridencoder import GridEncoder
 from .shencoder import SHEncoder
 
@@ -364,7 +364,8 @@ class NeRFNetwork(nn.Module):
 
     @torch.no_grad()
     def render_deformed(self, rays_o, rays_d, staged=False, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024, T_thresh=1e-2,
-                        mode=None, out=None, workspace=None, stats=None, io=None, embeddings=None, ip_state=None, noises=None, **kwargs):
+                        mode=None, out=None, workspace=None, stats=None, io=None, embeddings=None, ip_state=None, noises=None, max_passes=None,
+                        weights_ready=False, **kwargs):
         """renderer.py:587-599 -> rund_cuda semantics in one device-resident call.  Returns the same dict.
         mode 3: wavefront (default); 0: fused warp-cooperative kernel + tcgen05 MLP; 1: same with the fp32 SIMT MLP; 2: one lane
         per ray.  `workspace` / `stats` / `embeddings` / `ip_state` / `io` (_lib.FrameIoT) let a frame pipeline keep several
@@ -383,6 +384,11 @@ class NeRFNetwork(nn.Module):
             if io is None:
                 io = FrameIoT()
             io.noises = dptr(noises, "noises", torch.float32)
+        if max_passes or weights_ready:                                       # frame pipelines: fewer launches per frame (see pn_frame_io_t)
+            if io is None:
+                io = FrameIoT()
+            io.max_passes = int(max_passes or 0)
+            io.flags = PN_IO_WEIGHTS_READY if weights_ready else 0
         d, keep = self.deform_struct(ip_state, dt_gamma=dt_gamma, bg_color=bg_color, max_steps=max_steps, T_thresh=T_thresh, **kwargs)
         need = self.workspace_bytes(N, d.n_vtx, **kwargs)
         if workspace is None:
@@ -399,9 +405,12 @@ class NeRFNetwork(nn.Module):
             out = {"image": torch.empty(N, 3, dtype=torch.float32, device=device), "depth": torch.empty(N, dtype=torch.float32, device=device),
                    "depth_0": torch.empty(N, dtype=torch.float32, device=device), "weights_sum": torch.empty(N, dtype=torch.float32, device=device)}
         # kernels this call enqueues: bbox, 4 x IP grid, frame setup, IP pack, 3 x neighbourhood lists, (3 per pass | 1 fused), stats
-        self._render_launches = 11 + (1 + 3 * int(lib.pn_render_pass_count(int(max_steps))) if mode == 3 else 1)
+        n_pass = int(lib.pn_render_pass_count(int(max_steps)))
+        if io is not None and 0 < io.max_passes < n_pass:
+            n_pass = int(io.max_passes)
+        self._render_launches = 11 + (1 + 3 * n_pass if mode == 3 else 1)
         if io is not None:
-            self._render_launches += (1 if io.epoch else 0) + (1 if io.n_signal else 0)
+            self._render_launches += (1 if io.epoch else 0) + (1 if io.n_signal else 0) - (1 if (io.flags & PN_IO_WEIGHTS_READY and mode == 3) else 0)
         f = self._field_struct(embeddings)
         check(lib.pn_render_deformed_ex(C.byref(f), C.byref(d), dptr(rays_o), dptr(rays_d), N, dptr(out["image"]), dptr(out["depth"]),
                                         dptr(out["depth_0"]), dptr(out["weights_sum"]), dptr(workspace), workspace.numel(), dptr(stats),

@@ -72,7 +72,7 @@ class FramePipeline:
     frame(pose, intrinsics) enqueues one GUI frame and returns its slot; wait_host(slot) returns the pinned host frame once
     it has landed; drain() joins every stream into the current one.  The simulator steps once per frame unless paused."""
 
-    def __init__(self, model, sim, opt, slots=3, tile=16, weights=None, timeout_ms=20000, table_copies=True, mode=3, sim_sm_reserve=None):
+    def __init__(self, model, sim, opt, slots=3, tile=16, weights=None, timeout_ms=20000, table_copies=True, mode=3, sim_sm_reserve=None, lean_passes=True):
         import torch.distributed as dist
         from .dist import tile_partition
         self.model, self.sim, self.opt = model, sim, opt
@@ -170,6 +170,8 @@ class FramePipeline:
         self.sim_stream = torch.cuda.Stream(device=dev, priority=-1) if self.rank == 0 else None
         self.copy_stream = torch.cuda.Stream(device=dev) if self.rank == 0 else None
         self.frame_id = 0
+        self.max_passes = None
+        self.lean_passes = lean_passes
         self.launches_per_frame = 0
         self._warm = False
 
@@ -186,7 +188,7 @@ class FramePipeline:
         io.status, io.timeout_ms = dptr(self.status), self.timeout_ms
         return io
 
-    def _frame_body(self, sl, sync=True):
+    def _frame_body(self, sl, sync=True, lean=False):
         """rays of this rank's tiles + the deformed render into rank 0's frame slot (+ on rank 0: wait for the peers' pixels)."""
         m = self.model
         check(lib.pn_get_rays_pix(dptr(sl["cam"]), self.H, self.W, dptr(self.pix) if self.pix is not None else vp(0), self.n_my,
@@ -199,8 +201,11 @@ class FramePipeline:
         io = self._io(sl) if sync else None
         if io is None and self.pix is not None:
             io = FrameIoT(); io.pix = dptr(self.pix)
+        # lean (the captured graphs): the weight image of the slot's workspace was built by the warm-up call, and only as many passes
+        # as the warm-up frames needed (+1, the last one unbounded) are enqueued
         m.render_deformed(sl["rays_o"], sl["rays_d"], out=out, workspace=sl["workspace"], stats=sl["stats"], io=io, embeddings=sl["table"],
-                          ip_state=(sl["pos"], self.p_ori, sl["F"], sl["dF"]), mode=self.mode, **self.opt)
+                          ip_state=(sl["pos"], self.p_ori, sl["F"], sl["dF"]), mode=self.mode, max_passes=self.max_passes if lean else None,
+                          weights_ready=lean, **self.opt)
         n = 1 + m._render_launches
         if sync and self.rank == 0 and self.world > 1:                          # the frame is complete when every peer's pixels are in
             check(lib.pn_epoch_wait(dptr(sl["epoch"]), 0, dptr(sl["done_local"]), self.world - 1, 0, dptr(self.status), self.timeout_ms, stream_ptr()))
@@ -246,10 +251,18 @@ class FramePipeline:
             self.sim.stepforward(); self.sim.stepforward()                      # plain call + graph capture inside the simulator
             self.sim.dof.copy_(dof); self.sim.dof_vel.copy_(vel)
         torch.cuda.synchronize()
+        # passes the warm-up frames actually used (stats[7]), agreed over the ranks; one spare, and the last pass is unbounded anyway
+        used = max(int(sl["stats"][7].item()) for sl in self.slots)
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([used], dtype=torch.int64, device=self.dev if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            used = int(t.item())
+        self.max_passes = None if self.lean_passes is False else min(used + 1, int(lib.pn_render_pass_count(int(self.opt.max_steps))))
         self._barrier()
         n_frame = n_state = 0
         for sl in self.slots:
-            sl["graph"], n_frame = self._capture(lambda sl=sl: self._frame_body(sl), sl["stream"])
+            sl["graph"], n_frame = self._capture(lambda sl=sl: self._frame_body(sl, lean=True), sl["stream"])
             if self.rank == 0:
                 sl["state_graph"], n_state = self._capture(lambda sl=sl: self._state_body(sl), self.sim_stream)
         self.launches_per_frame = n_frame + n_state + (self.sim.step_launches if self.rank == 0 else 0)

@@ -21,8 +21,9 @@ for i in range(4):
     torch.cuda.synchronize()
     d = (a.dof - c.dof).abs().max().item(); dv = (a.dof_vel - c.dof_vel).abs().max().item()
     print(f"step {i}: max|ddof| {d:.3e} (scale {a.dof.abs().max().item():.2f}) max|dvel| {dv:.3e} (scale {a.dof_vel.abs().max().item():.3e})")
-prof = c._scratch[-8:].view(torch.int64).tolist()
-names = ["init+momentum", "F (8 lanes/IP)", "SVD+stress", "cluster barriers", "rhs partial", "final+matvec", "dof reload", "velocity"]
+tail = 16 * 30 * c.n_k
+prof = c._scratch[-8 - tail:-tail].view(torch.int64).tolist()
+names = ["init+CSR+momentum", "F (8 lanes/IP)", "SVD+stress", "cluster barriers", "rhs gather", "final+matvec", "dof reload", "-"]
 tot = sum(prof)
 for n, v in zip(names, prof):
     print(f"  {n:18s} {v:10d} cycles  {100.0 * v / tot:5.1f} %")
