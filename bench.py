@@ -322,11 +322,49 @@ def run_ours(args):
         "clocks": clocks, "wall_fps": K / wall, "host_enqueue_ms_per_frame": 1e3 * enqueue_s[0] / max(enqueue_n[0], 1),
     }
     line.update(extra)
+    if world == 1 and not args.quick and args.config == "chair":
+        pipe.close()
+        line["other_configs"] = other_configs(args, dev)
     if world == 1 and not args.no_cpu_baseline and not args.quick:
         line["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_budget)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(args, dev, frames=12):
+    """Short pipelined runs (N = 1) of the other BASELINE.json configs and of the variants the headline hides, so that the driver's
+    record carries them: the opaque field (density_scale 50: early termination, what a trained model looks like), the chair-like
+    body (100-250 kernels: the realistic global solve), trex (configs[2]) and the 1080p / 4k-IP frame (configs[3])."""
+    import gc
+
+    import torch
+    from pienerf_b200.frame import build_scene
+    from pienerf_b200.pipeline import FramePipeline
+    out = {}
+    for name, config, ds in (("chair_opaque", "chair", 50.0), ("chairlike", "chairlike", 1.0), ("trex", "trex", 1.0), ("synth1080", "synth1080", 1.0)):
+        model, sim, opt, pose, intr, body, field = build_scene(config, device=dev, density_scale=ds)
+        pipe = FramePipeline(model, sim, opt, slots=args.slots)
+        pipe.build(pose, intr)
+        for _ in range(4):
+            pipe.frame(pose, intr, to_host=True)
+        pipe.drain(); torch.cuda.synchronize()
+        res = {}
+        for key, to_host in (("value", False), ("e2e", True)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(frames):
+                pipe.frame(pose, intr, to_host=to_host)
+            pipe.drain(); e1.record(); torch.cuda.synchronize()
+            res[key] = frames / (e0.elapsed_time(e1) * 1e-3)
+        st = pipe.check()[0]
+        out[name] = {"frames_per_s": res["value"], "e2e_frames_per_s": res["e2e"], "config": f"{config}: {opt.W}x{opt.H}, {sim.n_ip} IPs, {sim.n_k} kernels, "
+                     f"density_scale {ds}, num_seek_IP {opt.num_seek_IP}", "kept_samples_per_frame": st[0], "field_evaluations_per_frame": st[2],
+                     "sim_launches_per_step": sim.step_launches, "passes": pipe.max_passes, "frames_timed": frames}
+        pipe.close()
+        del pipe, model, sim
+        gc.collect(); torch.cuda.empty_cache()
+    return out
 
 
 def ncu_traffic(config, world):

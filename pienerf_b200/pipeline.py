@@ -57,6 +57,48 @@ class PeerBlock:
         check(lib.pn_peer_open(handle, C.byref(p)))
         return int(p.value)
 
+    def free(self):
+        if self.ptr:
+            self.bytes = None
+            check(lib.pn_peer_free(vp(self.ptr)))
+            self.ptr = 0
+
+
+def green_streams(device_index, sim_sms, n_render_streams):
+    """SM partition of one GPU with CUDA green contexts (driver API, CUDA >= 12.4): `sim_sms` SMs for the simulator's stream, the
+    rest for the render streams.  Kernels launched into a green context's stream only run on its SMs, so the simulator's many small
+    launches never wait for (or share issue slots with) persistent render CTAs.  Returns (sim_stream, [render streams], n_render_sms)
+    as torch ExternalStreams, or None when the driver / bindings do not offer it."""
+    try:
+        from cuda.bindings import driver as drv
+    except Exception:
+        return None
+
+    def ok(ret):
+        if int(ret[0]) != 0:
+            raise RuntimeError(f"driver call failed: {ret[0]}")
+        return ret[1] if len(ret) == 2 else ret[1:]
+    try:
+        torch.zeros(1, device=f"cuda:{device_index}")                          # primary context exists and is current
+        dev = ok(drv.cuDeviceGet(device_index))
+        res = ok(drv.cuDeviceGetDevResource(dev, drv.CUdevResourceType.CU_DEV_RESOURCE_TYPE_SM))
+        groups, nb, remaining = ok(drv.cuDevSmResourceSplitByCount(1, res, 0, int(sim_sms)))
+        d_sim = ok(drv.cuDevResourceGenerateDesc([groups[0]], 1))
+        d_ren = ok(drv.cuDevResourceGenerateDesc([remaining], 1))
+        flags = drv.CUgreenCtxCreate_flags.CU_GREEN_CTX_DEFAULT_STREAM
+        g_sim = ok(drv.cuGreenCtxCreate(d_sim, dev, flags)); g_ren = ok(drv.cuGreenCtxCreate(d_ren, dev, flags))
+        nb_flag = int(drv.CUstream_flags.CU_STREAM_NON_BLOCKING)
+        s_sim = ok(drv.cuGreenCtxStreamCreate(g_sim, nb_flag, -1))
+        s_ren = [ok(drv.cuGreenCtxStreamCreate(g_ren, nb_flag, 0)) for _ in range(n_render_streams)]
+        n_sim = int(groups[0].sm.smCount); n_ren = int(remaining.sm.smCount)
+        keep = (g_sim, g_ren, s_sim, s_ren)                                     # contexts / streams live as long as the pipeline
+        wrap = lambda h: torch.cuda.ExternalStream(int(h), device=torch.device("cuda", device_index))
+        return wrap(s_sim), [wrap(h) for h in s_ren], n_sim, n_ren, keep
+    except Exception as e:                                                      # noqa: BLE001 - any failure means "not available here"
+        import warnings
+        warnings.warn(f"green contexts unavailable ({e}); falling back to stream priorities")
+        return None
+
 
 def _ptr_array(ptrs, device):
     return torch.tensor([int(p) for p in ptrs], dtype=torch.int64, device=device)
@@ -72,7 +114,7 @@ class FramePipeline:
     frame(pose, intrinsics) enqueues one GUI frame and returns its slot; wait_host(slot) returns the pinned host frame once
     it has landed; drain() joins every stream into the current one.  The simulator steps once per frame unless paused."""
 
-    def __init__(self, model, sim, opt, slots=3, tile=16, weights=None, timeout_ms=20000, table_copies=True, mode=3, sim_sm_reserve=None, lean_passes=True):
+    def __init__(self, model, sim, opt, slots=3, tile=16, weights=None, timeout_ms=20000, table_copies=True, mode=3, sim_sm_reserve=None, lean_passes=True, green=None):
         import torch.distributed as dist
         from .dist import tile_partition
         self.model, self.sim, self.opt = model, sim, opt
@@ -87,6 +129,16 @@ class FramePipeline:
         if sim_sm_reserve is None:
             sim_sm_reserve = 16 if (self.world > 1 and self.rank == 0) else 0
         self.sim_sm_reserve = int(sim_sm_reserve) if self.rank == 0 else 0
+        # hard partition instead of a soft reserve: green contexts (default on the simulating rank of a multi-GPU run)
+        self.green = None
+        if green is None:
+            green = self.world > 1 and self.rank == 0 and self.sim_sm_reserve > 0
+        if green and self.rank == 0 and self.sim_sm_reserve > 0:
+            self.green = green_streams(self.dev.index or 0, self.sim_sm_reserve, int(slots))
+            if self.green is not None:
+                n_all = C.c_int(0)
+                check(lib.pn_device_sm_count(C.byref(n_all)))
+                self.sim_sm_reserve = int(n_all.value) - self.green[3]          # what the partition really took (granularity of 8)
         check(lib.pn_set_render_sm_reserve(self.sim_sm_reserve))
         self.n_ip = n_ip = int(sim.n_ip) if sim is not None else int(model.p_ori.shape[0])
         npx = self.W * self.H
@@ -143,7 +195,7 @@ class FramePipeline:
             sl["table"] = model.encoder.embeddings.data if (s == 0 or not table_copies) else model.encoder.embeddings.data.clone()
             sl["epoch"] = torch.zeros(1, dtype=torch.int32, device=dev)        # bumped by the slot's frame graph
             sl["state_epoch"] = torch.zeros(1, dtype=torch.int32, device=dev)  # rank 0: bumped by the slot's state graph
-            sl["stream"] = torch.cuda.Stream(device=dev)
+            sl["stream"] = self.green[1][s] if self.green is not None else torch.cuda.Stream(device=dev)
             sl["render_done"] = None
             sl["state_ready"] = None
             sl["copy_done"] = None
@@ -167,7 +219,7 @@ class FramePipeline:
             sl["state_graph"] = None
             self.slots.append(sl)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.sim_stream = torch.cuda.Stream(device=dev, priority=-1) if self.rank == 0 else None
+        self.sim_stream = (self.green[0] if self.green is not None else torch.cuda.Stream(device=dev, priority=-1)) if self.rank == 0 else None
         self.copy_stream = torch.cuda.Stream(device=dev) if self.rank == 0 else None
         self.frame_id = 0
         self.max_passes = None
@@ -247,6 +299,7 @@ class FramePipeline:
                 sl["pos"].copy_(self.p_ori); sl["F"].zero_(); sl["F"][:, 0] = 1; sl["F"][:, 4] = 1; sl["F"][:, 8] = 1; sl["dF"].zero_()
             self._frame_body(sl, sync=False)
         if self.rank == 0 and self.sim is not None:
+            self.sim.capture_stream = self.sim_stream                           # the step's graph nodes belong to the simulator's stream (priority / SM partition)
             dof, vel = self.sim.dof.clone(), self.sim.dof_vel.clone()
             self.sim.stepforward(); self.sim.stepforward()                      # plain call + graph capture inside the simulator
             self.sim.dof.copy_(dof); self.sim.dof_vel.copy_(vel)
@@ -341,6 +394,19 @@ class FramePipeline:
         if sl["copy_done"] is not None:
             sl["copy_done"].synchronize()
         return sl["host"]
+
+    def close(self):
+        """Release the graphs, workspaces and the peer block (after a synchronize; peers must have closed their mappings' users)."""
+        torch.cuda.synchronize()
+        for sl in self.slots:
+            sl.clear()
+        self.slots = []
+        for r, p in enumerate(self.peer_ptr):
+            if r != self.rank and p:
+                lib.pn_peer_close(vp(p))
+        self.peer_ptr = []
+        self.block.free()
+        lib.pn_set_render_sm_reserve(0)
 
     def check(self):
         """After a synchronize: raise if a flag wait timed out or a frame reported an error."""

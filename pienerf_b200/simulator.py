@@ -232,7 +232,7 @@ class Simulator:
             cur = torch.cuda.current_stream()
             # captured on a HIGH-priority stream: graph kernel nodes keep the priority of the stream they were captured on, and on the
             # GPU that also renders the step's small kernels must get the first CTA slot that frees up (pipeline.py)
-            side = torch.cuda.Stream(device=self.dof.device, priority=-1)
+            side = getattr(self, "capture_stream", None) or torch.cuda.Stream(device=self.dof.device, priority=-1)
             side.wait_stream(cur)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
