@@ -130,8 +130,11 @@ def run_ours(args):
     W, H = opt.W, opt.H
     N = W * H
     weights = None
-    if world > 1 and args.rank0_share is not None:                            # rank 0 also runs the simulator: optional smaller tile share
-        f0 = args.rank0_share / world
+    share = args.rank0_share
+    if world > 1 and share is None:                                           # rank 0 also runs the simulator: measured smaller tile share
+        share = FramePipeline.calibrate_rank0_share(model, sim, opt, pose, intr, slots=args.slots, sim_sm_reserve=args.sim_sm_reserve)
+    if world > 1 and share < 0.999:
+        f0 = share / world
         weights = [f0] + [(1.0 - f0) / (world - 1)] * (world - 1)
     pipe = FramePipeline(model, sim, opt, slots=args.slots, weights=weights, sim_sm_reserve=args.sim_sm_reserve)
     pipe.build(pose, intr)
@@ -304,7 +307,7 @@ def run_ours(args):
                     "parallelism": f"16x16 ray tiles over {world} GPU(s), simulator on rank 0; {pipe.S} frames in flight per GPU (one CUDA graph per rank-frame); "
                                    + ("IP state pushed and pixels returned by peer-memory stores over NVLink (no collective in the frame loop)" if world > 1 else "single GPU")
                                    + (f"; tile shares {[round(x, 4) for x in weights]}" if weights else "")
-                                   + (f"; rank 0 keeps {pipe.sim_sm_reserve} SMs out of its render grids for the simulator" if pipe.sim_sm_reserve else ""),
+                                   + (f"; persistent render grids sized for {pipe.sim_sm_reserve} SMs fewer than the GPU has (room for the small kernels of the frames in flight)" if pipe.sim_sm_reserve else ""),
                     "l2": f"no flush in the timed loop: inputs larger than L2 — {pipe.S} frame slots rotate, each with its own 46.7 MiB copy of the hash table, "
                           "its own sample lists and rays (per-frame traffic on rank 0 ~ %.0f MB); stand-alone kernel timings flush with a 256 MiB fill" % (rows * 40 / 1e6 + 46.7)},
         "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 80, "d2h_bytes_per_step": N * 5 * 4,
@@ -542,8 +545,8 @@ def main():
     ap.add_argument("--density-scale", type=float, default=1.0, dest="density_scale")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=3, help="frames in flight per GPU (each with its own workspace and hash-table copy)")
-    ap.add_argument("--rank0-share", type=float, default=None, dest="rank0_share", help="N>1: rank 0's tile share relative to an equal split (e.g. 0.8)")
-    ap.add_argument("--sim-sm-reserve", type=int, default=None, dest="sim_sm_reserve", help="SMs rank 0 keeps out of its render grids for the simulator (default 16 when N>1, else 0)")
+    ap.add_argument("--rank0-share", type=float, default=None, dest="rank0_share", help="N>1: rank 0's tile share relative to an equal split (default: measured, FramePipeline.calibrate_rank0_share)")
+    ap.add_argument("--sim-sm-reserve", type=int, default=None, dest="sim_sm_reserve", help="SMs every rank keeps out of its persistent render grids for the small kernels of the frames in flight (default 8 for N<=2, else 16)")
     ap.add_argument("--quick", action="store_true", help="skip the stand-alone kernel microbenches and the CPU baseline (development runs)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--cpu-stride", type=int, default=16)

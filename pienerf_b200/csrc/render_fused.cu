@@ -694,9 +694,9 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
         for (int p = 0; p < n_pass; p++, cap_p *= 2) {
             const int cap_now = (limited && p == n_pass - 1) ? (int)d->max_steps : cap_p;
             switch (d->num_seek_IP) {
-                case 1: wave_march_kernel<1><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_now); break;
-                case 2: wave_march_kernel<2><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_now); break;
-                default: wave_march_kernel<3><<<sms * PN_MARCH_MINB, 256, 0, st>>>(A, P, Wv, p, cap_now); break;
+                case 1: wave_march_kernel<1><<<sms * PN_MARCH_MINB, PN_MARCH_THREADS, 0, st>>>(A, P, Wv, p, cap_now); break;
+                case 2: wave_march_kernel<2><<<sms * PN_MARCH_MINB, PN_MARCH_THREADS, 0, st>>>(A, P, Wv, p, cap_now); break;
+                default: wave_march_kernel<3><<<sms * PN_MARCH_MINB, PN_MARCH_THREADS, 0, st>>>(A, P, Wv, p, cap_now); break;
             }
             if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk], st));
             wave_field_ws_kernel<<<sms, (kWsProd + kWsCons) * 128, smem, st>>>(A, Wv, p);

@@ -50,8 +50,11 @@ struct WaveArgs {
 #ifndef PN_MARCH_MINB
 #define PN_MARCH_MINB 4   // 32 warps / SM at 64 registers (some spills) beat 24 at 80 and 16 at 128: the list scan is latency-bound
 #endif
+#ifndef PN_MARCH_THREADS
+#define PN_MARCH_THREADS 256   // A/B: 1024 with PN_MARCH_MINB 1 = one CTA per SM, so a grid of (SMs - reserve) CTAs leaves whole SMs free
+#endif
 template <int KMAX>
-__global__ void __launch_bounds__(256, PN_MARCH_MINB) wave_march_kernel(const RenderArgs A, const IpPack P, const WaveArgs Wv, int pass, int pass_cap) {
+__global__ void __launch_bounds__(PN_MARCH_THREADS, PN_MARCH_MINB) wave_march_kernel(const RenderArgs A, const IpPack P, const WaveArgs Wv, int pass, int pass_cap) {
     pn::BendCfg bc = A.bend;
 #pragma unroll
     for (int i = 0; i < 3; i++) { bc.bbmin[i] = A.geom->bbmin[i]; bc.bbmax[i] = A.geom->bbmax[i]; bc.hi[i] = A.geom->hi[i]; bc.res[i] = A.geom->res[i]; }

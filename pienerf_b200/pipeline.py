@@ -123,16 +123,16 @@ class FramePipeline:
         self.dev = next(model.parameters()).device
         self.S, self.W, self.H, self.mode = int(slots), int(opt.W), int(opt.H), mode
         self.timeout_ms = int(timeout_ms)
-        # the GPU that also simulates keeps a few SMs' worth of CTA slots out of the persistent render grids, so that the
-        # simulator's launches (high-priority stream) never queue behind a whole render kernel (multi-GPU runs only by default:
-        # on one GPU the 0.2 ms step hides inside the 2.4 ms frame anyway)
+        # Every rank sizes its persistent march / field grids for (SMs - reserve) SMs: the small latency-bound kernels of the frames in
+        # flight (IP-grid preparation, compositor, the simulator's launches on rank 0) then always find a free SM instead of queueing
+        # behind CTAs that hold every SM until their kernel ends.  Measured on B200 (profiles/r2_reserve.md): 8 SMs are best for a
+        # whole 800x800 frame on one GPU (2.36 -> 2.23 ms with the simulator), 16 when a rank renders 1/8 of it (0.414 -> 0.381 ms).
         if sim_sm_reserve is None:
-            sim_sm_reserve = 16 if (self.world > 1 and self.rank == 0) else 0
-        self.sim_sm_reserve = int(sim_sm_reserve) if self.rank == 0 else 0
-        # hard partition instead of a soft reserve: green contexts (default on the simulating rank of a multi-GPU run)
+            sim_sm_reserve = 8 if self.world <= 2 else 16
+        self.sim_sm_reserve = int(sim_sm_reserve)
+        # hard partition instead of a soft reserve (green contexts): measured slower — the simulator's kernels want the whole GPU for
+        # a short time, not 16 SMs for a long time (0.73 ms per step on 16 SMs, 0.57 on 24, 0.21 on all) — kept as an option
         self.green = None
-        if green is None:
-            green = self.world > 1 and self.rank == 0 and self.sim_sm_reserve > 0
         if green and self.rank == 0 and self.sim_sm_reserve > 0:
             self.green = green_streams(self.dev.index or 0, self.sim_sm_reserve, int(slots))
             if self.green is not None:
@@ -323,6 +323,44 @@ class FramePipeline:
         self._barrier()
         self._warm = True
 
+    @staticmethod
+    def calibrate_rank0_share(model, sim, opt, pose, intrinsics, slots=3, frames=12, **kw):
+        """Rank 0 also runs the simulator, whose kernels time-share its GPU with the render: give it a smaller tile share x (relative
+        to an equal split) such that  x * r + S = r * (N - x) / (N - 1),  r = render time of an equal share (measured: `frames`
+        paused frames through an equal-split pipeline, slowest rank), S = simulator step time (measured alone on rank 0).
+        Collective: every rank calls it; returns the same x on every rank."""
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        if world == 1:
+            return 1.0
+        pipe = FramePipeline(model, sim, opt, slots=slots, **kw)
+        pipe.build(pose, intrinsics)
+        for _ in range(4):
+            pipe.frame(pose, intrinsics, to_host=False, paused=True)
+        pipe.drain(); torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(frames):
+            pipe.frame(pose, intrinsics, to_host=False, paused=True)
+        pipe.drain(); e1.record(); torch.cuda.synchronize()
+        r = e0.elapsed_time(e1) / frames
+        S = 0.0
+        if pipe.rank == 0:
+            dof, vel = sim.dof.clone(), sim.dof_vel.clone()
+            e0.record()
+            for _ in range(20):
+                sim.stepforward()
+            e1.record(); torch.cuda.synchronize()
+            S = e0.elapsed_time(e1) / 20
+            sim.dof.copy_(dof); sim.dof_vel.copy_(vel)
+        t = torch.tensor([r, S], dtype=torch.float64, device=pipe.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        r, S = float(t[0]), float(t[1])
+        dist.barrier()
+        pipe.close()
+        x = 1.0 - S * (world - 1) / (world * r)
+        return float(min(1.0, max(0.25, x)))
+
     def _barrier(self):
         import torch.distributed as dist
         if self.world > 1:
@@ -405,6 +443,7 @@ class FramePipeline:
             if r != self.rank and p:
                 lib.pn_peer_close(vp(p))
         self.peer_ptr = []
+        self._barrier()                                                          # nobody frees a block another rank still has mapped
         self.block.free()
         lib.pn_set_render_sm_reserve(0)
 
