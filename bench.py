@@ -211,19 +211,26 @@ def run_ours(args):
         a.record(); b.record()
         for e in lst:
             e.record()
-    sync_all()
-    for i in range(reps):
-        flush.fill_(float(i))
-        a, b, lst = pv[i]
-        _lib.lib.pn_set_profile_events(_lib.vp(a.cuda_event), _lib.vp(b.cuda_event))
-        arr = (_lib.vp * len(lst))(*[e.cuda_event for e in lst])
-        _lib.lib.pn_set_profile_event_list(arr, len(lst))
-        pipe._frame_body(pipe.slots[i % pipe.S], sync=False)
-        _lib.lib.pn_set_profile_events(_lib.vp(0), _lib.vp(0)); _lib.lib.pn_set_profile_event_list(None, 0)
-    sync_all()
-    render_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in pv]))
-    field_ms = float(np.mean([sum(lst[2 * k].elapsed_time(lst[2 * k + 1]) for k in range(n_pass)) for _, _, lst in pv]))
-    field0_ms = float(np.mean([lst[0].elapsed_time(lst[1]) for _, _, lst in pv]))
+    def eager_profile():
+        sync_all()
+        for i in range(reps):
+            flush.fill_(float(i))
+            a, b, lst = pv[i]
+            _lib.lib.pn_set_profile_events(_lib.vp(a.cuda_event), _lib.vp(b.cuda_event))
+            arr = (_lib.vp * len(lst))(*[e.cuda_event for e in lst])
+            _lib.lib.pn_set_profile_event_list(arr, len(lst))
+            pipe._frame_body(pipe.slots[i % pipe.S], sync=False)
+            _lib.lib.pn_set_profile_events(_lib.vp(0), _lib.vp(0)); _lib.lib.pn_set_profile_event_list(None, 0)
+        sync_all()
+        return (float(np.mean([a.elapsed_time(b) for a, b, _ in pv])),
+                float(np.mean([sum(lst[2 * k].elapsed_time(lst[2 * k + 1]) for k in range(n_pass)) for _, _, lst in pv])),
+                float(np.mean([lst[0].elapsed_time(lst[1]) for _, _, lst in pv])))
+    render_ms, field_ms, field0_ms = eager_profile()                          # as in the timed loop: grids sized for (SMs - reserve)
+    field_ms_all = field_ms
+    if pipe.sim_sm_reserve:                                                   # and with every SM, for the kernel's own roofline
+        _lib.lib.pn_set_render_sm_reserve(0)
+        _, field_ms_all, _ = eager_profile()
+        _lib.lib.pn_set_render_sm_reserve(pipe.sim_sm_reserve)
 
     # ---- stand-alone kernel rooflines (hash microbench on EVERY rank = BASELINE.json configs[4]; MLP pass on rank 0)
     hbm, tf, src = measured_peaks()
@@ -321,7 +328,10 @@ def run_ours(args):
                      "peak_source": src, "kernel_ms_per_frame": field_ms, "launches_per_frame": n_pass, "first_pass_launch_ms": field0_ms,
                      "algorithmic_bytes": f"{ALGO_BYTES_PER_SAMPLE_FUSED} B/sample x {evaluated:.0f} field evaluations per frame on rank 0 (summed over the frame's launches; rows incl. slab padding: {rows:.0f})",
                      "measured": "eager un-pipelined frames, CUDA events around every field-kernel launch, L2 flushed before each frame",
-                     "share_of_eager_frame": field_ms / render_ms, "render_passes_ms_per_frame": render_ms},
+                     "share_of_eager_frame": field_ms / render_ms, "render_passes_ms_per_frame": render_ms,
+                     "sms_used": f"{148 - pipe.sim_sm_reserve} of 148 (the frame pipeline keeps {pipe.sim_sm_reserve} SMs free for the small kernels of the frames in flight)",
+                     "all_sms": {"kernel_ms_per_frame": field_ms_all, "achieved": evaluated * ALGO_BYTES_PER_SAMPLE_FUSED / (field_ms_all * 1e-3) / 1e9,
+                                 "frac": evaluated * ALGO_BYTES_PER_SAMPLE_FUSED / (field_ms_all * 1e-3) / 1e9 / hbm}},
         "clocks": clocks, "wall_fps": K / wall, "host_enqueue_ms_per_frame": 1e3 * enqueue_s[0] / max(enqueue_n[0], 1),
     }
     line.update(extra)

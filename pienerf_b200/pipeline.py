@@ -125,7 +125,7 @@ class FramePipeline:
         self.timeout_ms = int(timeout_ms)
         # Every rank sizes its persistent march / field grids for (SMs - reserve) SMs: the small latency-bound kernels of the frames in
         # flight (IP-grid preparation, compositor, the simulator's launches on rank 0) then always find a free SM instead of queueing
-        # behind CTAs that hold every SM until their kernel ends.  Measured on B200 (profiles/r2_reserve.md): 8 SMs are best for a
+        # behind CTAs that hold every SM until their kernel ends.  Measured on B200 (profiles/r2_measurements.md): 8 SMs are best for a
         # whole 800x800 frame on one GPU (2.36 -> 2.23 ms with the simulator), 16 when a rank renders 1/8 of it (0.414 -> 0.381 ms).
         if sim_sm_reserve is None:
             sim_sm_reserve = 8 if self.world <= 2 else 16
