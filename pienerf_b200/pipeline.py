@@ -100,6 +100,11 @@ def green_streams(device_index, sim_sms, n_render_streams):
         return None
 
 
+def dist_backend():
+    import torch.distributed as dist
+    return dist.get_backend() if dist.is_initialized() else None
+
+
 def _ptr_array(ptrs, device):
     return torch.tensor([int(p) for p in ptrs], dtype=torch.int64, device=device)
 
@@ -114,7 +119,7 @@ class FramePipeline:
     frame(pose, intrinsics) enqueues one GUI frame and returns its slot; wait_host(slot) returns the pinned host frame once
     it has landed; drain() joins every stream into the current one.  The simulator steps once per frame unless paused."""
 
-    def __init__(self, model, sim, opt, slots=3, tile=16, weights=None, timeout_ms=20000, table_copies=True, mode=3, sim_sm_reserve=None, lean_passes=True, green=None):
+    def __init__(self, model, sim, opt, slots=3, tile=16, weights=None, timeout_ms=20000, table_copies=True, mode=3, sim_sm_reserve=None, lean_passes=True, green=None, merge_passes=None):
         import torch.distributed as dist
         from .dist import tile_partition
         self.model, self.sim, self.opt = model, sim, opt
@@ -224,6 +229,7 @@ class FramePipeline:
         self.frame_id = 0
         self.max_passes = None
         self.lean_passes = lean_passes
+        self.merge_passes = merge_passes
         self.launches_per_frame = 0
         self._warm = False
 
@@ -312,6 +318,19 @@ class FramePipeline:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             used = int(t.item())
         self.max_passes = None if self.lean_passes is False else min(used + 1, int(lib.pn_render_pass_count(int(self.opt.max_steps))))
+        # Small ray shares (a rank of a 4- or 8-GPU frame): every pass costs a ramp-up and a drain of three kernels, so when the
+        # warm-up frames show no early termination to speak of (field evaluations ~ composited samples: nothing is wasted by marching
+        # a ray to its end) the second pass is the last one and takes everything the first 32 samples per ray left.
+        if self.max_passes is not None and self.merge_passes is not False:
+            st = [sl["stats"].tolist() for sl in self.slots]
+            waste = max(float(s[2]) / max(float(s[0]), 1.0) for s in st)
+            small = self.n_my <= (self.merge_passes if isinstance(self.merge_passes, int) and self.merge_passes > 1 else 200_000)
+            flag = torch.tensor([1 if (waste < 1.02 and small and used >= 2) else 0], dtype=torch.int64, device=self.dev if (self.world == 1 or dist_backend() == "nccl") else "cpu")
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()):
+                self.max_passes = 2
         self._barrier()
         n_frame = n_state = 0
         for sl in self.slots:

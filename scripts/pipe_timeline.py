@@ -18,6 +18,7 @@ slots = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 paused = len(sys.argv) > 4 and sys.argv[4] == "paused"
 reserve = int(sys.argv[5]) if len(sys.argv) > 5 else None
 green = len(sys.argv) > 6 and sys.argv[6] == "green"
+merge = False if (len(sys.argv) > 7 and sys.argv[7] == "nomerge") else None
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -27,7 +28,7 @@ from pienerf_b200.frame import build_scene
 from pienerf_b200.pipeline import FramePipeline
 
 model, sim, opt, pose, intr, body, field = build_scene(config, device=dev)
-pipe = FramePipeline(model, sim, opt, slots=slots, sim_sm_reserve=reserve, green=green)
+pipe = FramePipeline(model, sim, opt, slots=slots, sim_sm_reserve=reserve, green=green, merge_passes=merge)
 pipe.build(pose, intr)
 for _ in range(6):
     pipe.frame(pose, intr, to_host=False, paused=paused)
@@ -80,7 +81,7 @@ torch.cuda.profiler.stop()
 if world > 1:
     dist.barrier()
 total = t0.elapsed_time(t1)
-lines = [f"rank {rank}/{world} {config}: {K} frames in {total:.3f} ms = {total / K:.3f} ms/frame ({1e3 * K / total:.1f} fps), {slots} slots, paused={paused}, reserve={pipe.sim_sm_reserve}, green={pipe.green is not None}"]
+lines = [f"rank {rank}/{world} {config}: {K} frames in {total:.3f} ms = {total / K:.3f} ms/frame ({1e3 * K / total:.1f} fps), {slots} slots, paused={paused}, reserve={pipe.sim_sm_reserve}, green={pipe.green is not None}, passes={pipe.max_passes}"]
 for k, e in enumerate(rec):
     parts = [f"frame {k:2d} slot {e['slot']}"]
     for tag in ("state", "step", "frame"):
