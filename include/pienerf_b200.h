@@ -187,6 +187,9 @@ int pn_epoch_signal(const uint32_t *epoch, uint32_t *const *flags_dev, int n_fla
 /* Rows of the per-pass sample list of mode 3 (0 = automatic: 24 per ray, 1 Mi .. 32 Mi).  Call before sizing the workspace with
  * pn_render_workspace_bytes.  A full list defers the remaining rays to the next pass (stats[6]); tests use a small list. */
 int pn_set_wave_capacity(int rows);
+/* Per-frame IP preparation of pn_render_deformed: 0 (default) = one single-CTA kernel when the IP-grid capacity is <= 64 Ki cells
+ * (every configuration without --cut), 1 = always the multi-kernel chain (bbox, counting sort, pack, neighbourhood lists). */
+int pn_set_prep_mode(int force_multi_kernel);
 /* Size the persistent march / field grids of mode 3 for (SM count - n_sm) SMs, leaving n_sm SMs' worth of CTA slots to kernels of
  * other streams (the simulator's launches on the GPU that also renders).  0 = use every SM (default).  Process-wide; a CUDA
  * graph captured afterwards keeps the grid sizes it was captured with. */

@@ -451,6 +451,163 @@ int set_smem(K kernel, size_t bytes) {
 
 #include "render_wave.cuh"
 
+namespace {
+
+// block-wide exclusive scan of v[0..n) into out[0..n) (+ total in out[n] when `with_total`), 1024 threads, any n
+__device__ void block_scan_exclusive(const int *v, int n, int *out, int *zero_fill, bool with_total) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int x = i < n ? v[i] : 0;
+        int incl = x;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warp_tot[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += t; }
+            warp_tot[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int before = carry + ((threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0) + incl - x;
+        if (i < n) { out[i] = before; if (zero_fill) zero_fill[i] = 0; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + x;
+        __syncthreads();
+    }
+    if (with_total && threadIdx.x == 0) out[n] = carry;
+    __syncthreads();
+}
+
+// The whole per-frame IP preparation of the wavefront renderer as ONE single-CTA kernel: bbox + resolution (renderer.py:782-791),
+// the deterministic counting sort of get_pnts_in_grids (nerf/utils.py:355-443), the cell-sorted IP records and the per-cell
+// neighbourhood lists — ten dependent launches of a few microseconds each otherwise, which every rank of a multi-GPU frame repeats.
+// Same arithmetic and the same results as the stand-alone kernels (ip_bbox / ip_grid_* / ip_pack / nb_*), phases separated by
+// __syncthreads; the work is tiny (a few thousand IPs, ~10^3..10^4 grid cells), so one SM is enough and 147 stay with the renderer.
+__global__ void __launch_bounds__(1024) ip_prep_fused_kernel(const float *__restrict__ p_def, const float *__restrict__ p_ori, const float *__restrict__ F,
+                                                             int n, float hgs, int cut, float bound, int res_max, int n_grid_cap, int zyx_order,
+                                                             FrameGeom *__restrict__ g, int *cnt, int *bgn, int *fill, int *idx, float4 *ip_pos,
+                                                             float *ip_rec, int *nb_cnt, int *nb_start, float4 *nb_list) {
+    __shared__ float smin[3][32], smax[3][32];
+    __shared__ int s_over[3], s_res[3];
+    __shared__ float s_bbmin[3];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // ---- bbox (ip_bbox_kernel)
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = tid; i < n; i += nt) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { const float v = p_def[3 * i + c]; lo[c] = fminf(lo[c], v); hi[c] = fmaxf(hi[c], v); }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if ((tid & 31) == 0) { smin[c][tid >> 5] = lo[c]; smax[c][tid >> 5] = hi[c]; }
+    }
+    __syncthreads();
+    if (tid < 3) {
+        const int c = tid;
+        float a = FLT_MAX, b = -FLT_MAX;
+        for (int w = 0; w < (nt >> 5); w++) { a = fminf(a, smin[c][w]); b = fmaxf(b, smax[c][w]); }
+        if (cut) { a = -bound; b = bound; }
+        const float mn = a - 1e-3f, mx = b + 1e-3f;
+        const float rf = ceilf((mx - mn) * (1.0f / hgs));
+        int r = (int)rf;
+        s_over[c] = 0;
+        if (!(rf >= 1.0f && rf <= (float)res_max)) { r = rf >= 1.0f ? res_max : 1; s_over[c] = 1; }
+        g->bbmin[c] = mn; g->bbmax[c] = mx; g->hi[c] = (float)((double)mx - 1e-6); g->res[c] = r;
+        s_res[c] = r; s_bbmin[c] = mn;
+    }
+    __syncthreads();
+    const int r0 = s_res[0], r1 = s_res[1], r2 = s_res[2];
+    const int n_grid = min(r0 * r1 * r2, n_grid_cap);
+    if (tid == 0) { g->n_grid = r0 * r1 * r2; g->overflow = s_over[0] | s_over[1] | s_over[2]; }
+    // ---- counting sort of the IPs into the hgs grid (ip_grid_count / scan / fill / sort)
+    for (int c = tid; c < n_grid; c += nt) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const int gid = ip_cell(p_def, i, s_bbmin, hgs, s_res);
+        if (gid >= 0 && gid < n_grid_cap) atomicAdd(cnt + gid, 1);
+    }
+    __syncthreads();
+    block_scan_exclusive(cnt, n_grid, bgn, fill, false);
+    for (int i = tid; i < n; i += nt) {
+        const int gid = ip_cell(p_def, i, s_bbmin, hgs, s_res);
+        if (gid >= 0 && gid < n_grid_cap) idx[bgn[gid] + atomicAdd(fill + gid, 1)] = i;
+    }
+    __syncthreads();
+    for (int c = tid; c < n_grid; c += nt) {                  // ascending IP index inside a cell (deterministic)
+        const int m = cnt[c];
+        int *a = idx + bgn[c];
+        for (int i = 1; i < m; i++) {
+            const int v = a[i];
+            int j = i - 1;
+            while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; }
+            a[j + 1] = v;
+        }
+    }
+    __syncthreads();
+    // ---- cell-sorted IP records with F^-1 (ip_pack_kernel)
+    if (tid == 0) bgn[n_grid] = n;
+    for (int k = tid; k < n; k += nt) {
+        const int ip = idx[k];
+        const float px = p_def[3 * ip], py = p_def[3 * ip + 1], pz = p_def[3 * ip + 2];
+        ip_pos[k] = make_float4(px, py, pz, __int_as_float(ip));
+        float A[9], Ai[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) A[i] = F[9 * ip + i] + 0.0f;
+        pn::adjugate_inverse(A, Ai);
+        float *r = ip_rec + 16 * (size_t)k;
+        r[0] = p_ori[3 * ip]; r[1] = p_ori[3 * ip + 1]; r[2] = p_ori[3 * ip + 2];
+        r[3] = px; r[4] = py; r[5] = pz;
+#pragma unroll
+        for (int i = 0; i < 9; i++) r[6 + i] = Ai[i];
+        r[15] = 0.f;
+    }
+    // ---- per-cell neighbourhood lists (nb_count_kernel / scan / nb_fill_kernel)
+    for (int c = tid; c < n_grid; c += nt) {
+        const int g0 = c % r0, g1 = (c / r0) % r1, g2 = c / (r0 * r1);
+        int m = 0;
+        for (int dz = -1; dz <= 1; dz++)
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int a0 = g0 + dx, a1 = g1 + dy, a2 = g2 + dz;
+                    if (a0 >= 0 && a0 < r0 && a1 >= 0 && a1 < r1 && a2 >= 0 && a2 < r2) m += cnt[(a2 * r1 + a1) * r0 + a0];
+                }
+        nb_cnt[c] = m;
+    }
+    __syncthreads();
+    block_scan_exclusive(nb_cnt, n_grid, nb_start, nullptr, true);
+    for (int c = tid; c < n_grid; c += nt) {
+        const int g0 = c % r0, g1 = (c / r0) % r1, g2 = c / (r0 * r1);
+        int o = nb_start[c];
+        if (nb_start[c + 1] == o) continue;
+        for (int q = -1; q < 26; q++) {
+            int d0 = 0, d1 = 0, d2 = 0;
+            if (q >= 0) {
+                if (zyx_order) { d2 = pn::kNeigh[q][0]; d1 = pn::kNeigh[q][1]; d0 = pn::kNeigh[q][2]; }
+                else { d0 = pn::kNeigh[q][0]; d1 = pn::kNeigh[q][1]; d2 = pn::kNeigh[q][2]; }
+            }
+            const int a0 = g0 + d0, a1 = g1 + d1, a2 = g2 + d2;
+            if (a0 < 0 || a0 >= r0 || a1 < 0 || a1 >= r1 || a2 < 0 || a2 >= r2) continue;
+            const int gid = (a2 * r1 + a1) * r0 + a0;
+            for (int k = bgn[gid]; k < bgn[gid + 1]; k++) {
+                const float4 p = ip_pos[k];
+                nb_list[o++] = make_float4(p.x, p.y, p.z, __int_as_float(k));
+            }
+        }
+    }
+}
+
+constexpr int kFusedPrepMaxCells = 64 * 1024;   // beyond this (trex with --cut: 67^3 cells) the multi-kernel path has the parallelism
+
+}  // namespace
+
 int pn_field_forward_tc(const pn_field_t *f, const float *xyzs, const float *dirs, uint32_t M, float *sigmas, float *rgbs,
                         cudaStream_t st);
 
@@ -527,6 +684,8 @@ extern "C" int pn_set_wave_capacity(int rows) {
     g_wave_cap_override = rows;
     return PN_OK;
 }
+static int g_prep_force_multi = 0;   // tests: compare the fused preparation kernel with the multi-kernel chain
+extern "C" int pn_set_prep_mode(int force_multi_kernel) { g_prep_force_multi = force_multi_kernel; return PN_OK; }
 static int g_sm_reserve = 0;
 extern "C" int pn_set_render_sm_reserve(int n_sm) {
     PN_REQUIRE(n_sm >= 0 && n_sm < pn_sm_count_cached(), "reserve must leave SMs for the renderer");
@@ -634,8 +793,17 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
     if (io && io->epoch)
         if (int rc = pn_flag_wait_launch(io, st)) return rc;       // bump the slot's epoch; wait e.g. for this frame's IP state to land in this GPU's memory
     PN_CUDA(cudaMemsetAsync(queue, 0, sizeof(FrameQueue), st));
-    ip_bbox_kernel<<<1, 1024, 0, st>>>(d->p_def, d->n_vtx, d->hgs, d->cut, d->bound, res_max_for(d->bound, d->hgs), geom, nullptr, nullptr, nullptr);
-    if (int rc = build_ip_grid_impl(d->p_def, d->n_vtx, geom->bbmin, d->hgs, geom->res, max_cells, cnt, bgn, fill, idx, st)) return rc;
+    // IP preparation: one single-CTA kernel when the grid is small (every config without --cut), else the parallel multi-kernel chain
+    const bool fused_prep = mode != 2 && max_cells <= kFusedPrepMaxCells && !g_prep_force_multi;
+    if (fused_prep) {
+        ip_prep_fused_kernel<<<1, 1024, 0, st>>>(d->p_def, d->p_ori, d->F_IP, d->n_vtx, d->hgs, d->cut, d->bound, res_max_for(d->bound, d->hgs), max_cells,
+                                                 d->num_seek_IP == 1, geom, cnt, bgn, fill, idx, (float4 *)(base + w.ip_pos), (float *)(base + w.ip_rec),
+                                                 (int *)(base + w.nb_cnt), (int *)(base + w.nb_start), (float4 *)(base + w.nb_list));
+        PN_LAUNCH_CHECK("ip_prep_fused_kernel");
+    } else {
+        ip_bbox_kernel<<<1, 1024, 0, st>>>(d->p_def, d->n_vtx, d->hgs, d->cut, d->bound, res_max_for(d->bound, d->hgs), geom, nullptr, nullptr, nullptr);
+        if (int rc = build_ip_grid_impl(d->p_def, d->n_vtx, geom->bbmin, d->hgs, geom->res, max_cells, cnt, bgn, fill, idx, st)) return rc;
+    }
     frame_setup_kernel<<<div_up(N, 256u), 256, 0, st>>>(rays_o, rays_d, N, geom, d->min_near, d->bg_color, nears, fars,
                                                          active, queue, io ? io->pix : nullptr, image, depth, depth_0, weights_sum);
     PN_LAUNCH_CHECK("frame_setup_kernel");
@@ -659,13 +827,15 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
     if (mode == 3) {
         float4 *ip_pos = (float4 *)(base + w.ip_pos);
         float *ip_rec = (float *)(base + w.ip_rec);
-        ip_pack_kernel<<<div_up(d->n_vtx, 256), 256, 0, st>>>(d->p_def, d->p_ori, d->F_IP, idx, d->n_vtx, geom->res, max_cells, bgn, ip_pos, ip_rec);
         int *nb_cnt = (int *)(base + w.nb_cnt), *nb_start = (int *)(base + w.nb_start), *nb_fill = (int *)(base + w.nb_fill);
         float4 *nb_list = (float4 *)(base + w.nb_list);
-        nb_count_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(cnt, geom->res, max_cells, nb_cnt);
-        ip_grid_scan<<<1, 1024, 0, st>>>(nb_cnt, geom->res, max_cells, nb_start, nb_fill);
-        nb_fill_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(bgn, ip_pos, geom->res, max_cells, d->num_seek_IP == 1, nb_start, nb_list);
-        PN_LAUNCH_CHECK("ip_pack / neighbourhood lists");
+        if (!fused_prep) {
+            ip_pack_kernel<<<div_up(d->n_vtx, 256), 256, 0, st>>>(d->p_def, d->p_ori, d->F_IP, idx, d->n_vtx, geom->res, max_cells, bgn, ip_pos, ip_rec);
+            nb_count_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(cnt, geom->res, max_cells, nb_cnt);
+            ip_grid_scan<<<1, 1024, 0, st>>>(nb_cnt, geom->res, max_cells, nb_start, nb_fill);
+            nb_fill_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(bgn, ip_pos, geom->res, max_cells, d->num_seek_IP == 1, nb_start, nb_list);
+            PN_LAUNCH_CHECK("ip_pack / neighbourhood lists");
+        }
         IpPack P{ip_pos, ip_rec, bgn, nb_start, nb_list};
         WaveArgs Wv{};
         Wv.ctl = (PassCtl *)(base + w.ctl); Wv.counters = (long long *)(base + w.counters);
@@ -717,13 +887,15 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
     if (mode == 0 || mode == 1) {
         float4 *ip_pos = (float4 *)(base + w.ip_pos);
         float *ip_rec = (float *)(base + w.ip_rec);
-        ip_pack_kernel<<<div_up(d->n_vtx, 256), 256, 0, st>>>(d->p_def, d->p_ori, d->F_IP, idx, d->n_vtx, geom->res, max_cells, bgn, ip_pos, ip_rec);
         int *nb_cnt = (int *)(base + w.nb_cnt), *nb_start = (int *)(base + w.nb_start), *nb_fill = (int *)(base + w.nb_fill);
         float4 *nb_list = (float4 *)(base + w.nb_list);
-        nb_count_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(cnt, geom->res, max_cells, nb_cnt);
-        ip_grid_scan<<<1, 1024, 0, st>>>(nb_cnt, geom->res, max_cells, nb_start, nb_fill);
-        nb_fill_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(bgn, ip_pos, geom->res, max_cells, d->num_seek_IP == 1, nb_start, nb_list);
-        PN_LAUNCH_CHECK("ip_pack / neighbourhood lists");
+        if (!fused_prep) {
+            ip_pack_kernel<<<div_up(d->n_vtx, 256), 256, 0, st>>>(d->p_def, d->p_ori, d->F_IP, idx, d->n_vtx, geom->res, max_cells, bgn, ip_pos, ip_rec);
+            nb_count_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(cnt, geom->res, max_cells, nb_cnt);
+            ip_grid_scan<<<1, 1024, 0, st>>>(nb_cnt, geom->res, max_cells, nb_start, nb_fill);
+            nb_fill_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(bgn, ip_pos, geom->res, max_cells, d->num_seek_IP == 1, nb_start, nb_list);
+            PN_LAUNCH_CHECK("ip_pack / neighbourhood lists");
+        }
         IpPack P{ip_pos, ip_rec, bgn, nb_start, nb_list};
         const bool tc = mode == 0;
         const size_t smem = tc ? (((sizeof(RenderTcSmem) + 127) & ~size_t(127)) + kTcGroups * 4 * sizeof(WarpShared) + 128)

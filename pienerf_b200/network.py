@@ -408,7 +408,8 @@ class NeRFNetwork(nn.Module):
         n_pass = int(lib.pn_render_pass_count(int(max_steps)))
         if io is not None and 0 < io.max_passes < n_pass:
             n_pass = int(io.max_passes)
-        self._render_launches = 11 + (1 + 3 * n_pass if mode == 3 else 1)
+        fused_prep = mode != 2 and (math.ceil((2 * float(kwargs.get("bound", self.bound)) + 2e-3) / float(kwargs.get("hash_grid_size"))) + 1) ** 3 <= 64 * 1024
+        self._render_launches = (3 if fused_prep else 11) + (1 + 3 * n_pass if mode == 3 else 1)
         if io is not None:
             self._render_launches += (1 if io.epoch else 0) + (1 if io.n_signal else 0) - (1 if (io.flags & PN_IO_WEIGHTS_READY and mode == 3) else 0)
         f = self._field_struct(embeddings)

@@ -143,3 +143,24 @@ def test_mlp_only_pass_matches_torch_fp32():
     sb, cb = model.mlp_only(big, dbig)
     torch.cuda.synchronize()
     assert torch.equal(sb[:M], sig) and torch.equal(cb[:M], rgb)
+
+
+@pytest.mark.parametrize("K", [1, 3])
+def test_fused_ip_preparation_kernel_equals_the_multi_kernel_chain(K):
+    """bbox + counting sort + IP records + neighbourhood lists as one single-CTA kernel vs the ten stand-alone kernels: same frame bit for bit."""
+    from pienerf_b200._lib import check, lib
+    model, field, bits, state, rays_o, rays_d = _setup(0.03, W=96, H=96)
+    ro_, rd_ = _gpu(rays_o)[None], _gpu(rays_d)[None]
+    opt = dict(OPT, num_seek_IP=K)
+    try:
+        check(lib.pn_set_prep_mode(1))
+        a = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in model.render_deformed(ro_, rd_, mode=3, **KW, **opt).items()}
+        check(lib.pn_set_prep_mode(0))
+        b = model.render_deformed(ro_, rd_, mode=3, **KW, **opt)
+        for name in ("image", "depth_0", "weights_sum"):
+            assert torch.equal(a[name], b[name]), name
+        assert a["stats"].tolist()[:4] == b["stats"].tolist()[:4] and int(a["stats"][0]) > 1000
+        c = model.render_deformed(ro_, rd_, mode=0, **KW, **opt)                # the fused-frame kernel reads the same prepared structures
+        assert torch.equal(c["image"], b["image"])
+    finally:
+        check(lib.pn_set_prep_mode(0))
