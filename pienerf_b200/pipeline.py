@@ -210,8 +210,11 @@ class FramePipeline:
                 fb = self.block.view(self.off_frame + s * self.frame_bytes, torch.float32, (npx * 5,))
                 sl["frame"] = {"image": fb[:3 * npx].view(npx, 3), "depth": fb[3 * npx:4 * npx], "depth_0": fb[4 * npx:5 * npx]}
                 sl["cam_host"] = torch.zeros(20, dtype=torch.float32).pin_memory()
-                sl["host"] = {"image": torch.empty(npx, 3, dtype=torch.float32).pin_memory(), "depth": torch.empty(npx, dtype=torch.float32).pin_memory(),
-                              "depth_0": torch.empty(npx, dtype=torch.float32).pin_memory()}
+                # the frame slot is one contiguous [image | depth | depth_0] run: ONE device-to-host copy per frame into one pinned buffer
+                sl["frame_flat"] = fb
+                hb = torch.empty(npx * 5, dtype=torch.float32).pin_memory()
+                sl["host_flat"] = hb
+                sl["host"] = {"image": hb[:3 * npx].view(npx, 3), "depth": hb[3 * npx:4 * npx], "depth_0": hb[4 * npx:5 * npx]}
             sl["frame_ptr"] = (fbase, fbase + 12 * npx, fbase + 16 * npx)
             # flag addresses
             sl["my_state_flag"] = self.block.ptr + self.off_sflag + 4 * s
@@ -344,41 +347,53 @@ class FramePipeline:
 
     @staticmethod
     def calibrate_rank0_share(model, sim, opt, pose, intrinsics, slots=3, frames=12, **kw):
-        """Rank 0 also runs the simulator, whose kernels time-share its GPU with the render: give it a smaller tile share x (relative
-        to an equal split) such that  x * r + S = r * (N - x) / (N - 1),  r = render time of an equal share (measured: `frames`
-        paused frames through an equal-split pipeline, slowest rank), S = simulator step time (measured alone on rank 0).
-        Collective: every rank calls it; returns the same x on every rank."""
+        """Rank 0 also runs the simulator.  Its chain (state + step) is sequential — one frame per chain latency — and that latency
+        grows with the render work sharing rank 0's GPU (the field kernel saturates the L2 the step's small kernels read through):
+        c(x) ~ c0 + (c1 - c0) x  for a tile share x relative to an equal split, c0 = the chain alone, c1 = beside a full share.
+        The other ranks need r (N - x) / (N - 1) per frame, r = render time of an equal share.  Measured here: r (paused frames
+        through an equal-split pipeline, slowest rank), c1 (the same pipeline with the simulator running), c0 (the step alone +
+        the state kernels); returned: the x that equalises the two, clamped to [0.1, 1].  Collective: every rank calls it and
+        gets the same x."""
         import torch.distributed as dist
         world = dist.get_world_size() if dist.is_initialized() else 1
         if world == 1:
             return 1.0
         pipe = FramePipeline(model, sim, opt, slots=slots, **kw)
         pipe.build(pose, intrinsics)
-        for _ in range(4):
-            pipe.frame(pose, intrinsics, to_host=False, paused=True)
-        pipe.drain(); torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(frames):
-            pipe.frame(pose, intrinsics, to_host=False, paused=True)
-        pipe.drain(); e1.record(); torch.cuda.synchronize()
-        r = e0.elapsed_time(e1) / frames
-        S = 0.0
+
+        def period(paused):
+            for _ in range(4):
+                pipe.frame(pose, intrinsics, to_host=False, paused=paused)
+            pipe.drain(); torch.cuda.synchronize(); dist.barrier()
+            e0.record()
+            for _ in range(frames):
+                pipe.frame(pose, intrinsics, to_host=False, paused=paused)
+            pipe.drain(); e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / frames
+        dof = vel = None
         if pipe.rank == 0:
             dof, vel = sim.dof.clone(), sim.dof_vel.clone()
+        r = period(True)
+        c1 = period(False)
+        S = 0.0
+        if pipe.rank == 0:
             e0.record()
             for _ in range(20):
                 sim.stepforward()
             e1.record(); torch.cuda.synchronize()
             S = e0.elapsed_time(e1) / 20
             sim.dof.copy_(dof); sim.dof_vel.copy_(vel)
-        t = torch.tensor([r, S], dtype=torch.float64, device=pipe.dev)
+        t = torch.tensor([r, c1, S], dtype=torch.float64, device=pipe.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        r, S = float(t[0]), float(t[1])
+        r, c1, S = float(t[0]), float(t[1]), float(t[2])
         dist.barrier()
         pipe.close()
-        x = 1.0 - S * (world - 1) / (world * r)
-        return float(min(1.0, max(0.25, x)))
+        c0 = S + 0.04                                                           # + camera upload, ip_info, state push
+        c1 = max(c1, c0 + 1e-3)
+        n = world
+        x = (r * n / (n - 1) - c0) / ((c1 - c0) + r / (n - 1))
+        return float(min(1.0, max(0.1, x)))
 
     def _barrier(self):
         import torch.distributed as dist
@@ -429,8 +444,7 @@ class FramePipeline:
             cs = self.copy_stream
             cs.wait_event(sl["render_done"])
             with torch.cuda.stream(cs):
-                for k in ("image", "depth", "depth_0"):                          # trainer.py:589-593 .cpu().numpy() of the frame
-                    sl["host"][k].copy_(sl["frame"][k], non_blocking=True)
+                sl["host_flat"].copy_(sl["frame_flat"], non_blocking=True)       # trainer.py:589-593 .cpu().numpy() of image, depth, depth_0
                 ev = torch.cuda.Event(); ev.record(cs)
                 sl["copy_done"] = ev
         self.frame_id += 1
