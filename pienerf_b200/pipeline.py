@@ -352,7 +352,8 @@ class FramePipeline:
         c(x) ~ c0 + (c1 - c0) x  for a tile share x relative to an equal split, c0 = the chain alone, c1 = beside a full share.
         The other ranks need r (N - x) / (N - 1) per frame, r = render time of an equal share.  Measured here: r (paused frames
         through an equal-split pipeline, slowest rank), c1 (the same pipeline with the simulator running), c0 (the step alone +
-        the state kernels); returned: the x that equalises the two, clamped to [0.1, 1].  Collective: every rank calls it and
+        the state kernels).  For large shares (2 GPUs) what matters instead is the GPU time the step takes from rank 0's render:
+        x r + S = r (N - x) / (N - 1).  Returned: the smaller of the two balancing shares, clamped to [0.1, 1].  Collective: every rank calls it and
         gets the same x."""
         import torch.distributed as dist
         world = dist.get_world_size() if dist.is_initialized() else 1
@@ -392,8 +393,9 @@ class FramePipeline:
         c0 = S + 0.04                                                           # + camera upload, ip_info, state push
         c1 = max(c1, c0 + 1e-3)
         n = world
-        x = (r * n / (n - 1) - c0) / ((c1 - c0) + r / (n - 1))
-        return float(min(1.0, max(0.1, x)))
+        x_chain = (r * n / (n - 1) - c0) / ((c1 - c0) + r / (n - 1))          # the chain's latency must not exceed the others' frame time
+        x_share = 1.0 - S * (n - 1) / (n * r)                                   # nor rank 0's render + the step's own GPU time (large shares)
+        return float(min(1.0, max(0.1, min(x_chain, x_share))))
 
     def _barrier(self):
         import torch.distributed as dist
