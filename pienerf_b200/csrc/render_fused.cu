@@ -491,7 +491,8 @@ __device__ void block_scan_exclusive(const int *v, int n, int *out, int *zero_fi
 __global__ void __launch_bounds__(1024) ip_prep_fused_kernel(const float *__restrict__ p_def, const float *__restrict__ p_ori, const float *__restrict__ F,
                                                              int n, float hgs, int cut, float bound, int res_max, int n_grid_cap, int zyx_order,
                                                              FrameGeom *__restrict__ g, int *cnt, int *bgn, int *fill, int *idx, float4 *ip_pos,
-                                                             float *ip_rec, int *nb_cnt, int *nb_start, float4 *nb_list) {
+                                                             float *ip_rec, int *nb_cnt, int *nb_start, float4 *nb_list, float4 *nb_sorted,
+                                                             float *nb_md) {
     __shared__ float smin[3][32], smax[3][32];
     __shared__ int s_over[3], s_res[3];
     __shared__ float s_bbmin[3];
@@ -603,33 +604,26 @@ __global__ void __launch_bounds__(1024) ip_prep_fused_kernel(const float *__rest
             }
         }
     }
-}
-
-// Distance-sorted copy of the neighbourhood lists (nearest_list_sorted): a warp per cell ranks the cell's entries by (lower bound of
-// the distance to any point of the cell, visiting rank); lists longer than 64 stay in visiting order with bound 0 (no early exit,
-// same result).  A grid of its own: ranking 1-2 k lists of ~47 entries is ~0.7 M warp-instructions, too much for the single CTA above.
-__global__ void __launch_bounds__(256) nb_sort_kernel(const FrameGeom *__restrict__ g, float hgs, int n_grid_cap, const int *__restrict__ nb_start,
-                                                      const float4 *__restrict__ nb_list, float4 *__restrict__ nb_sorted, float *__restrict__ nb_md) {
-    const int r0 = g->res[0], r1 = g->res[1], r2 = g->res[2];
-    const int n_grid = min(r0 * r1 * r2, n_grid_cap);
-    const int lane = threadIdx.x & 31;
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= n_grid) return;
-    {
+    if (!nb_sorted) return;
+    __syncthreads();
+    // ---- distance-sorted copy (nearest_list_sorted): a warp per cell ranks the cell's entries by (lower bound of the distance to any
+    // point of the cell, visiting rank); lists longer than 64 stay in visiting order with bound 0 (no early exit, same result)
+    const int lane = tid & 31;
+    for (int c = tid >> 5; c < n_grid; c += nt >> 5) {
         const int b = nb_start[c], L = nb_start[c + 1] - b;
-        if (L == 0) return;
+        if (L == 0) continue;
         if (L > 64) {
             for (int j = lane; j < L; j += 32) {
                 const float4 q = nb_list[b + j];
                 nb_sorted[b + j] = make_float4(q.x, q.y, q.z, __int_as_float(__float_as_int(q.w) | (min(j, 65535) << 16)));
                 nb_md[b + j] = 0.f;
             }
-            return;
+            continue;
         }
         const int g0 = c % r0, g1 = (c / r0) % r1, g2 = c / (r0 * r1);
         // the cell's box, widened by more than any rounding of floor((x - bbmin) / hgs) can misplace a sample
-        const float lo0 = g->bbmin[0] + g0 * hgs - 1e-5f, lo1 = g->bbmin[1] + g1 * hgs - 1e-5f, lo2 = g->bbmin[2] + g2 * hgs - 1e-5f;
-        const float hi0 = g->bbmin[0] + (g0 + 1) * hgs + 1e-5f, hi1 = g->bbmin[1] + (g1 + 1) * hgs + 1e-5f, hi2 = g->bbmin[2] + (g2 + 1) * hgs + 1e-5f;
+        const float lo0 = s_bbmin[0] + g0 * hgs - 1e-5f, lo1 = s_bbmin[1] + g1 * hgs - 1e-5f, lo2 = s_bbmin[2] + g2 * hgs - 1e-5f;
+        const float hi0 = s_bbmin[0] + (g0 + 1) * hgs + 1e-5f, hi1 = s_bbmin[1] + (g1 + 1) * hgs + 1e-5f, hi2 = s_bbmin[2] + (g2 + 1) * hgs + 1e-5f;
         float4 q[2];
         float md[2];
 #pragma unroll
@@ -858,10 +852,8 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
     if (fused_prep) {
         ip_prep_fused_kernel<<<1, 1024, 0, st>>>(d->p_def, d->p_ori, d->F_IP, d->n_vtx, d->hgs, d->cut, d->bound, res_max_for(d->bound, d->hgs), max_cells,
                                                  d->num_seek_IP == 1, geom, cnt, bgn, fill, idx, (float4 *)(base + w.ip_pos), (float *)(base + w.ip_rec),
-                                                 (int *)(base + w.nb_cnt), (int *)(base + w.nb_start), (float4 *)(base + w.nb_list));
-        if (sorted_lists)
-            nb_sort_kernel<<<div_up(max_cells * 32, 256), 256, 0, st>>>(geom, d->hgs, max_cells, (const int *)(base + w.nb_start), (const float4 *)(base + w.nb_list),
-                                                                         (float4 *)(base + w.nb_sorted), (float *)(base + w.nb_md));
+                                                 (int *)(base + w.nb_cnt), (int *)(base + w.nb_start), (float4 *)(base + w.nb_list),
+                                                 sorted_lists ? (float4 *)(base + w.nb_sorted) : nullptr, sorted_lists ? (float *)(base + w.nb_md) : nullptr);
         PN_LAUNCH_CHECK("ip_prep_fused_kernel");
     } else {
         ip_bbox_kernel<<<1, 1024, 0, st>>>(d->p_def, d->n_vtx, d->hgs, d->cut, d->bound, res_max_for(d->bound, d->hgs), geom, nullptr, nullptr, nullptr);

@@ -148,11 +148,10 @@ __device__ __forceinline__ int nearest_list_sorted(const IpPack &P, const pn::Be
 #pragma unroll
     for (int i = 0; i < KMAX; i++) { bd[i] = FLT_MAX; ks[i] = -1; rk[i] = 0x7fffffff; }
     for (int k = s; k < e; k += PN_LIST_BATCH) {
+        if (k > s && __ldg(P.nb_md + k) > bd[KMAX - 1]) break;
         float4 qs[PN_LIST_BATCH];
 #pragma unroll
         for (int j = 0; j < PN_LIST_BATCH; j++) qs[j] = __ldg(P.nb_sorted + min(k + j, e - 1));
-        // the bound of the NEXT batch travels with this batch's loads (a dependent load per batch would double the latency chain)
-        const float md_next = k + PN_LIST_BATCH < e ? __ldg(P.nb_md + k + PN_LIST_BATCH) : FLT_MAX;
 #pragma unroll
         for (int j = 0; j < PN_LIST_BATCH; j++) {
             const float4 q = qs[j];
@@ -174,7 +173,6 @@ __device__ __forceinline__ int nearest_list_sorted(const IpPack &P, const pn::Be
                 }
             }
         }
-        if (md_next > bd[KMAX - 1]) break;       // every remaining candidate is farther than the current K-th best
     }
     int found = 0;
 #pragma unroll
