@@ -190,9 +190,6 @@ int pn_set_wave_capacity(int rows);
 /* Per-frame IP preparation of pn_render_deformed: 0 (default) = one single-CTA kernel when the IP-grid capacity is <= 64 Ki cells
  * (every configuration without --cut), 1 = always the multi-kernel chain (bbox, counting sort, pack, neighbourhood lists). */
 int pn_set_prep_mode(int force_multi_kernel);
-/* Neighbourhood lists the wavefront march scans: 0 (default) = the distance-sorted copy with early exit where it applies (fused
- * preparation, num_seek_IP >= 2, fewer than 65536 IPs), 1 = always the visiting-order lists.  Same result either way. */
-int pn_set_list_mode(int visiting_order_only);
 /* Size the persistent march / field grids of mode 3 for (SM count - n_sm) SMs, leaving n_sm SMs' worth of CTA slots to kernels of
  * other streams (the simulator's launches on the GPU that also renders).  0 = use every SM (default).  Process-wide; a CUDA
  * graph captured afterwards keeps the grid sizes it was captured with. */

@@ -89,7 +89,6 @@ _PROTOS = {
     "pn_set_render_sm_reserve": (i32, [i32]),
     "pn_set_wave_capacity": (i32, [i32]),
     "pn_set_prep_mode": (i32, [i32]),
-    "pn_set_list_mode": (i32, [i32]),
     "pn_set_profile_events": (i32, [vp, vp]),
     "pn_set_profile_event_list": (i32, [vp, i32]),
     "pn_render_pass_count": (i32, [u32]),

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(128, 3) field_forward_kernel(const pn_field_t 
 
 constexpr size_t kWeightsImageBytes = 48 * 1024;   // >= sizeof(pn::tc::Weights), checked in render_wave.cuh
 struct WorkspaceLayout {
-    size_t geom, queue, nears, fars, active, pig_cnt, pig_bgn, pig_fill, pig_idx, ip_pos, ip_rec, nb_cnt, nb_start, nb_fill, nb_list, nb_sorted, nb_md;
+    size_t geom, queue, nears, fars, active, pig_cnt, pig_bgn, pig_fill, pig_idx, ip_pos, ip_rec, nb_cnt, nb_start, nb_fill, nb_list;
     size_t ctl, alive0, alive1, rs_march, rs_comp, link, xyzdt, meta, out, slab_next, counters, weights_img;   // wavefront mode
     int cap;
     size_t total;
@@ -419,7 +419,6 @@ WorkspaceLayout layout(uint32_t N, int n_vtx, int max_cells) {
     w.ip_rec = take(sizeof(float) * 16 * (size_t)n_vtx);
     w.nb_cnt = take(sizeof(int) * (size_t)max_cells); w.nb_start = take(sizeof(int) * ((size_t)max_cells + 1));
     w.nb_fill = take(sizeof(int) * (size_t)max_cells); w.nb_list = take(sizeof(float4) * 27 * (size_t)n_vtx);
-    w.nb_sorted = take(sizeof(float4) * 27 * (size_t)n_vtx); w.nb_md = take(sizeof(float) * 27 * (size_t)n_vtx);
     w.cap = wave_capacity(N);
     w.ctl = take(16 * 16);
     w.counters = take(64);
@@ -491,8 +490,7 @@ __device__ void block_scan_exclusive(const int *v, int n, int *out, int *zero_fi
 __global__ void __launch_bounds__(1024) ip_prep_fused_kernel(const float *__restrict__ p_def, const float *__restrict__ p_ori, const float *__restrict__ F,
                                                              int n, float hgs, int cut, float bound, int res_max, int n_grid_cap, int zyx_order,
                                                              FrameGeom *__restrict__ g, int *cnt, int *bgn, int *fill, int *idx, float4 *ip_pos,
-                                                             float *ip_rec, int *nb_cnt, int *nb_start, float4 *nb_list, float4 *nb_sorted,
-                                                             float *nb_md) {
+                                                             float *ip_rec, int *nb_cnt, int *nb_start, float4 *nb_list) {
     __shared__ float smin[3][32], smax[3][32];
     __shared__ int s_over[3], s_res[3];
     __shared__ float s_bbmin[3];
@@ -604,54 +602,6 @@ __global__ void __launch_bounds__(1024) ip_prep_fused_kernel(const float *__rest
             }
         }
     }
-    if (!nb_sorted) return;
-    __syncthreads();
-    // ---- distance-sorted copy (nearest_list_sorted): a warp per cell ranks the cell's entries by (lower bound of the distance to any
-    // point of the cell, visiting rank); lists longer than 64 stay in visiting order with bound 0 (no early exit, same result)
-    const int lane = tid & 31;
-    for (int c = tid >> 5; c < n_grid; c += nt >> 5) {
-        const int b = nb_start[c], L = nb_start[c + 1] - b;
-        if (L == 0) continue;
-        if (L > 64) {
-            for (int j = lane; j < L; j += 32) {
-                const float4 q = nb_list[b + j];
-                nb_sorted[b + j] = make_float4(q.x, q.y, q.z, __int_as_float(__float_as_int(q.w) | (min(j, 65535) << 16)));
-                nb_md[b + j] = 0.f;
-            }
-            continue;
-        }
-        const int g0 = c % r0, g1 = (c / r0) % r1, g2 = c / (r0 * r1);
-        // the cell's box, widened by more than any rounding of floor((x - bbmin) / hgs) can misplace a sample
-        const float lo0 = s_bbmin[0] + g0 * hgs - 1e-5f, lo1 = s_bbmin[1] + g1 * hgs - 1e-5f, lo2 = s_bbmin[2] + g2 * hgs - 1e-5f;
-        const float hi0 = s_bbmin[0] + (g0 + 1) * hgs + 1e-5f, hi1 = s_bbmin[1] + (g1 + 1) * hgs + 1e-5f, hi2 = s_bbmin[2] + (g2 + 1) * hgs + 1e-5f;
-        float4 q[2];
-        float md[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int j = lane + 32 * u;
-            q[u] = j < L ? nb_list[b + j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float a0 = fmaxf(fmaxf(lo0 - q[u].x, q[u].x - hi0), 0.f), a1 = fmaxf(fmaxf(lo1 - q[u].y, q[u].y - hi1), 0.f),
-                        a2 = fmaxf(fmaxf(lo2 - q[u].z, q[u].z - hi2), 0.f);
-            md[u] = j < L ? (a0 * a0 + a1 * a1 + a2 * a2) * 0.9999f : FLT_MAX;
-        }
-        int pos[2] = {0, 0};
-        for (int j = 0; j < L; j++) {
-            const float mj = __shfl_sync(0xffffffffu, j < 32 ? md[0] : md[1], j & 31);
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int i = lane + 32 * u;
-                pos[u] += (mj < md[u]) || (mj == md[u] && j < i);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int i = lane + 32 * u;
-            if (i < L) {
-                nb_sorted[b + pos[u]] = make_float4(q[u].x, q[u].y, q[u].z, __int_as_float(__float_as_int(q[u].w) | (i << 16)));
-                nb_md[b + pos[u]] = md[u];
-            }
-        }
-    }
 }
 
 constexpr int kFusedPrepMaxCells = 64 * 1024;   // beyond this (trex with --cut: 67^3 cells) the multi-kernel path has the parallelism
@@ -734,8 +684,6 @@ extern "C" int pn_set_wave_capacity(int rows) {
     g_wave_cap_override = rows;
     return PN_OK;
 }
-static int g_unsorted_lists = 0;     // tests / A-B: scan the visiting-order lists even where the sorted copy applies
-extern "C" int pn_set_list_mode(int visiting_order_only) { g_unsorted_lists = visiting_order_only; return PN_OK; }
 static int g_prep_force_multi = 0;   // tests: compare the fused preparation kernel with the multi-kernel chain
 extern "C" int pn_set_prep_mode(int force_multi_kernel) { g_prep_force_multi = force_multi_kernel; return PN_OK; }
 static int g_sm_reserve = 0;
@@ -847,13 +795,10 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
     PN_CUDA(cudaMemsetAsync(queue, 0, sizeof(FrameQueue), st));
     // IP preparation: one single-CTA kernel when the grid is small (every config without --cut), else the parallel multi-kernel chain
     const bool fused_prep = mode != 2 && max_cells <= kFusedPrepMaxCells && !g_prep_force_multi;
-    // distance-sorted neighbourhood lists with early exit for the wavefront march (K >= 2; entry codes are 16 + 16 bits)
-    const bool sorted_lists = fused_prep && mode == 3 && d->num_seek_IP >= 2 && d->n_vtx < 65536 && !g_unsorted_lists;
     if (fused_prep) {
         ip_prep_fused_kernel<<<1, 1024, 0, st>>>(d->p_def, d->p_ori, d->F_IP, d->n_vtx, d->hgs, d->cut, d->bound, res_max_for(d->bound, d->hgs), max_cells,
                                                  d->num_seek_IP == 1, geom, cnt, bgn, fill, idx, (float4 *)(base + w.ip_pos), (float *)(base + w.ip_rec),
-                                                 (int *)(base + w.nb_cnt), (int *)(base + w.nb_start), (float4 *)(base + w.nb_list),
-                                                 sorted_lists ? (float4 *)(base + w.nb_sorted) : nullptr, sorted_lists ? (float *)(base + w.nb_md) : nullptr);
+                                                 (int *)(base + w.nb_cnt), (int *)(base + w.nb_start), (float4 *)(base + w.nb_list));
         PN_LAUNCH_CHECK("ip_prep_fused_kernel");
     } else {
         ip_bbox_kernel<<<1, 1024, 0, st>>>(d->p_def, d->n_vtx, d->hgs, d->cut, d->bound, res_max_for(d->bound, d->hgs), geom, nullptr, nullptr, nullptr);
@@ -891,8 +836,7 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
             nb_fill_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(bgn, ip_pos, geom->res, max_cells, d->num_seek_IP == 1, nb_start, nb_list);
             PN_LAUNCH_CHECK("ip_pack / neighbourhood lists");
         }
-        IpPack P{ip_pos, ip_rec, bgn, nb_start, nb_list, sorted_lists ? (const float4 *)(base + w.nb_sorted) : nullptr,
-                 sorted_lists ? (const float *)(base + w.nb_md) : nullptr};
+        IpPack P{ip_pos, ip_rec, bgn, nb_start, nb_list};
         WaveArgs Wv{};
         Wv.ctl = (PassCtl *)(base + w.ctl); Wv.counters = (long long *)(base + w.counters);
         Wv.alive[0] = (int *)(base + w.alive0); Wv.alive[1] = (int *)(base + w.alive1);
@@ -919,17 +863,10 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
         if (g_prof_start) PN_CUDA(cudaEventRecord(g_prof_start, st));
         for (int p = 0; p < n_pass; p++, cap_p *= 2) {
             const int cap_now = (limited && p == n_pass - 1) ? (int)d->max_steps : cap_p;
-            const dim3 mg(sms * PN_MARCH_MINB), mb(PN_MARCH_THREADS);
             switch (d->num_seek_IP) {
-                case 1: wave_march_kernel<1, false><<<mg, mb, 0, st>>>(A, P, Wv, p, cap_now); break;
-                case 2:
-                    if (sorted_lists) wave_march_kernel<2, true><<<mg, mb, 0, st>>>(A, P, Wv, p, cap_now);
-                    else wave_march_kernel<2, false><<<mg, mb, 0, st>>>(A, P, Wv, p, cap_now);
-                    break;
-                default:
-                    if (sorted_lists) wave_march_kernel<3, true><<<mg, mb, 0, st>>>(A, P, Wv, p, cap_now);
-                    else wave_march_kernel<3, false><<<mg, mb, 0, st>>>(A, P, Wv, p, cap_now);
-                    break;
+                case 1: wave_march_kernel<1><<<sms * PN_MARCH_MINB, PN_MARCH_THREADS, 0, st>>>(A, P, Wv, p, cap_now); break;
+                case 2: wave_march_kernel<2><<<sms * PN_MARCH_MINB, PN_MARCH_THREADS, 0, st>>>(A, P, Wv, p, cap_now); break;
+                default: wave_march_kernel<3><<<sms * PN_MARCH_MINB, PN_MARCH_THREADS, 0, st>>>(A, P, Wv, p, cap_now); break;
             }
             if (g_prof_list && 2 * fk + 1 < g_prof_n) PN_CUDA(cudaEventRecord(g_prof_list[2 * fk], st));
             wave_field_ws_kernel<<<sms, (kWsProd + kWsCons) * 128, smem, st>>>(A, Wv, p);
@@ -959,7 +896,7 @@ extern "C" int pn_render_deformed_ex(const pn_field_t *f, const pn_deform_t *d, 
             nb_fill_kernel<<<div_up(max_cells, 256), 256, 0, st>>>(bgn, ip_pos, geom->res, max_cells, d->num_seek_IP == 1, nb_start, nb_list);
             PN_LAUNCH_CHECK("ip_pack / neighbourhood lists");
         }
-        IpPack P{ip_pos, ip_rec, bgn, nb_start, nb_list, nullptr, nullptr};
+        IpPack P{ip_pos, ip_rec, bgn, nb_start, nb_list};
         const bool tc = mode == 0;
         const size_t smem = tc ? (((sizeof(RenderTcSmem) + 127) & ~size_t(127)) + kTcGroups * 4 * sizeof(WarpShared) + 128)
                                : (((sizeof(pn::FieldBlockSmem) + 127) & ~size_t(127)) + 4 * sizeof(WarpShared) + 128);

@@ -23,10 +23,6 @@ struct IpPack {
     const int *cell_start;  // [n_grid+1]
     const int *nb_start;    // [n_grid+1] CSR of the per-cell neighbourhood lists
     const float4 *nb_list;  // [<= 27 n] (p_def.xyz, bitcast position k in the cell-sorted arrays)
-    // distance-sorted copy of the lists (wavefront march, K >= 2, n < 65536; nullptr otherwise): entries of a cell ordered by a lower
-    // bound of their distance to any point of the cell, w = k | visiting rank << 16; nb_md = that bound squared, per entry
-    const float4 *nb_sorted;
-    const float *nb_md;
 };
 
 // Per-frame neighbourhood lists: for every IP-grid cell, the IPs of its 27-cell neighbourhood in exactly the order in
@@ -133,53 +129,6 @@ __device__ __forceinline__ int nearest_list(const IpPack &P, const pn::BendCfg &
     return found;
 }
 
-// The same K nearest IPs from the distance-sorted copy of the list.  Candidates arrive roughly nearest first, so (a) the scan stops
-// as soon as the lower bound of the next batch exceeds the current K-th best distance — typically after half the list — and (b)
-// insertions are rare.  The reference's result is "the K smallest by (distance, visiting rank)" (strict-less insertion in visiting
-// order); comparing (d, rank) lexicographically reproduces it in any scan order, exact ties included.
-template <int KMAX>
-__device__ __forceinline__ int nearest_list_sorted(const IpPack &P, const pn::BendCfg &c, float x, float y, float z, int g0, int g1, int g2,
-                                                   int (&ks)[KMAX]) {
-    static_assert(KMAX >= 2, "K = 1 follows find_closest_IP (own cell first): visiting-order list");
-    const int cell = (g2 * c.res[1] + g1) * c.res[0] + g0;
-    const int s = __ldg(P.nb_start + cell), e = __ldg(P.nb_start + cell + 1);
-    float bd[KMAX];
-    int rk[KMAX];
-#pragma unroll
-    for (int i = 0; i < KMAX; i++) { bd[i] = FLT_MAX; ks[i] = -1; rk[i] = 0x7fffffff; }
-    for (int k = s; k < e; k += PN_LIST_BATCH) {
-        if (k > s && __ldg(P.nb_md + k) > bd[KMAX - 1]) break;
-        float4 qs[PN_LIST_BATCH];
-#pragma unroll
-        for (int j = 0; j < PN_LIST_BATCH; j++) qs[j] = __ldg(P.nb_sorted + min(k + j, e - 1));
-#pragma unroll
-        for (int j = 0; j < PN_LIST_BATCH; j++) {
-            const float4 q = qs[j];
-            const float d = (q.x - x) * (q.x - x) + (q.y - y) * (q.y - y) + (q.z - z) * (q.z - z);
-            if (k + j < e && d <= bd[KMAX - 1]) {
-                const int wv = __float_as_int(q.w), id = wv & 0xffff, r = (int)((unsigned)wv >> 16);
-                auto before = [&](int i) { return d < bd[i] || (d == bd[i] && r < rk[i]); };
-                if (before(KMAX - 1)) {
-                    if (KMAX == 2) {
-                        if (before(0)) { bd[1] = bd[0]; ks[1] = ks[0]; rk[1] = rk[0]; bd[0] = d; ks[0] = id; rk[0] = r; }
-                        else { bd[1] = d; ks[1] = id; rk[1] = r; }
-                    } else {
-                        if (before(1 % KMAX)) {
-                            bd[KMAX - 1] = bd[1 % KMAX]; ks[KMAX - 1] = ks[1 % KMAX]; rk[KMAX - 1] = rk[1 % KMAX];
-                            if (before(0)) { bd[1 % KMAX] = bd[0]; ks[1 % KMAX] = ks[0]; rk[1 % KMAX] = rk[0]; bd[0] = d; ks[0] = id; rk[0] = r; }
-                            else { bd[1 % KMAX] = d; ks[1 % KMAX] = id; rk[1 % KMAX] = r; }
-                        } else { bd[KMAX - 1] = d; ks[KMAX - 1] = id; rk[KMAX - 1] = r; }
-                    }
-                }
-            }
-        }
-    }
-    int found = 0;
-#pragma unroll
-    for (int i = 0; i < KMAX; i++) found += ks[i] != -1;
-    return found;
-}
-
 // Per-frame packing of the IP state in IP-grid cell order.  Finv uses the very arithmetic of the per-sample
 // inverse (pn::adjugate_inverse), so hoisting it out of the march loop changes no bit when max_iter_num == 1
 // (first Newton iterate: q = 0 => A = F exactly, b = -q_ exactly; raymarching.cu:1268-1304).
@@ -206,7 +155,7 @@ __global__ void __launch_bounds__(256) ip_pack_kernel(const float *__restrict__ 
 }
 
 // bend_sample (march_device.cuh) over the packed, cell-sorted IP state.  Identical decisions and arithmetic.
-template <int KMAX, bool SORTED = false>
+template <int KMAX>
 __device__ __forceinline__ bool bend_sample_packed(const IpPack &P, const pn::BendCfg &c, float &x, float &y, float &z) {
     if (c.cut && !(x > c.cb[0] && x < c.cb[1] && y > c.cb[2] && x < c.cb[3] && z > c.cb[4] && z < c.cb[5])) return true;
     int g0 = (int)floorf((x - c.bbmin[0]) / c.hgs);
@@ -214,9 +163,7 @@ __device__ __forceinline__ bool bend_sample_packed(const IpPack &P, const pn::Be
     int g2 = (int)floorf((z - c.bbmin[2]) / c.hgs);
     g0 = min(max(g0, 0), c.res[0] - 1); g1 = min(max(g1, 0), c.res[1] - 1); g2 = min(max(g2, 0), c.res[2] - 1);
     int ks[KMAX];
-    int n_ip;
-    if constexpr (SORTED && KMAX >= 2) n_ip = nearest_list_sorted<KMAX>(P, c, x, y, z, g0, g1, g2, ks);
-    else n_ip = nearest_list<KMAX>(P, c, x, y, z, g0, g1, g2, ks);
+    int n_ip = nearest_list<KMAX>(P, c, x, y, z, g0, g1, g2, ks);
     if (n_ip <= 0) return false;
     for (int k = 0; k < n_ip; k++) {  // boundary filter with the shrinking loop bound (raymarching.cu:1246-1251)
         const float4 q = __ldg(P.pos + ks[k < KMAX ? k : 0]);

@@ -53,7 +53,7 @@ struct WaveArgs {
 #ifndef PN_MARCH_THREADS
 #define PN_MARCH_THREADS 256   // A/B: 1024 with PN_MARCH_MINB 1 = one CTA per SM, so a grid of (SMs - reserve) CTAs leaves whole SMs free
 #endif
-template <int KMAX, bool SORTED = false>
+template <int KMAX>
 __global__ void __launch_bounds__(PN_MARCH_THREADS, PN_MARCH_MINB) wave_march_kernel(const RenderArgs A, const IpPack P, const WaveArgs Wv, int pass, int pass_cap) {
     pn::BendCfg bc = A.bend;
 #pragma unroll
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(PN_MARCH_THREADS, PN_MARCH_MINB) wave_march_ke
             bool emit = false;
             if (need) {
                 pn::deformed_sample(bc, ox, oy, oz, dx, dy, dz, t, x, y, z);
-                const bool found = bend_sample_packed<KMAX, SORTED>(P, bc, x, y, z);
+                const bool found = bend_sample_packed<KMAX>(P, bc, x, y, z);
                 const bool occ = pn::occupancy_and_exit(m, x, y, z, t, dt, dx, dy, dz, rdx, rdy, rdz, tt);
                 emit = occ && found;
             }

@@ -164,25 +164,3 @@ def test_fused_ip_preparation_kernel_equals_the_multi_kernel_chain(K):
         assert torch.equal(c["image"], b["image"])
     finally:
         check(lib.pn_set_prep_mode(0))
-
-
-@pytest.mark.parametrize("K,amp", [(3, 0.0), (3, 0.04), (2, 0.03)])
-def test_distance_sorted_neighbourhood_lists_give_the_same_frame(K, amp):
-    """The wavefront march scans a distance-sorted copy of the per-cell lists with early exit; the result must be the reference's
-    "K smallest by (distance, visiting rank)" exactly — undeformed lattice (exact distance ties between IPs) included."""
-    from pienerf_b200._lib import check, lib
-    model, field, bits, state, rays_o, rays_d = _setup(amp, W=128, H=128)
-    ro_, rd_ = _gpu(rays_o)[None], _gpu(rays_d)[None]
-    opt = dict(OPT, num_seek_IP=K)
-    try:
-        check(lib.pn_set_list_mode(1))
-        a = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in model.render_deformed(ro_, rd_, mode=3, **KW, **opt).items()}
-        check(lib.pn_set_list_mode(0))
-        b = model.render_deformed(ro_, rd_, mode=3, **KW, **opt)
-        for name in ("image", "depth_0", "weights_sum"):
-            assert torch.equal(a[name], b[name]), name
-        assert a["stats"].tolist()[:4] == b["stats"].tolist()[:4] and int(a["stats"][0]) > 5000
-        c = model.render_deformed(ro_, rd_, mode=0, **KW, **opt)                # fused kernel: visiting-order lists, same frame
-        assert torch.equal(c["image"], b["image"])
-    finally:
-        check(lib.pn_set_list_mode(0))
