@@ -248,11 +248,9 @@ typedef struct {
 } pn_qgmls_step_t;
 uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k, int adj_slices);
 int pn_qgmls_step(const pn_qgmls_step_t *step_host, int solver /*0 dense inverse, 1 PCG on A*/, void *stream);
-/* How pn_qgmls_step (solver 0) runs.  1 (default): the multi-kernel chain — for n <= 512 two launches per local-global iteration
- * (stress; gather + global solve by the last CTA to finish), 1 + 2*iters in all; 3 + 4*iters for larger systems.  2: the same with
- * the gather and the solve as separate launches (1 + 3*iters; A/B, bit-identical to 1).  0: ONE thread-block-cluster kernel for
- * the whole step when n <= 1280 (experimental, measured slower on B200; differs from 1 by fp64 round-off: another fixed summation
- * order in the rhs gather).  Every variant is bit-reproducible. */
+/* How pn_qgmls_step (solver 0) runs: force_multi_kernel = 1 (default) = 3 + 4*iters launches; 0 = ONE thread-block-cluster
+ * kernel for the whole step when the system is small enough (n <= 1280; experimental, measured slower on B200).  The two
+ * differ by fp64 round-off (different fixed summation order in the rhs gather); each is bit-reproducible. */
 int pn_qgmls_step_mode(int force_multi_kernel);
 /* kernels one pn_qgmls_step enqueues for this problem size (1 when the cluster kernel applies) */
 int pn_qgmls_step_launches(int n_ip, int n_k, int iters, int solver, int pcg_iters);

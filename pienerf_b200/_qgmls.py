@@ -70,16 +70,14 @@ def step(desc, solver=0):
     check(lib.pn_qgmls_step(C.byref(desc), int(solver), stream_ptr()))
 
 
-_step_mode = [1]
+_step_mode = [True]
 
 
-def step_mode(mode):
-    """How `step` runs (pn_qgmls_step_mode).  True / 1 (default): the multi-kernel chain, replayed as one CUDA graph — for n <= 512 two
-    launches per local-global iteration (the last CTA of the gather does the global solve); 2: gather and solve as separate launches
-    (A/B, same bits); False / 0: the whole step as ONE thread-block-cluster kernel when n <= 1280 (experimental, measured slower)."""
-    mode = int(mode)
-    check(lib.pn_qgmls_step_mode(mode))
-    _step_mode[0] = mode
+def step_mode(force_multi_kernel):
+    """True (default): 3 + 4*iters launches replayed as one CUDA graph; False: the whole step as ONE thread-block-cluster kernel
+    when n <= 1280 (experimental: measured slower on B200)."""
+    check(lib.pn_qgmls_step_mode(1 if force_multi_kernel else 0))
+    _step_mode[0] = bool(force_multi_kernel)
 
 
 def step_mode_value():

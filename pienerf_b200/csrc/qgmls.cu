@@ -508,105 +508,6 @@ __global__ void __launch_bounds__(256) fused_matvec3_kernel(const double *__rest
     }
 }
 
-// collect_rhs_IP + the global solve of one local-global iteration as ONE launch (n <= 512): the gather of rhs_partial_kernel, four
-// (kernel, slice) items per 512-thread CTA; the CTA that finishes LAST (a ticket counter) then builds rhs = momentum + gathered -
-// rhs_rest in shared memory and applies the pre-inverted matrix (fused_matvec3_kernel<1>'s rows, lane partition and shuffle tree), so
-// an iteration is two dependent launches instead of three.  Which CTA is last varies; what it computes does not (fixed summation
-// orders): the step stays bit-reproducible, and bit-identical to the three-launch path.
-__global__ void __launch_bounds__(512) rhs_partial_solve_kernel(const int *__restrict__ adj_bgn, const int *__restrict__ adj, const double *__restrict__ stress,
-                                                                const double *__restrict__ dNx, int n_k, int slices, double *partial, int *ticket,
-                                                                const double *__restrict__ mat, int n, const double *__restrict__ mom,
-                                                                const double *__restrict__ rhs_rest, const double *__restrict__ dof_rest, double dt,
-                                                                double *__restrict__ dof, const double *__restrict__ last, double *__restrict__ vel_out) {
-    extern __shared__ __align__(16) double xs[];              // [n3] rhs (last CTA only)
-    __shared__ double part[4][4][30];
-    __shared__ int s_last;
-    const int group = threadIdx.x >> 7, gt = threadIdx.x & 127, lane = threadIdx.x & 31, gw = gt >> 5;
-    const int item = blockIdx.x * 4 + group;
-    if (item < n_k * slices) {
-        const int k = item / slices, sl = item % slices;
-        const int e = adj_bgn[k] + sl * 128 + gt;
-        double acc[30];
-#pragma unroll
-        for (int i = 0; i < 30; i++) acc[i] = 0.0;
-        if (e < adj_bgn[k + 1]) {
-            const int code = adj[e], v = code >> 3, i = code & 7;
-            const double *S = stress + (size_t)v * 9;
-            const double *dN = dNx + (size_t)v * 240 + i * 30;
-            const double s0 = S[0], s1 = S[1], s2 = S[2], s3 = S[3], s4 = S[4], s5 = S[5], s6 = S[6], s7 = S[7], s8 = S[8];
-#pragma unroll
-            for (int x = 0; x < 10; x++) {
-                const double g0 = dN[x], g1 = dN[10 + x], g2 = dN[20 + x];
-                acc[3 * x] = s0 * g0 + s1 * g1 + s2 * g2;
-                acc[3 * x + 1] = s3 * g0 + s4 * g1 + s5 * g2;
-                acc[3 * x + 2] = s6 * g0 + s7 * g1 + s8 * g2;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 30; i++) {
-            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(kFull, acc[i], o);
-            if (lane == 0) part[group][gw][i] = acc[i];
-        }
-    }
-    __syncthreads();
-    if (item < n_k * slices && gt < 30)
-        partial[(size_t)item * 30 + gt] = ((part[group][0][gt] + part[group][1][gt]) + part[group][2][gt]) + part[group][3][gt];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int t = atomicAdd(ticket, 1);
-        s_last = t == (int)gridDim.x - 1;
-        if (s_last) *ticket = 0;                              // ready for the next iteration's launch
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int n3 = 3 * n;
-    for (int id = threadIdx.x; id < n3; id += blockDim.x) {
-        const int k = id / 30, i = id % 30;
-        double sum = 0.0;
-        for (int sl = 0; sl < slices; sl++) sum += __ldcg(partial + ((size_t)k * slices + sl) * 30 + i);
-        xs[id] = (mom[id] + sum) - rhs_rest[id];
-    }
-    __syncthreads();
-    for (int row = threadIdx.x >> 5; row < n; row += blockDim.x >> 5) {
-        const double *m = mat + (size_t)row * n;
-        double a0 = 0, a1 = 0, a2 = 0;
-        if ((n & 1) == 0) {
-            const double2 *m2 = reinterpret_cast<const double2 *>(m);
-            const int h = n / 2;
-            for (int j0 = lane; j0 < h; j0 += 128) {         // four 128-bit row loads in flight; sums in matvec3_kernel's order (j = lane, lane + 32, ...)
-                double2 w[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) w[u] = (j0 + 32 * u < h) ? __ldg(m2 + j0 + 32 * u) : make_double2(0.0, 0.0);
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (j0 + 32 * u < h) {
-                        const double *xa = xs + 6 * (size_t)(j0 + 32 * u);
-                        a0 += w[u].x * xa[0] + w[u].y * xa[3]; a1 += w[u].x * xa[1] + w[u].y * xa[4]; a2 += w[u].x * xa[2] + w[u].y * xa[5];
-                    }
-                }
-            }
-        } else {
-            for (int j = lane; j < n; j += 32) {
-                const double w = __ldg(m + j);
-                a0 += w * xs[3 * j]; a1 += w * xs[3 * j + 1]; a2 += w * xs[3 * j + 2];
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            a0 += __shfl_xor_sync(kFull, a0, o); a1 += __shfl_xor_sync(kFull, a1, o); a2 += __shfl_xor_sync(kFull, a2, o);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const double v = (c == 0 ? a0 : (c == 1 ? a1 : a2)) + dof_rest[3 * row + c];
-                dof[3 * row + c] = v;
-                if (vel_out) vel_out[3 * row + c] = (v - last[3 * row + c]) / dt * 0.998;
-            }
-        }
-    }
-}
-
 __global__ void axpy_tilde_kernel(const double *__restrict__ dof, const double *__restrict__ vel, double dt, int n3,
                                   double *__restrict__ tilde, double *__restrict__ last) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1199,7 +1100,7 @@ extern "C" int pn_qgmls_matvec3(const double *mat, const double *x, int n, doubl
 
 extern "C" uint64_t pn_qgmls_step_scratch_doubles(int n_ip, int n_k, int adj_slices) {
     // stress | tilde last mom rhs x | pcg | partial | 8 phase cycle counters of the cluster kernel | its 16 per-CTA partial rhs vectors
-    return 9ull * n_ip + 9ull * 30 * n_k + 16 + 30ull * n_k * (adj_slices > 0 ? adj_slices : 1) + 8 + 16ull * 30 * n_k + 2;   // + the ticket counter
+    return 9ull * n_ip + 9ull * 30 * n_k + 16 + 30ull * n_k * (adj_slices > 0 ? adj_slices : 1) + 8 + 16ull * 30 * n_k;
 }
 
 // Cluster size for the one-kernel step: 16 CTAs (non-portable size, one GPC) if the device can co-schedule them, else 8;
@@ -1231,7 +1132,7 @@ static int step_cluster_size(int n_ip, int n, int n_k) {
 
 extern "C" int pn_qgmls_step_launches(int n_ip, int n_k, int iters, int solver, int pcg_iters) {
     if (solver == 0 && !g_step_force_multi && step_cluster_size(n_ip, 10 * n_k, n_k) > 0) return 1;
-    if (solver == 0 && 10 * n_k <= 512) return g_step_force_multi == 2 ? 1 + 3 * iters : 1 + 2 * iters;
+    if (solver == 0 && 10 * n_k <= 512) return 1 + 3 * iters;
     return 3 + iters * (solver == 0 ? 4 : 6 + 4 * pcg_iters);
 }
 
@@ -1281,15 +1182,6 @@ extern "C" int pn_qgmls_step(const pn_qgmls_step_t *s, int solver, void *stream)
     }
     for (int it = 0; it < s->iters; it++) {
         ip_stress_kernel<<<div_up(s->n_ip * 8, 128), 128, 0, st>>>(dx3, s->topo, s->mu, s->lam, s->dNx, s->dof, s->n_ip, stress);
-        if (fuse && g_step_force_multi != 2) {
-            // two launches per iteration: stress, then gather + (last CTA) global solve
-            int *ticket = reinterpret_cast<int *>(partial + 30 * (size_t)s->n_k * s->adj_slices + 8 + 16 * 30 * (size_t)s->n_k);
-            if (it == 0) PN_CUDA(cudaMemsetAsync(ticket, 0, sizeof(int), st));
-            rhs_partial_solve_kernel<<<div_up(s->n_k * s->adj_slices, 4), 512, xs_bytes, st>>>(s->adj_bgn, s->adj, stress, s->dNx, s->n_k, s->adj_slices, partial, ticket,
-                                                                                               s->Ainv, n, mom, s->rhs_rest, s->dof_rest, s->dt, s->dof, last,
-                                                                                               it == s->iters - 1 ? s->dof_vel : nullptr);
-            continue;
-        }
         rhs_partial_kernel<<<dim3(s->n_k, s->adj_slices), 128, 0, st>>>(s->adj_bgn, s->adj, stress, s->dNx, s->adj_slices, partial);
         if (fuse) {
             fused_matvec3_kernel<1><<<div_up(n * 32, 256), 256, xs_bytes, st>>>(s->Ainv, n, partial, mom, s->rhs_rest, s->adj_slices, s->dt, s->dof_rest, nullptr, s->dof,
