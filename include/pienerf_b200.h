@@ -22,7 +22,7 @@ extern "C" {
 #define PN_OK 0
 #define PN_EINVAL (-1)   /* bad argument (unsupported D/C/degree, null pointer, ...) */
 #define PN_ECUDA (-2)    /* CUDA runtime error; see pn_last_error() */
-#define PN_ENOTIMPL (-3) /* training-only entry point outside the hot path */
+#define PN_ENOTIMPL (-3) /* combination the B200 library does not provide (e.g. fp64 tables) */
 
 const char *pn_last_error(void);
 int pn_version(void);
@@ -36,16 +36,29 @@ int pn_device_sm_count(int *sm_count);
 int pn_grid_encode_forward(const float *inputs, const void *embeddings, const int *offsets, void *outputs,
                            uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, void *dy_dx,
                            uint32_t gridtype, int align_corners, uint32_t interp, int emb_half, void *stream);
-/* gridencoder.cu:473-503 grid_encode_backward / :639-645 grad_total_variation: training only. */
-int pn_grid_encode_backward(void);
-int pn_grad_total_variation(void);
+/* Training side.
+ * gridencoder/src/gridencoder.h:13 + gridencoder.cu:473-503 grid_encode_backward.  grad [L,B,C], grad_embeddings [sO,C]
+ * (caller-zeroed, accumulated into), dy_dx [B,L*D*C] / grad_inputs [B,D] (both or neither; grad_inputs is overwritten):
+ * all of the embeddings' dtype (emb_half).  inputs stay f32.  Sums land through atomics: run-to-run rounding differs. */
+int pn_grid_encode_backward(const void *grad, const float *inputs, const void *embeddings, const int *offsets,
+                            void *grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                            const void *dy_dx, void *grad_inputs, uint32_t gridtype, int align_corners, uint32_t interp,
+                            int emb_half, void *stream);
+/* gridencoder.h:15 + gridencoder.cu:639-645 grad_total_variation.  inputs [B,D] in [0,1] OF THE EMBEDDINGS' DTYPE (as the
+ * reference reads them); grad [sO,C] is accumulated into. */
+int pn_grad_total_variation(const void *inputs, const void *embeddings, void *grad, const int *offsets, float weight,
+                            uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                            int align_corners, int emb_half, void *stream);
 
 /* ---------------------------------------------------------------- A. _shencoder */
 /* shencoder/src/shencoder.h:7 + shencoder.cu:400-417 sh_encode_forward.
  * inputs [B,D>=3] f32; outputs [B,C*C] f32; C = degree in 1..8; dy_dx [B,D*C*C] or NULL. */
 int pn_sh_encode_forward(const float *inputs, float *outputs, uint32_t B, uint32_t D, uint32_t C, float *dy_dx,
                          void *stream);
-int pn_sh_encode_backward(void); /* shencoder.cu:419-438: training only */
+/* Training side: shencoder.h:10 + shencoder.cu:419-438 sh_encode_backward.  grad [B,C*C], dy_dx [B,D*C*C] as written by
+ * pn_sh_encode_forward (D must be 3 there); grad_inputs [B,D] is ACCUMULATED into (caller zeroes it), as in the reference. */
+int pn_sh_encode_backward(const float *grad, const float *inputs, uint32_t B, uint32_t D, uint32_t C, const float *dy_dx,
+                          float *grad_inputs, void *stream);
 
 /* ---------------------------------------------------------------- A. _raymarching */
 /* raymarching/src/raymarching.h:7 + raymarching.cu:151-159 */
@@ -78,10 +91,26 @@ int pn_march_rays_quadratic_bending(const int *pig_cnt, const int *pig_bgn, cons
                                     float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *grid,
                                     const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
                                     const float *noises, void *stream);
-/* raymarching.cu:485-493, 583-591, 688-696: training only. */
-int pn_march_rays_train(void);
-int pn_composite_rays_train_forward(void);
-int pn_composite_rays_train_backward(void);
+/* Training side.
+ * raymarching.h:13 + raymarching.cu:485-493 march_rays_train.  rays_o/rays_d [N,3], nears/fars/noises [N], grid = density
+ * bitfield; xyzs/dirs [M,3], deltas [M,2] (caller-zeroed), rays [N,3] i32 = (ray, offset, num_steps), counter [2] i32 =
+ * (points, rays), advanced as the reference's atomics advance it.  Packing is deterministic here: row n of `rays` is ray n
+ * and offsets ascend with n (the reference's order is the order its atomics retire in); a ray whose samples do not fit in M
+ * is dropped whole, as in the reference.  Three launches, no host synchronisation. */
+int pn_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                        uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
+                        const float *fars, float *xyzs, float *dirs, float *deltas, int *rays, int *counter,
+                        const float *noises, void *stream);
+/* raymarching.h:14 + raymarching.cu:583-591: sigmas [M], rgbs [M,3], deltas [M,2], rays [N,3] -> weights_sum/depth [N],
+ * image [N,3], indexed by rays[:,0]. */
+int pn_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas, const int *rays, uint32_t M,
+                                    uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image,
+                                    void *stream);
+/* raymarching.h:15 + raymarching.cu:688-696: grad_sigmas [M] / grad_rgbs [M,3] caller-zeroed; no depth gradient. */
+int pn_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
+                                     const float *rgbs, const float *deltas, const int *rays, const float *weights_sum,
+                                     const float *image, uint32_t M, uint32_t N, float T_thresh, float *grad_sigmas,
+                                     float *grad_rgbs, void *stream);
 
 /* ---------------------------------------------------------------- B. per-frame preparation */
 /* nerf/utils.py:55-138 get_rays (N=-1, B=1): pose_host = 16 floats row-major cam2world (HOST). */

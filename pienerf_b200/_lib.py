@@ -52,10 +52,10 @@ _PROTOS = {
     "pn_version": (i32, []),
     "pn_device_sm_count": (i32, [vp]),
     "pn_grid_encode_forward": (i32, [vp, vp, vp, vp, u32, u32, u32, u32, f32, u32, vp, u32, i32, u32, i32, vp]),
-    "pn_grid_encode_backward": (i32, []),
-    "pn_grad_total_variation": (i32, []),
+    "pn_grid_encode_backward": (i32, [vp, vp, vp, vp, vp, u32, u32, u32, u32, f32, u32, vp, vp, u32, i32, u32, i32, vp]),
+    "pn_grad_total_variation": (i32, [vp, vp, vp, vp, f32, u32, u32, u32, u32, f32, u32, u32, i32, i32, vp]),
     "pn_sh_encode_forward": (i32, [vp, vp, u32, u32, u32, vp, vp]),
-    "pn_sh_encode_backward": (i32, []),
+    "pn_sh_encode_backward": (i32, [vp, vp, u32, u32, u32, vp, vp, vp]),
     "pn_near_far_from_aabb": (i32, [vp, vp, vp, u32, f32, vp, vp, vp]),
     "pn_sph_from_ray": (i32, [vp, vp, f32, u32, vp, vp]),
     "pn_morton3D": (i32, [vp, u32, vp, vp]),
@@ -65,9 +65,9 @@ _PROTOS = {
     "pn_composite_rays": (i32, [u32, u32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pn_march_rays_quadratic_bending": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, f32, vp, i32, f32, i32, vp,
                                               u32, u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "pn_march_rays_train": (i32, []),
-    "pn_composite_rays_train_forward": (i32, []),
-    "pn_composite_rays_train_backward": (i32, []),
+    "pn_march_rays_train": (i32, [vp, vp, vp, f32, f32, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "pn_composite_rays_train_forward": (i32, [vp, vp, vp, vp, u32, u32, f32, vp, vp, vp, vp]),
+    "pn_composite_rays_train_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, f32, vp, vp, vp]),
     "pn_get_rays": (i32, [vp, f32, f32, f32, f32, u32, u32, vp, vp, vp]),
     "pn_build_ip_grid": (i32, [vp, i32, vp, f32, vp, i32, vp, vp, vp, vp]),
     "pn_ip_bbox": (i32, [vp, i32, f32, i32, f32, vp, vp, vp, vp]),

@@ -62,13 +62,28 @@ def march_rays_quadratic_bending(pig_cnt, pig_bgn, pig_idx, n_vtx, n_grid, p_def
         dptr(noises, "noises", f32), stream_ptr()))
 
 
-def march_rays_train(*args):
-    check(lib.pn_march_rays_train())
+def march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays,
+                     counter, noises):
+    """raymarching.cu:485-493; fp32 only (the reference's wrapper casts to float32, raymarching.py:165)."""
+    i32 = torch.int32
+    check(lib.pn_march_rays_train(dptr(rays_o, "rays_o", f32), dptr(rays_d, "rays_d", f32), dptr(grid, "grid", torch.uint8),
+                                  float(bound), float(dt_gamma), int(max_steps), int(N), int(C), int(H), int(M),
+                                  dptr(nears, "nears", f32), dptr(fars, "fars", f32), dptr(xyzs, "xyzs", f32),
+                                  dptr(dirs, "dirs", f32), dptr(deltas, "deltas", f32), dptr(rays, "rays", i32),
+                                  dptr(counter, "counter", i32), dptr(noises, "noises", f32), stream_ptr()))
 
 
-def composite_rays_train_forward(*args):
-    check(lib.pn_composite_rays_train_forward())
+def composite_rays_train_forward(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image):
+    check(lib.pn_composite_rays_train_forward(dptr(sigmas, "sigmas", f32), dptr(rgbs, "rgbs", f32), dptr(deltas, "deltas", f32),
+                                              dptr(rays, "rays", torch.int32), int(M), int(N), float(T_thresh),
+                                              dptr(weights_sum, "weights_sum", f32), dptr(depth, "depth", f32),
+                                              dptr(image, "image", f32), stream_ptr()))
 
 
-def composite_rays_train_backward(*args):
-    check(lib.pn_composite_rays_train_backward())
+def composite_rays_train_backward(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh,
+                                  grad_sigmas, grad_rgbs):
+    check(lib.pn_composite_rays_train_backward(
+        dptr(grad_weights_sum, "grad_weights_sum", f32), dptr(grad_image, "grad_image", f32), dptr(sigmas, "sigmas", f32),
+        dptr(rgbs, "rgbs", f32), dptr(deltas, "deltas", f32), dptr(rays, "rays", torch.int32),
+        dptr(weights_sum, "weights_sum", f32), dptr(image, "image", f32), int(M), int(N), float(T_thresh),
+        dptr(grad_sigmas, "grad_sigmas", f32), dptr(grad_rgbs, "grad_rgbs", f32), stream_ptr()))

@@ -7,7 +7,7 @@
 // One translation unit, compiled four times with -DPN_EXT_<NAME> (pienerf_b200/build_ext.py) and linked against
 // libpienerf_b200.so; no kernels live here.  Tensors are checked the way the reference checks them (CUDA + contiguous + dtype,
 // gridencoder.cu:15-18), every call enqueues on torch's current stream, a non-zero C-ABI return code becomes the exception the
-// reference's bindings raise (RuntimeError; NotImplementedError for the training-only entry points).
+// reference's bindings raise (RuntimeError; NotImplementedError for dtypes the library does not carry, e.g. fp64 tables).
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/util/Optional.h>
@@ -21,7 +21,7 @@ void *cur_stream() { return at::cuda::is_available() ? (void *)at::cuda::getCurr
 void pn_check(int rc) {
     if (rc == PN_OK) return;
     const char *msg = pn_last_error();
-    TORCH_CHECK_NOT_IMPLEMENTED(rc != PN_ENOTIMPL, msg && msg[0] ? msg : "training-only entry point");   // -> NotImplementedError
+    TORCH_CHECK_NOT_IMPLEMENTED(rc != PN_ENOTIMPL, msg && msg[0] ? msg : "not provided by the B200 library");   // -> NotImplementedError
     TORCH_CHECK(false, msg && msg[0] ? msg : "pienerf_b200 error");
 }
 
@@ -77,13 +77,47 @@ void grid_encode_forward(const at::Tensor inputs, const at::Tensor embeddings, c
     pn_check(pn_grid_encode_forward(inputs.data_ptr<float>(), embeddings.data_ptr(), offsets.data_ptr<int>(), outputs.data_ptr(), B, D, C, L, S, H,
                                     opt_ptr<void>(dy_dx), gridtype, align_corners ? 1 : 0, interp, half ? 1 : 0, cur_stream()));
 }
-void grid_encode_backward(py::args) { pn_check(pn_grid_encode_backward()); }
-void grad_total_variation(py::args) { pn_check(pn_grad_total_variation()); }
+inline bool table_is_half(const at::Tensor &embeddings) {
+    const bool half = embeddings.scalar_type() == at::ScalarType::Half;
+    TORCH_CHECK_NOT_IMPLEMENTED(half || embeddings.scalar_type() == at::ScalarType::Float, "embeddings must be a float32 or float16 tensor (no fp64 tables)");
+    return half;
+}
+inline void *same_dtype_ptr(const at::Tensor &x, const at::Tensor &like, const char *name) {
+    chk_cuda_contig(x, name);
+    TORCH_CHECK(x.scalar_type() == like.scalar_type(), name, " must have the dtype of embeddings");
+    return x.data_ptr();
+}
+// gridencoder.cu:473-503
+void grid_encode_backward(const at::Tensor grad, const at::Tensor inputs, const at::Tensor embeddings, const at::Tensor offsets, at::Tensor grad_embeddings,
+                          const uint32_t B, const uint32_t D, const uint32_t C, const uint32_t L, const float S, const uint32_t H,
+                          const c10::optional<at::Tensor> dy_dx, c10::optional<at::Tensor> grad_inputs, const uint32_t gridtype, const bool align_corners,
+                          const uint32_t interp) {
+    chk_cuda_contig(embeddings, "embeddings");
+    const bool half = table_is_half(embeddings);
+    const bool has_j = dy_dx.has_value() && dy_dx->defined(), has_gi = grad_inputs.has_value() && grad_inputs->defined();
+    TORCH_CHECK(has_j == has_gi, "dy_dx and grad_inputs go together");
+    TORCH_CHECK(C == 1 || C == 2 || C == 4 || C == 8, "GridEncoding: C must be 1, 2, 4, or 8.");
+    pn_check(pn_grid_encode_backward(same_dtype_ptr(grad, embeddings, "grad"), PN_F32(inputs), embeddings.data_ptr(), PN_I32(offsets),
+                                     same_dtype_ptr(grad_embeddings, embeddings, "grad_embeddings"), B, D, C, L, S, H,
+                                     has_j ? same_dtype_ptr(*dy_dx, embeddings, "dy_dx") : nullptr,
+                                     has_gi ? same_dtype_ptr(*grad_inputs, embeddings, "grad_inputs") : nullptr, gridtype, align_corners ? 1 : 0, interp,
+                                     half ? 1 : 0, cur_stream()));
+}
+// gridencoder.cu:639-645
+void grad_total_variation(const at::Tensor inputs, const at::Tensor embeddings, at::Tensor grad, const at::Tensor offsets, const float weight,
+                          const uint32_t B, const uint32_t D, const uint32_t C, const uint32_t L, const float S, const uint32_t H, const uint32_t gridtype,
+                          const bool align_corners) {
+    chk_cuda_contig(embeddings, "embeddings");
+    const bool half = table_is_half(embeddings);
+    TORCH_CHECK(C == 1 || C == 2 || C == 4 || C == 8, "GridEncoding: C must be 1, 2, 4, or 8.");
+    pn_check(pn_grad_total_variation(same_dtype_ptr(inputs, embeddings, "inputs"), embeddings.data_ptr(), same_dtype_ptr(grad, embeddings, "grad"),
+                                     PN_I32(offsets), weight, B, D, C, L, S, H, gridtype, align_corners ? 1 : 0, half ? 1 : 0, cur_stream()));
+}
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("grid_encode_forward", &grid_encode_forward, "grid_encode_forward (CUDA)");
-    m.def("grid_encode_backward", &grid_encode_backward, "grid_encode_backward (training only)");
-    m.def("grad_total_variation", &grad_total_variation, "grad_total_variation (training only)");
+    m.def("grid_encode_backward", &grid_encode_backward, "grid_encode_backward (CUDA)");
+    m.def("grad_total_variation", &grad_total_variation, "grad_total_variation (CUDA)");
 }
 #endif
 
@@ -92,11 +126,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 void sh_encode_forward(at::Tensor inputs, at::Tensor outputs, const uint32_t B, const uint32_t D, const uint32_t C, c10::optional<at::Tensor> dy_dx) {
     pn_check(pn_sh_encode_forward(PN_F32(inputs), PN_F32(outputs), B, D, C, opt_ptr<float>(dy_dx), cur_stream()));
 }
-void sh_encode_backward(py::args) { pn_check(pn_sh_encode_backward()); }
+// shencoder.cu:419-438
+void sh_encode_backward(at::Tensor grad, at::Tensor inputs, const uint32_t B, const uint32_t D, const uint32_t C, at::Tensor dy_dx, at::Tensor grad_inputs) {
+    pn_check(pn_sh_encode_backward(PN_F32(grad), PN_F32(inputs), B, D, C, PN_F32(dy_dx), PN_F32(grad_inputs), cur_stream()));
+}
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sh_encode_forward", &sh_encode_forward, "SH encode forward (CUDA)");
-    m.def("sh_encode_backward", &sh_encode_backward, "SH encode backward (training only)");
+    m.def("sh_encode_backward", &sh_encode_backward, "SH encode backward (CUDA)");
 }
 #endif
 
@@ -145,9 +182,31 @@ void march_rays_quadratic_bending(const at::Tensor pig_cnt, const at::Tensor pig
                                              PN_F32(rays_d), bound, dt_gamma, max_steps, C, H, (const uint8_t *)grid.data_ptr(), PN_F32(near), PN_F32(far),
                                              PN_F32(xyzs), PN_F32(dirs), PN_F32(deltas), PN_F32(noises), cur_stream()));
 }
-void march_rays_train(py::args) { pn_check(pn_march_rays_train()); }
-void composite_rays_train_forward(py::args) { pn_check(pn_composite_rays_train_forward()); }
-void composite_rays_train_backward(py::args) { pn_check(pn_composite_rays_train_backward()); }
+inline uint8_t *u8_ptr(const at::Tensor &x, const char *name) {
+    chk_cuda_contig(x, name);
+    TORCH_CHECK(x.scalar_type() == at::ScalarType::Byte, name, " must be a uint8 tensor");
+    return x.data_ptr<uint8_t>();
+}
+// raymarching.cu:485-493
+void march_rays_train(const at::Tensor rays_o, const at::Tensor rays_d, const at::Tensor grid, const float bound, const float dt_gamma,
+                      const uint32_t max_steps, const uint32_t N, const uint32_t C, const uint32_t H, const uint32_t M, const at::Tensor nears,
+                      const at::Tensor fars, at::Tensor xyzs, at::Tensor dirs, at::Tensor deltas, at::Tensor rays, at::Tensor counter, at::Tensor noises) {
+    pn_check(pn_march_rays_train(PN_F32(rays_o), PN_F32(rays_d), u8_ptr(grid, "grid"), bound, dt_gamma, max_steps, N, C, H, M, PN_F32(nears), PN_F32(fars),
+                                 PN_F32(xyzs), PN_F32(dirs), PN_F32(deltas), PN_I32(rays), PN_I32(counter), PN_F32(noises), cur_stream()));
+}
+// raymarching.cu:583-591
+void composite_rays_train_forward(const at::Tensor sigmas, const at::Tensor rgbs, const at::Tensor deltas, const at::Tensor rays, const uint32_t M,
+                                  const uint32_t N, const float T_thresh, at::Tensor weights_sum, at::Tensor depth, at::Tensor image) {
+    pn_check(pn_composite_rays_train_forward(PN_F32(sigmas), PN_F32(rgbs), PN_F32(deltas), PN_I32(rays), M, N, T_thresh, PN_F32(weights_sum),
+                                             PN_F32(depth), PN_F32(image), cur_stream()));
+}
+// raymarching.cu:688-696
+void composite_rays_train_backward(const at::Tensor grad_weights_sum, const at::Tensor grad_image, const at::Tensor sigmas, const at::Tensor rgbs,
+                                   const at::Tensor deltas, const at::Tensor rays, const at::Tensor weights_sum, const at::Tensor image, const uint32_t M,
+                                   const uint32_t N, const float T_thresh, at::Tensor grad_sigmas, at::Tensor grad_rgbs) {
+    pn_check(pn_composite_rays_train_backward(PN_F32(grad_weights_sum), PN_F32(grad_image), PN_F32(sigmas), PN_F32(rgbs), PN_F32(deltas), PN_I32(rays),
+                                              PN_F32(weights_sum), PN_F32(image), M, N, T_thresh, PN_F32(grad_sigmas), PN_F32(grad_rgbs), cur_stream()));
+}
 // extras over the reference module: the per-frame preparation the reference does with torch / Warp glue (nerf/utils.py:55-138,355-443)
 void get_rays(const at::Tensor pose_host, const float fx, const float fy, const float cx, const float cy, const uint32_t H, const uint32_t W,
               at::Tensor rays_o, at::Tensor rays_d) {
@@ -170,9 +229,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("morton3D", &morton3D, "morton3D (CUDA)");
     m.def("morton3D_invert", &morton3D_invert, "morton3D_invert (CUDA)");
     m.def("packbits", &packbits, "packbits (CUDA)");
-    m.def("march_rays_train", &march_rays_train, "march_rays_train (training only)");
-    m.def("composite_rays_train_forward", &composite_rays_train_forward, "composite_rays_train_forward (training only)");
-    m.def("composite_rays_train_backward", &composite_rays_train_backward, "composite_rays_train_backward (training only)");
+    m.def("march_rays_train", &march_rays_train, "march_rays_train (CUDA)");
+    m.def("composite_rays_train_forward", &composite_rays_train_forward, "composite_rays_train_forward (CUDA)");
+    m.def("composite_rays_train_backward", &composite_rays_train_backward, "composite_rays_train_backward (CUDA)");
     m.def("march_rays", &march_rays, "march rays (CUDA)");
     m.def("march_rays_quadratic_bending", &march_rays_quadratic_bending, "march rays through the quadratic GMLS warp (CUDA)");
     m.def("composite_rays", &composite_rays, "composite rays (CUDA)");

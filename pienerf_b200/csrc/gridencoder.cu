@@ -209,12 +209,3 @@ extern "C" int pn_grid_encode_forward(const float *inputs, const void *embedding
     return dispatch_D<float>(inputs, (const float *)embeddings, offsets, (float *)outputs, B, D, C, L, S, H,
                              (float *)dy_dx, gridtype, align_corners != 0, interp, st);
 }
-
-extern "C" int pn_grid_encode_backward(void) {
-    pn_set_error("grid_encode_backward is training-only and outside the B200 hot path (SURVEY.md 8f.4)");
-    return PN_ENOTIMPL;
-}
-extern "C" int pn_grad_total_variation(void) {
-    pn_set_error("grad_total_variation is training-only and outside the B200 hot path (SURVEY.md 8f.4)");
-    return PN_ENOTIMPL;
-}

@@ -299,16 +299,3 @@ extern "C" int pn_march_rays_quadratic_bending(
     PN_LAUNCH_CHECK("march_kernel<bend>");
     return PN_OK;
 }
-
-extern "C" int pn_march_rays_train(void) {
-    pn_set_error("march_rays_train is training-only and outside the B200 hot path (SURVEY.md 8f.4)");
-    return PN_ENOTIMPL;
-}
-extern "C" int pn_composite_rays_train_forward(void) {
-    pn_set_error("composite_rays_train_forward is training-only and outside the B200 hot path (SURVEY.md 8f.4)");
-    return PN_ENOTIMPL;
-}
-extern "C" int pn_composite_rays_train_backward(void) {
-    pn_set_error("composite_rays_train_backward is training-only and outside the B200 hot path (SURVEY.md 8f.4)");
-    return PN_ENOTIMPL;
-}

@@ -1,13 +1,34 @@
 // Real spherical harmonics Y_l^m(x,y,z) in Cartesian polynomial form, bands l = 0..DEG-1, written into
 // y[DEG*DEG] in the reference's output order (shencoder/src/shencoder.cu:49-123).  Term order inside each
 // polynomial matches the reference so fp32 results agree bit-for-bit under the same FMA contraction.
+//
+// sh_eval is a template over the scalar type: with T = float it is the forward encoder; with T = SHDual (a value and
+// one directional derivative, forward-mode differentiation) the same polynomials yield d Y / d x, d Y / d y, d Y / d z
+// (shencoder.cu:128-344 of the reference spells those 3 x 64 derivatives out by hand).
 #pragma once
 
 namespace pn {
 
-template <unsigned DEG>
-__device__ __forceinline__ void sh_eval(float x, float y, float z, float *__restrict__ o) {
-    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+struct SHDual {
+    float v, d;  // value, derivative along the seeded direction
+    __device__ __forceinline__ SHDual() {}
+    __device__ __forceinline__ SHDual(float c) : v(c), d(0.f) {}
+    __device__ __forceinline__ SHDual(float vv, float dd) : v(vv), d(dd) {}
+};
+__device__ __forceinline__ SHDual operator+(SHDual a, SHDual b) { return SHDual(a.v + b.v, a.d + b.d); }
+__device__ __forceinline__ SHDual operator-(SHDual a, SHDual b) { return SHDual(a.v - b.v, a.d - b.d); }
+__device__ __forceinline__ SHDual operator-(SHDual a) { return SHDual(-a.v, -a.d); }
+__device__ __forceinline__ SHDual operator*(SHDual a, SHDual b) { return SHDual(a.v * b.v, a.d * b.v + a.v * b.d); }
+__device__ __forceinline__ SHDual operator+(float a, SHDual b) { return SHDual(a + b.v, b.d); }
+__device__ __forceinline__ SHDual operator+(SHDual a, float b) { return SHDual(a.v + b, a.d); }
+__device__ __forceinline__ SHDual operator-(float a, SHDual b) { return SHDual(a - b.v, -b.d); }
+__device__ __forceinline__ SHDual operator-(SHDual a, float b) { return SHDual(a.v - b, a.d); }
+__device__ __forceinline__ SHDual operator*(float a, SHDual b) { return SHDual(a * b.v, a * b.d); }
+__device__ __forceinline__ SHDual operator*(SHDual a, float b) { return SHDual(a.v * b, a.d * b); }
+
+template <unsigned DEG, typename T = float>
+__device__ __forceinline__ void sh_eval(T x, T y, T z, T *__restrict__ o) {
+    const T xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
     o[0] = 0.28209479177387814f;
     if constexpr (DEG > 1) {
         o[1] = -0.48860251190291987f * y;
@@ -31,7 +52,7 @@ __device__ __forceinline__ void sh_eval(float x, float y, float z, float *__rest
         o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
     }
     if constexpr (DEG > 4) {
-        const float x4 = x2 * x2, y4 = y2 * y2, z4 = z2 * z2;
+        const T x4 = x2 * x2, y4 = y2 * y2, z4 = z2 * z2;
         o[16] = 2.5033429417967046f * xy * (x2 - y2);
         o[17] = 1.7701307697799304f * yz * (-3.0f * x2 + y2);
         o[18] = 0.94617469575756008f * xy * (7.0f * z2 - 1.0f);
@@ -55,7 +76,7 @@ __device__ __forceinline__ void sh_eval(float x, float y, float z, float *__rest
             o[35] = 0.65638205684017015f * x * (10.0f * x2 * y2 - x4 - 5.0f * y4);
         }
         if constexpr (DEG > 6) {
-            const float x6 = x4 * x2, y6 = y4 * y2, z6 = z4 * z2;
+            const T x6 = x4 * x2, y6 = y4 * y2, z6 = z4 * z2;
             o[36] = 1.3663682103838286f * xy * (-10.0f * x2 * y2 + 3.0f * x4 + 3.0f * y4);
             o[37] = 2.3666191622317521f * yz * (10.0f * x2 * y2 - 5.0f * x4 - y4);
             o[38] = 2.0182596029148963f * xy * (x2 - y2) * (11.0f * z2 - 1.0f);

@@ -1,10 +1,12 @@
-"""Host-side mirror of gridencoder/grid.py (GridEncoder, grid_encode) for the inference hot path.
+"""Host-side mirror of gridencoder/grid.py (GridEncoder, grid_encode).
 
-Same constructor arguments, attributes (`offsets`, `embeddings`, `per_level_scale`, ...) and call
-semantics as the reference module; forward only (backward/TV are training-side)."""
+Same constructor arguments, attributes (`offsets`, `embeddings`, `per_level_scale`, ...) and call semantics as the
+reference module, including the backward pass and the total-variation gradient (training side)."""
 import numpy as np
 import torch
 import torch.nn as nn
+from torch.amp import custom_bwd, custom_fwd
+from torch.autograd import Function
 
 from . import _gridencoder as _backend
 
@@ -12,24 +14,58 @@ _gridtype_to_id = {"hash": 0, "tiled": 1}
 _interp_to_id = {"linear": 0, "smoothstep": 1}
 
 
-@torch.no_grad()
+class _grid_encode(Function):
+    """grid.py:24-91: inputs [B,D] in [0,1] -> [B, L*C]; gradients to the table and (calc_grad_inputs) to the inputs."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0,
+                align_corners=False, interpolation=0, level_major=False):
+        inputs = inputs.to(torch.float32).contiguous()
+        B, D = inputs.shape
+        L = offsets.shape[0] - 1
+        C = embeddings.shape[1]
+        S = np.log2(per_level_scale)
+        H = base_resolution
+        if torch.is_autocast_enabled() and C % 2 == 0:           # grid.py:43-44
+            embeddings = embeddings.to(torch.half)
+        embeddings = embeddings.contiguous()
+        outputs = torch.empty(L, B, C, device=inputs.device, dtype=embeddings.dtype)
+        dy_dx = torch.empty(B, L * D * C, device=inputs.device, dtype=embeddings.dtype) if calc_grad_inputs else None
+        _backend.grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, dy_dx, gridtype, align_corners,
+                                     interpolation)
+        ctx.save_for_backward(inputs, embeddings, offsets, dy_dx)
+        ctx.dims = [B, D, C, L, S, H, gridtype, interpolation]
+        ctx.align_corners = align_corners
+        ctx.level_major = level_major
+        if level_major:                                          # the kernel's native [L,B,C] (used by the fused field)
+            return outputs
+        return outputs.permute(1, 0, 2).reshape(B, L * C)        # grid.py:57
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, grad):
+        inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
+        B, D, C, L, S, H, gridtype, interpolation = ctx.dims
+        if ctx.level_major:
+            grad = grad.contiguous()
+        else:
+            grad = grad.contiguous().view(B, L, C).permute(1, 0, 2).contiguous()   # [B, L*C] -> [L, B, C]
+        grad = grad.to(embeddings.dtype)
+        grad_embeddings = torch.zeros_like(embeddings)
+        grad_inputs = torch.zeros_like(inputs, dtype=embeddings.dtype) if dy_dx is not None else None
+        _backend.grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, dy_dx, grad_inputs,
+                                      gridtype, ctx.align_corners, interpolation)
+        if dy_dx is not None:
+            grad_inputs = grad_inputs.to(inputs.dtype)
+        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None, None
+
+
 def grid_encode(inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0,
                 align_corners=False, interpolation=0, level_major=False):
-    """grid.py:24-63 forward: inputs [B,D] in [0,1] -> [B, L*C] (or the kernel's native [L,B,C] if level_major)."""
-    inputs = inputs.to(torch.float32).contiguous()
-    B, D = inputs.shape
-    L = offsets.shape[0] - 1
-    C = embeddings.shape[1]
-    S = np.log2(per_level_scale)
-    if torch.is_autocast_enabled() and C % 2 == 0:           # grid.py:43-44
-        embeddings = embeddings.to(torch.half)
-    outputs = torch.empty(L, B, C, device=inputs.device, dtype=embeddings.dtype)
-    dy_dx = torch.empty(B, L * D * C, device=inputs.device, dtype=embeddings.dtype) if calc_grad_inputs else None
-    _backend.grid_encode_forward(inputs, embeddings.contiguous(), offsets, outputs, B, D, C, L, S, base_resolution, dy_dx,
-                                 gridtype, align_corners, interpolation)
-    if level_major:
-        return outputs
-    return outputs.permute(1, 0, 2).reshape(B, L * C)          # grid.py:57
+    """grid.py:93 `grid_encode = _grid_encode.apply`, with keyword arguments allowed."""
+    return _grid_encode.apply(inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs, gridtype,
+                              align_corners, interpolation, level_major)
 
 
 class GridEncoder(nn.Module):
@@ -82,8 +118,24 @@ class GridEncoder(nn.Module):
         prefix_shape = list(inputs.shape[:-1])
         inputs = inputs.view(-1, self.input_dim)
         outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
-                              False, self.gridtype_id, self.align_corners, self.interp_id)
+                              inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id)
         return outputs.view(prefix_shape + [self.output_dim])
 
-    def grad_total_variation(self, *args, **kwargs):
-        _backend.grad_total_variation()
+    @torch.autocast("cuda", enabled=False)
+    def grad_total_variation(self, weight=1e-7, inputs=None, bound=1, B=1000000):
+        """grid.py:163-190: adds the TV gradient at `inputs` (or B random points) to embeddings.grad, in full precision."""
+        D = self.input_dim
+        C = self.embeddings.shape[1]
+        L = self.offsets.shape[0] - 1
+        S = np.log2(self.per_level_scale)
+        H = self.base_resolution
+        if inputs is None:
+            inputs = torch.rand(B, self.input_dim, device=self.embeddings.device)
+        else:
+            inputs = (inputs + bound) / (2 * bound)
+            inputs = inputs.view(-1, self.input_dim)
+            B = inputs.shape[0]
+        if self.embeddings.grad is None:
+            raise ValueError('grad is None, should be called after loss.backward() and before optimizer.step()!')
+        _backend.grad_total_variation(inputs.to(self.embeddings.dtype).contiguous(), self.embeddings, self.embeddings.grad, self.offsets,
+                                      weight, B, D, C, L, S, H, self.gridtype_id, self.align_corners)

@@ -1,7 +1,10 @@
-"""Host-side mirror of raymarching/raymarching.py (inference functions) plus the two per-frame helpers the
+"""Host-side mirror of raymarching/raymarching.py (inference functions and the training pair march_rays_train /
+composite_rays_train) plus the two per-frame helpers the
 renderer takes from nerf/utils.py (get_rays, get_pnts_in_grids).  Same names, argument order, return values and
 caller-allocates-zeroed-outputs convention as the reference wrappers."""
 import torch
+from torch.amp import custom_bwd, custom_fwd
+from torch.autograd import Function
 
 from . import _raymarching as _backend
 from ._lib import check, dptr, lib, stream_ptr
@@ -128,12 +131,85 @@ def march_rays_quadratic_bending(pig_cnt, pig_bgn, pig_idx, n_vtx, n_grid, p_def
     return xyzs, dirs, deltas
 
 
-def _not_hot_path(*a, **k):
-    _backend.march_rays_train()
+# ---- training side ---------------------------------------------------------------------
+
+class _march_rays_train(Function):
+    """raymarching.py:163-235: forward only; returns (xyzs [M,3], dirs [M,3], deltas [M,2], rays [N,3])."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1, perturb=False,
+                align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024):
+        if not rays_o.is_cuda: rays_o = rays_o.cuda()
+        if not rays_d.is_cuda: rays_d = rays_d.cuda()
+        if not density_bitfield.is_cuda: density_bitfield = density_bitfield.cuda()
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        density_bitfield = density_bitfield.contiguous()
+        N = rays_o.shape[0]
+        M = N * max_steps
+        if not force_all_rays and mean_count > 0:            # running estimate of the sample count (raymarching.py:202-205)
+            if align > 0:
+                mean_count += align - mean_count % align
+            M = mean_count
+        xyzs = torch.zeros(M, 3, dtype=rays_o.dtype, device=rays_o.device)
+        dirs = torch.zeros(M, 3, dtype=rays_o.dtype, device=rays_o.device)
+        deltas = torch.zeros(M, 2, dtype=rays_o.dtype, device=rays_o.device)
+        rays = torch.empty(N, 3, dtype=torch.int32, device=rays_o.device)
+        if step_counter is None:
+            step_counter = torch.zeros(2, dtype=torch.int32, device=rays_o.device)
+        if perturb:
+            noises = torch.rand(N, dtype=rays_o.dtype, device=rays_o.device)
+        else:
+            noises = torch.zeros(N, dtype=rays_o.dtype, device=rays_o.device)
+        _backend.march_rays_train(rays_o, rays_d, density_bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears.contiguous(),
+                                  fars.contiguous(), xyzs, dirs, deltas, rays, step_counter, noises)
+        if force_all_rays or mean_count <= 0:                # first epochs: trim to the samples actually produced
+            m = step_counter[0].item()
+            if align > 0:
+                m += align - m % align
+            xyzs, dirs, deltas = xyzs[:m], dirs[:m], deltas[:m]
+        return xyzs, dirs, deltas, rays
 
 
-march_rays_train = _not_hot_path
-composite_rays_train = _not_hot_path
+march_rays_train = _march_rays_train.apply
+
+
+class _composite_rays_train(Function):
+    """raymarching.py:240-290: (sigmas [M], rgbs [M,3], deltas [M,2], rays [N,3]) -> weights_sum [N], depth [N], image [N,3]."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, sigmas, rgbs, deltas, rays, T_thresh=1e-4):
+        sigmas = sigmas.contiguous()
+        rgbs = rgbs.contiguous()
+        deltas = deltas.contiguous()
+        M = sigmas.shape[0]
+        N = rays.shape[0]
+        weights_sum = torch.empty(N, dtype=sigmas.dtype, device=sigmas.device)
+        depth = torch.empty(N, dtype=sigmas.dtype, device=sigmas.device)
+        image = torch.empty(N, 3, dtype=sigmas.dtype, device=sigmas.device)
+        _backend.composite_rays_train_forward(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image)
+        ctx.save_for_backward(sigmas, rgbs, deltas, rays, weights_sum, depth, image)
+        ctx.dims = [M, N, T_thresh]
+        return weights_sum, depth, image
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, grad_weights_sum, grad_depth, grad_image):
+        # the depth gradient is not propagated, as in the reference (raymarching.py:277)
+        grad_weights_sum = grad_weights_sum.contiguous()
+        grad_image = grad_image.contiguous()
+        sigmas, rgbs, deltas, rays, weights_sum, depth, image = ctx.saved_tensors
+        M, N, T_thresh = ctx.dims
+        grad_sigmas = torch.zeros_like(sigmas)
+        grad_rgbs = torch.zeros_like(rgbs)
+        _backend.composite_rays_train_backward(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N,
+                                               T_thresh, grad_sigmas, grad_rgbs)
+        return grad_sigmas, grad_rgbs, None, None, None
+
+
+composite_rays_train = _composite_rays_train.apply
 
 
 # ---- nerf/utils.py pieces of the hot path --------------------------------------------------------------

@@ -1,19 +1,43 @@
-"""Host-side mirror of shencoder/sphere_harmonics.py (SHEncoder) for the inference hot path."""
+"""Host-side mirror of shencoder/sphere_harmonics.py (SHEncoder, sh_encode with its backward pass)."""
 import torch
 import torch.nn as nn
+from torch.amp import custom_bwd, custom_fwd
+from torch.autograd import Function
 
 from . import _shencoder as _backend
 
 
-@torch.no_grad()
+class _sh_encoder(Function):
+    """sphere_harmonics.py:14-56: inputs [B,3] -> [B, degree**2] float32, with input gradients when asked for."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, inputs, degree, calc_grad_inputs=False):
+        inputs = inputs.to(torch.float32).contiguous()
+        B, input_dim = inputs.shape
+        outputs = torch.empty(B, degree ** 2, dtype=inputs.dtype, device=inputs.device)
+        dy_dx = torch.empty(B, input_dim * degree ** 2, dtype=inputs.dtype, device=inputs.device) if calc_grad_inputs else None
+        _backend.sh_encode_forward(inputs, outputs, B, input_dim, degree, dy_dx)
+        ctx.save_for_backward(inputs, dy_dx)
+        ctx.dims = [B, input_dim, degree]
+        return outputs
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, grad):
+        inputs, dy_dx = ctx.saved_tensors
+        if dy_dx is None:
+            return None, None, None
+        grad = grad.to(torch.float32).contiguous()
+        B, input_dim, degree = ctx.dims
+        grad_inputs = torch.zeros_like(inputs)
+        _backend.sh_encode_backward(grad, inputs, B, input_dim, degree, dy_dx, grad_inputs)
+        return grad_inputs, None, None
+
+
 def sh_encode(inputs, degree, calc_grad_inputs=False):
-    """sphere_harmonics.py:14-39 forward: inputs [B,3] -> [B, degree**2] float32."""
-    inputs = inputs.to(torch.float32).contiguous()
-    B, input_dim = inputs.shape
-    outputs = torch.empty(B, degree ** 2, dtype=inputs.dtype, device=inputs.device)
-    dy_dx = torch.empty(B, input_dim * degree ** 2, dtype=inputs.dtype, device=inputs.device) if calc_grad_inputs else None
-    _backend.sh_encode_forward(inputs, outputs, B, input_dim, degree, dy_dx)
-    return outputs
+    """sphere_harmonics.py:58 `sh_encode = _sh_encoder.apply`, with keyword arguments allowed."""
+    return _sh_encoder.apply(inputs, degree, calc_grad_inputs)
 
 
 class SHEncoder(nn.Module):
@@ -34,5 +58,5 @@ class SHEncoder(nn.Module):
         inputs = inputs / size
         prefix_shape = list(inputs.shape[:-1])
         inputs = inputs.reshape(-1, self.input_dim)
-        outputs = sh_encode(inputs, self.degree, False)
+        outputs = sh_encode(inputs, self.degree, inputs.requires_grad)
         return outputs.reshape(prefix_shape + [self.output_dim])

@@ -1,5 +1,5 @@
 """No-GPU checks of the drop-in boundary: the C-ABI library loads and exports exactly what include/*.h declares;
-training-only entry points refuse loudly; the drop-in module names resolve for the reference's wrappers."""
+training entry points validate their arguments without a GPU; the drop-in module names resolve for the reference's wrappers."""
 import ctypes
 import os
 import re
@@ -33,13 +33,31 @@ def test_header_cites_reference_for_every_entry_point():
         assert f in src, f
 
 
-def test_training_entry_points_refuse_without_gpu():
+def test_training_entry_points_validate_without_gpu():
+    """The training entry points are real kernels now: without a GPU they must refuse CPU tensors the way the
+    reference's CHECK_CUDA does, and the raw C-ABI must refuse null pointers instead of launching."""
+    import torch
     from pienerf_b200 import _gridencoder, _lib, _raymarching, _shencoder
-    for fn in (_gridencoder.grid_encode_backward, _gridencoder.grad_total_variation, _shencoder.sh_encode_backward,
-               _raymarching.march_rays_train, _raymarching.composite_rays_train_forward, _raymarching.composite_rays_train_backward):
-        with pytest.raises(NotImplementedError, match="training-only"):
-            fn()
-    assert _lib.lib.pn_grid_encode_backward() == _lib.PN_ENOTIMPL
+    x = torch.zeros(4, 3); e = torch.zeros(8, 2); o = torch.zeros(2, dtype=torch.int32); g = torch.zeros(1, 4, 2)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        _gridencoder.grid_encode_backward(g, x, e, o, e.clone(), 4, 3, 2, 1, 1.0, 16, None, None, 0, False, 0)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        _gridencoder.grad_total_variation(x, e, e.clone(), o, 1.0, 4, 3, 2, 1, 1.0, 16, 0, False)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        _shencoder.sh_encode_backward(torch.zeros(4, 16), x, 4, 3, 4, torch.zeros(4, 48), torch.zeros(4, 3))
+    r = torch.zeros(4, 3, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        _raymarching.march_rays_train(x, x, torch.zeros(8, dtype=torch.uint8), 1.0, 0.0, 16, 4, 1, 128, 64, x[:, 0], x[:, 0], x, x, x[:, :2], r,
+                                      torch.zeros(2, dtype=torch.int32), x[:, 0])
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        _raymarching.composite_rays_train_forward(x[:, 0], x, x[:, :2], r, 4, 4, 1e-4, x[:, 0], x[:, 0], x)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        _raymarching.composite_rays_train_backward(x[:, 0], x, x[:, 0], x, x[:, :2], r, x[:, 0], x, 4, 4, 1e-4, x[:, 0], x)
+    vp = lambda: _lib.vp(0)  # noqa: E731
+    assert _lib.lib.pn_grid_encode_backward(vp(), vp(), vp(), vp(), vp(), 4, 3, 2, 1, 1.0, 16, vp(), vp(), 0, 0, 0, 0, vp()) == -1   # PN_EINVAL
+    assert "null pointer" in _lib.last_error()
+    assert _lib.lib.pn_march_rays_train(vp(), vp(), vp(), 1.0, 0.0, 16, 4, 1, 128, 64, vp(), vp(), vp(), vp(), vp(), vp(), vp(), vp(), vp()) == -1
+    assert _lib.lib.pn_sh_encode_backward(vp(), vp(), 4, 3, 4, vp(), vp(), vp()) == -1
 
 
 def test_argument_validation_without_gpu():
@@ -70,10 +88,14 @@ def test_compiled_extension_modules_mirror_the_reference_bindings():
     for n, fns in want.items():
         for f in fns:
             assert callable(getattr(mods[n], f)), (n, f)
-    with pytest.raises(NotImplementedError, match="training-only"):
-        mods["_raymarching"].march_rays_train()
-    with pytest.raises(NotImplementedError, match="training-only"):
-        mods["_gridencoder"].grid_encode_backward(1, 2, 3)
+    x = torch.zeros(4, 3)
+    with pytest.raises(TypeError):
+        mods["_raymarching"].march_rays_train()                                                                # real entry point: positional signature enforced
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        mods["_gridencoder"].grid_encode_backward(torch.zeros(1, 4, 2), x, torch.zeros(8, 2), torch.zeros(2, dtype=torch.int32), torch.zeros(8, 2),
+                                                  4, 3, 2, 1, 1.0, 16, None, None, 0, False, 0)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        mods["_shencoder"].sh_encode_backward(torch.zeros(4, 16), x, 4, 3, 4, torch.zeros(4, 48), torch.zeros(4, 3))
     x = torch.zeros(4, 3)
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
         mods["_gridencoder"].grid_encode_forward(x, x, x.int(), x, 4, 3, 2, 1, 1.0, 16, None, 0, False, 0)

@@ -100,3 +100,60 @@ def test_dropin_prefers_compiled_modules_and_renders(ext):
     assert set(dropin.installed.values()) == {"pybind11"}
     assert sys.modules["_raymarching"].__file__.endswith("ext/_raymarching.so")
     dropin.install(compiled=False)
+
+
+def test_training_entry_points_equal_ctypes_modules(ext):
+    """The compiled modules' training entry points (gridencoder/shencoder/raymarching bindings.cpp of the reference) reach the
+    same C-ABI kernels as the ctypes modules: deterministic outputs are bit-equal, reduction outputs agree to reduction order."""
+    from pienerf_b200 import _gridencoder, _raymarching, _shencoder
+    from pienerf_b200.synthetic import grid_offsets
+    g = torch.Generator(device="cuda").manual_seed(3)
+    N = 2048
+    o = torch.zeros(N, 3, device="cuda"); o[:, 2] = -2.0
+    d = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda", generator=g) * 0.2 + torch.tensor([0.0, 0.0, 1.0], device="cuda"), dim=-1)
+    aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1], device="cuda")
+    nears = torch.empty(N, device="cuda"); fars = torch.empty(N, device="cuda")
+    _raymarching.near_far_from_aabb(o, d, aabb, N, 0.2, nears, fars)
+    bits = torch.randint(0, 256, (128 ** 3 // 8,), dtype=torch.uint8, device="cuda", generator=g)
+    noises = torch.rand(N, device="cuda", generator=g)
+    outs = []
+    for m in (_raymarching, ext["_raymarching"]):
+        M = N * 32
+        xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); deltas = torch.zeros(M, 2, device="cuda")
+        rays = torch.empty(N, 3, dtype=torch.int32, device="cuda"); counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+        m.march_rays_train(o, d, bits, 1.0, 0.0, 64, N, 1, 128, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises)
+        sig = xyzs.abs().sum(-1) * 20; rgb = torch.sigmoid(xyzs)
+        ws = torch.empty(N, device="cuda"); dep = torch.empty(N, device="cuda"); img = torch.empty(N, 3, device="cuda")
+        m.composite_rays_train_forward(sig, rgb, deltas, rays, M, N, 1e-3, ws, dep, img)
+        gs = torch.zeros(M, device="cuda"); gc = torch.zeros(M, 3, device="cuda")
+        m.composite_rays_train_backward(torch.ones(N, device="cuda"), torch.ones(N, 3, device="cuda"), sig, rgb, deltas, rays, ws, img, M, N, 1e-3, gs, gc)
+        outs.append((xyzs, dirs, deltas, rays, counter, ws, dep, img, gs, gc))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert int(outs[0][4][0]) > N and int(outs[0][4][1]) == N and float(outs[0][8].abs().max()) > 0
+
+    offsets, pls = grid_offsets(num_levels=8, desired_resolution=256, log2_hashmap_size=15)
+    emb = torch.rand(int(offsets[-1]), 2, device="cuda", generator=g) * 2 - 1
+    off = torch.from_numpy(offsets).cuda()
+    B = 20000; S = float(np.log2(pls))
+    x = torch.rand(B, 3, device="cuda", generator=g); grad = torch.randn(8, B, 2, device="cuda", generator=g)
+    out = torch.empty(8, B, 2, device="cuda"); dy_dx = torch.empty(B, 8 * 3 * 2, device="cuda")
+    _gridencoder.grid_encode_forward(x, emb, off, out, B, 3, 2, 8, S, 16, dy_dx, 0, False, 0)
+    res = []
+    for m in (_gridencoder, ext["_gridencoder"]):
+        ge = torch.zeros_like(emb); gi = torch.zeros(B, 3, device="cuda"); tv = torch.zeros_like(emb)
+        m.grid_encode_backward(grad, x, emb, off, ge, B, 3, 2, 8, S, 16, dy_dx, gi, 0, False, 0)
+        m.grad_total_variation(x, emb, tv, off, 1e-2, B, 3, 2, 8, S, 16, 0, False)
+        res.append((ge, gi, tv))
+    assert torch.equal(res[0][1], res[1][1])
+    assert float((res[0][0] - res[1][0]).abs().max()) < 1e-5 * float(res[0][0].abs().max())
+    assert float((res[0][2] - res[1][2]).abs().max()) < 1e-5 * float(res[0][2].abs().max())
+    dn = torch.nn.functional.normalize(torch.randn(B, 3, device="cuda", generator=g), dim=-1); gsh = torch.randn(B, 36, device="cuda", generator=g)
+    sh = []
+    for m in (_shencoder, ext["_shencoder"]):
+        y = torch.empty(B, 36, device="cuda"); j = torch.empty(B, 3 * 36, device="cuda"); gi = torch.zeros(B, 3, device="cuda")
+        m.sh_encode_forward(dn, y, B, 3, 6, j)
+        m.sh_encode_backward(gsh, dn, B, 3, 6, j, gi)
+        sh.append((y, j, gi))
+    for a, b in zip(*sh):
+        assert torch.equal(a, b)

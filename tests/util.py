@@ -55,3 +55,24 @@ def deformed_ip_state(body, seed=0, amp=0.02):
 def psnr(a, b):
     mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
     return 99.0 if mse == 0 else -10 * math.log10(mse)
+
+
+def repack_by_ray(xyzs, dirs, deltas, rays):
+    """march_rays_train outputs re-packed in ray order: rows of `rays` sorted by ray index, sample runs concatenated in that
+    order and re-based at 0.  The reference packs in the order its atomics retire (raymarching.cu:407-414); the oracle and the
+    CUDA library pack in ray order already, for them this is the identity (up to the trim to the samples produced)."""
+    order = np.argsort(rays[:, 0], kind="stable")
+    R = np.zeros_like(rays)
+    X, D, L = [], [], []
+    off = 0
+    for row, k in enumerate(order):
+        n, o, num = (int(v) for v in rays[k])
+        fits = num > 0 and o + num <= xyzs.shape[0]
+        R[row] = (n, off, num)
+        if fits:
+            X.append(xyzs[o:o + num]); D.append(dirs[o:o + num]); L.append(deltas[o:o + num])
+        elif num > 0:
+            X.append(np.zeros((num, 3), xyzs.dtype)); D.append(np.zeros((num, 3), dirs.dtype)); L.append(np.zeros((num, 2), deltas.dtype))
+        off += num
+    cat = lambda parts, w: np.concatenate(parts) if parts else np.zeros((0, w), np.float32)  # noqa: E731
+    return cat(X, 3), cat(D, 3), cat(L, 2), R
