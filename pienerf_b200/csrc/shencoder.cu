@@ -28,23 +28,16 @@ __global__ void __launch_bounds__(256) sh_forward(const float *__restrict__ in, 
     }
 }
 
-// dy_dx [B, 3, DEG*DEG]: row a holds d Y / d (x,y,z)[a].  The forward outputs are written from the float evaluation so
-// they stay bit-identical with and without the Jacobian.
+// dy_dx [B, 3, DEG*DEG]: row a holds d Y / d (x,y,z)[a].  The outputs themselves come from sh_forward (launched beside this
+// kernel), so they are bit-identical with and without the Jacobian.
 template <uint32_t DEG>
-__global__ void __launch_bounds__(128) sh_forward_jacobian(const float *__restrict__ in, float *__restrict__ out,
-                                                           float *__restrict__ dy_dx, uint32_t B, uint32_t D) {
+__global__ void __launch_bounds__(128) sh_forward_jacobian(const float *__restrict__ in, float *__restrict__ dy_dx, uint32_t B,
+                                                           uint32_t D) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     constexpr uint32_t C2 = DEG * DEG;
     const float *p = in + (size_t)b * D;
     const float x = p[0], y = p[1], z = p[2];
-    {
-        float v[C2];
-        pn::sh_eval<DEG>(x, y, z, v);
-        float *o = out + (size_t)b * C2;
-#pragma unroll
-        for (uint32_t i = 0; i < C2; i++) o[i] = v[i];
-    }
     float *j = dy_dx + (size_t)b * D * C2;
 #pragma unroll
     for (uint32_t a = 0; a < 3; a++) {
@@ -80,20 +73,19 @@ extern "C" int pn_sh_encode_forward(const float *inputs, float *outputs, uint32_
         PN_REQUIRE(D == 3, "SH input gradients expect D == 3 (dy_dx is [B, 3, C*C])");
         const uint32_t gj = div_up(B, 128u);
         switch (C) {
-            case 1: sh_forward_jacobian<1><<<gj, 128, 0, st>>>(inputs, outputs, dy_dx, B, D); break;
-            case 2: sh_forward_jacobian<2><<<gj, 128, 0, st>>>(inputs, outputs, dy_dx, B, D); break;
-            case 3: sh_forward_jacobian<3><<<gj, 128, 0, st>>>(inputs, outputs, dy_dx, B, D); break;
-            case 4: sh_forward_jacobian<4><<<gj, 128, 0, st>>>(inputs, outputs, dy_dx, B, D); break;
-            case 5: sh_forward_jacobian<5><<<gj, 128, 0, st>>>(inputs, outputs, dy_dx, B, D); break;
-            case 6: sh_forward_jacobian<6><<<gj, 128, 0, st>>>(inputs, outputs, dy_dx, B, D); break;
-            case 7: sh_forward_jacobian<7><<<gj, 128, 0, st>>>(inputs, outputs, dy_dx, B, D); break;
-            case 8: sh_forward_jacobian<8><<<gj, 128, 0, st>>>(inputs, outputs, dy_dx, B, D); break;
+            case 1: sh_forward_jacobian<1><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
+            case 2: sh_forward_jacobian<2><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
+            case 3: sh_forward_jacobian<3><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
+            case 4: sh_forward_jacobian<4><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
+            case 5: sh_forward_jacobian<5><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
+            case 6: sh_forward_jacobian<6><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
+            case 7: sh_forward_jacobian<7><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
+            case 8: sh_forward_jacobian<8><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
             default:
                 pn_set_error("SH encoder: degree must be in 1..8");
                 return PN_EINVAL;
         }
         PN_LAUNCH_CHECK("sh_forward_jacobian");
-        return PN_OK;
     }
     const uint32_t grid = div_up(B, 256u);
     switch (C) {

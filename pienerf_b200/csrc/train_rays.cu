@@ -5,10 +5,14 @@
 // march_rays_train is three launches on the caller's stream instead of the reference's one kernel with two global
 // atomics per ray:
 //   1. train_count_kernel  — one thread per ray walks the occupancy bitfield and counts its samples into rays[n] =
-//                            (n, -, num_steps);
-//   2. train_scan_kernel   — one 1024-thread CTA turns the counts into exclusive offsets (rays[n].offset) and advances
-//                            the (points, rays) counter the way the reference's atomics do;
-//   3. train_write_kernel  — one thread per ray repeats the walk and writes xyzs / dirs / deltas at its offset.
+//                            (-, t_first, num_steps), t_first = ray parameter of its first sample; each 128-ray CTA leaves
+//                            its total in the index slot of its first ray;
+//   2. train_scan_kernel   — one 1024-thread CTA turns the per-CTA totals into per-CTA base offsets (N/128 values, in
+//                            place) and advances the (points, rays) counter the way the reference's atomics do;
+//   3. train_write_kernel  — each CTA scans its 128 counts from its base, completes rays[n] = (n, offset, num_steps), and
+//                            every thread resumes its walk AT t_first writing xyzs / dirs / deltas at its offset: the empty
+//                            space in front of the object (most of a walk) is crossed once, not twice as in the reference.
+// No scratch memory: the index and offset columns of `rays` carry the partial sums and t_first between the launches.
 // The sample stream per ray is identical to the reference's (same float arithmetic through march_device.cuh); what
 // changes is the packing: ray n is row n of `rays` and the samples of ray n precede those of ray n+1, so the output
 // is the same on every run (the reference's order is whatever order its atomics retire in).
@@ -37,37 +41,116 @@ __device__ __forceinline__ TrainRay load_train_ray(const pn::MarchCfg &m, const 
     return r;
 }
 
-// Walks ray r.  WRITE=false: returns the number of occupied samples (capped at `limit`).  WRITE=true: emits the first
-// `limit` samples.  One loop body for both passes so the two walks cannot drift apart.
-template <bool WRITE>
-__device__ __forceinline__ uint32_t walk_ray(const pn::MarchCfg &m, const TrainRay &r, uint32_t limit, float *xyzs,
-                                             float *dirs, float *deltas) {
-    float t = r.t0, last_t = r.t0;
+// The voxel test of pn::occupancy_and_exit (march_device.cuh) split in two, same expressions: the exit distance is only
+// computed for an empty voxel, and with a single cascade (SINGLE) the mip level is 0 whatever the position and the step
+// (min(C-1, .) of raymarching.cu:42-54), which removes the two frexpf of the level selection from every step.
+struct Voxel { int nx, ny, nz; float mip_bound; };
+template <bool SINGLE>
+__device__ __forceinline__ bool voxel_occupied(const pn::MarchCfg &m, float x, float y, float z, float dt, Voxel &v) {
+    const int level = SINGLE ? 0 : pn::mip_level(m, x, y, z, dt);
+    v.mip_bound = fminf(scalbnf(1, level), m.bound);
+    const float mip_rbound = 1 / v.mip_bound;
+    const float Hm1 = (float)(m.H - 1);
+    v.nx = (int)pn::clampf(0.5f * (x * mip_rbound + 1) * m.H, 0.0f, Hm1);
+    v.ny = (int)pn::clampf(0.5f * (y * mip_rbound + 1) * m.H, 0.0f, Hm1);
+    v.nz = (int)pn::clampf(0.5f * (z * mip_rbound + 1) * m.H, 0.0f, Hm1);
+    const uint32_t index = (uint32_t)level * (uint32_t)(m.H * m.H * m.H) + pn::morton3(v.nx, v.ny, v.nz);
+    return m.bits[index >> 3] & (1 << (index & 7));
+}
+__device__ __forceinline__ float voxel_exit(const pn::MarchCfg &m, const Voxel &v, float x, float y, float z, float t,
+                                            const TrainRay &r) {
+    const float rH = 1 / (float)m.H;
+    const float tx = (((v.nx + 0.5f + 0.5f * copysignf(1.0f, r.dx)) * rH * 2 - 1) * v.mip_bound - x) * r.rdx;
+    const float ty = (((v.ny + 0.5f + 0.5f * copysignf(1.0f, r.dy)) * rH * 2 - 1) * v.mip_bound - y) * r.rdy;
+    const float tz = (((v.nz + 0.5f + 0.5f * copysignf(1.0f, r.dz)) * rH * 2 - 1) * v.mip_bound - z) * r.rdz;
+    return t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+}
+
+// A thread's samples are one contiguous run of floats per output array.  Stream4 turns that run into aligned 128-bit
+// stores (scalar stores only before the first and after the last 16-byte boundary): a sample's 3+3+2 floats would
+// otherwise be 8 separate 4-byte requests, each to a sector no other lane of the warp touches.
+struct Stream4 {
+    float *p;            // next float of the run
+    float b0, b1, b2, b3;  // the four floats pushed last (b3 newest)
+    uint32_t held;       // how many of them are not stored yet
+    __device__ __forceinline__ explicit Stream4(float *start) : p(start), b0(0), b1(0), b2(0), b3(0), held(0) {}
+    __device__ __forceinline__ void flush_scalar() {
+        if (held >= 3) p[-3] = b1;
+        if (held >= 2) p[-2] = b2;
+        if (held >= 1) p[-1] = b3;
+        held = 0;
+    }
+    __device__ __forceinline__ void push(float v) {
+        b0 = b1; b1 = b2; b2 = b3; b3 = v;
+        held++; p++;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {  // a 16-byte window just completed
+            if (held == 4) { *reinterpret_cast<float4 *>(p - 4) = make_float4(b0, b1, b2, b3); held = 0; }
+            else flush_scalar();  // the run started inside this window
+        }
+    }
+};
+
+// Walks ray r.  WRITE=false: returns the number of occupied samples (capped at `limit`) and the ray parameter of the
+// first one in t_first.  WRITE=true: starts AT t_first (the empty space in front of the object, most of the walk, was
+// crossed by the counting pass and need not be crossed again) and emits the first `limit` samples.  One loop body for
+// both passes so the two walks cannot drift apart.
+template <bool WRITE, bool SINGLE>
+__device__ __forceinline__ uint32_t walk_ray(const pn::MarchCfg &m, const TrainRay &r, uint32_t limit, float &t_first,
+                                             float *xyzs, float *dirs, float *deltas) {
+    float t = WRITE ? t_first : r.t0, last_t = r.t0;
     uint32_t step = 0;
+    Stream4 sx(xyzs), sd(dirs);
+    const bool pair = (reinterpret_cast<uintptr_t>(deltas) & 7) == 0;
     while (t < r.far && step < limit) {
         const float x = pn::clampf(r.ox + t * r.dx, -m.bound, m.bound);
         const float y = pn::clampf(r.oy + t * r.dy, -m.bound, m.bound);
         const float z = pn::clampf(r.oz + t * r.dz, -m.bound, m.bound);
         const float dt = pn::step_size(m, t);
-        float tt;
-        if (pn::occupancy_and_exit(m, x, y, z, t, dt, r.dx, r.dy, r.dz, r.rdx, r.rdy, r.rdz, tt)) {
+        Voxel v;
+        if (voxel_occupied<SINGLE>(m, x, y, z, dt, v)) {
+            if (!WRITE && step == 0) t_first = t;
             t += dt;
             if (WRITE) {
-                xyzs[0] = x; xyzs[1] = y; xyzs[2] = z;
-                dirs[0] = r.dx; dirs[1] = r.dy; dirs[2] = r.dz;
-                deltas[0] = dt;
-                deltas[1] = t - last_t;  // distance from the previous sample: what depth integrates
+                sx.push(x); sx.push(y); sx.push(z);
+                sd.push(r.dx); sd.push(r.dy); sd.push(r.dz);
+                const float dl = t - last_t;  // distance from the previous sample: what depth integrates
+                if (pair) *reinterpret_cast<float2 *>(deltas) = make_float2(dt, dl);
+                else { deltas[0] = dt; deltas[1] = dl; }
                 last_t = t;
-                xyzs += 3; dirs += 3; deltas += 2;
+                deltas += 2;
             }
             step++;
         } else {
+            const float tt = voxel_exit(m, v, x, y, z, t, r);
             do { t += pn::step_size(m, t); } while (t < tt);  // leave the empty voxel
         }
     }
+    if (WRITE) { sx.flush_scalar(); sd.flush_scalar(); }
     return step;
 }
 
+// inclusive scan over the kTrainBlock threads of a CTA; returns this thread's inclusive value, *total = CTA sum
+__device__ __forceinline__ uint32_t block_scan_inclusive(uint32_t v, uint32_t *warp_tot, uint32_t *total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (uint32_t)o) v += u;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kTrainBlock / 32; w++) {
+        const uint32_t t = warp_tot[w];
+        if ((uint32_t)w < warp) before += t;
+        all += t;
+    }
+    *total = all;
+    return v + before;
+}
+
+template <bool SINGLE>
 __global__ void __launch_bounds__(kTrainBlock) train_count_kernel(pn::MarchCfg m, uint32_t max_steps, uint32_t N,
                                                                   const float *__restrict__ rays_o,
                                                                   const float *__restrict__ rays_d,
@@ -75,23 +158,32 @@ __global__ void __launch_bounds__(kTrainBlock) train_count_kernel(pn::MarchCfg m
                                                                   const float *__restrict__ fars,
                                                                   const float *__restrict__ noises,
                                                                   int *__restrict__ rays) {
+    __shared__ uint32_t warp_tot[kTrainBlock / 32];
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const TrainRay r = load_train_ray(m, rays_o, rays_d, nears, fars, noises, n);
-    rays[3 * n] = (int)n;
-    rays[3 * n + 2] = (int)walk_ray<false>(m, r, max_steps, nullptr, nullptr, nullptr);
+    uint32_t num = 0;
+    if (n < N) {
+        const TrainRay r = load_train_ray(m, rays_o, rays_d, nears, fars, noises, n);
+        float t_first = r.t0;
+        num = walk_ray<false, SINGLE>(m, r, max_steps, t_first, nullptr, nullptr, nullptr);
+        rays[3 * n + 1] = __float_as_int(t_first);  // parked in the offset slot until the write pass replaces it
+        rays[3 * n + 2] = (int)num;
+    }
+    uint32_t total;
+    block_scan_inclusive(num, warp_tot, &total);
+    if (threadIdx.x == 0) rays[3 * n] = (int)total;  // CTA total, parked in the index slot of the CTA's first ray
 }
 
-// Exclusive scan of rays[:,2] into rays[:,1], starting at the incoming point counter; one CTA, each thread owns a
-// contiguous run of rays so the packing is ray-ordered.
+// Exclusive scan of the per-CTA totals (one per kTrainBlock rays) into per-CTA base offsets, in place, starting at the
+// incoming point counter; one CTA, each thread owns a contiguous run of totals.
 __global__ void __launch_bounds__(kScanThreads) train_scan_kernel(uint32_t N, int *__restrict__ rays,
                                                                   int *__restrict__ counter) {
     __shared__ uint32_t warp_tot[kScanThreads / 32];
     __shared__ uint32_t base_s;
-    const uint32_t per = div_up(N, (uint32_t)kScanThreads);
-    const uint32_t lo = min(N, threadIdx.x * per), hi = min(N, lo + per);
+    const uint32_t nb = div_up(N, (uint32_t)kTrainBlock);
+    const uint32_t per = div_up(nb, (uint32_t)kScanThreads);
+    const uint32_t lo = min(nb, threadIdx.x * per), hi = min(nb, lo + per);
     uint32_t mine = 0;
-    for (uint32_t n = lo; n < hi; n++) mine += (uint32_t)rays[3 * n + 2];
+    for (uint32_t b = lo; b < hi; b++) mine += (uint32_t)rays[3 * (size_t)b * kTrainBlock];
     uint32_t incl = mine;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -113,9 +205,11 @@ __global__ void __launch_bounds__(kScanThreads) train_scan_kernel(uint32_t N, in
     }
     __syncthreads();
     uint32_t off = base_s + (warp ? warp_tot[warp - 1] : 0u) + incl - mine;
-    for (uint32_t n = lo; n < hi; n++) {
-        rays[3 * n + 1] = (int)off;
-        off += (uint32_t)rays[3 * n + 2];
+    for (uint32_t b = lo; b < hi; b++) {
+        const size_t slot = 3 * (size_t)b * kTrainBlock;
+        const uint32_t tot = (uint32_t)rays[slot];
+        rays[slot] = (int)off;
+        off += tot;
     }
     if (threadIdx.x == kScanThreads - 1) {  // what the reference's atomicAdd(counter, num_steps) / (counter+1, 1) leave
         counter[0] = (int)(base_s + warp_tot[kScanThreads / 32 - 1]);
@@ -123,23 +217,48 @@ __global__ void __launch_bounds__(kScanThreads) train_scan_kernel(uint32_t N, in
     }
 }
 
+template <bool SINGLE>
 __global__ void __launch_bounds__(kTrainBlock) train_write_kernel(pn::MarchCfg m, uint32_t N, uint32_t M,
                                                                   const float *__restrict__ rays_o,
                                                                   const float *__restrict__ rays_d,
                                                                   const float *__restrict__ nears,
                                                                   const float *__restrict__ fars,
                                                                   const float *__restrict__ noises,
-                                                                  const int *__restrict__ rays, float *__restrict__ xyzs,
+                                                                  int *__restrict__ rays, float *__restrict__ xyzs,
                                                                   float *__restrict__ dirs, float *__restrict__ deltas) {
+    __shared__ uint32_t warp_tot[kTrainBlock / 32];
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t base = (uint32_t)rays[3 * (size_t)blockIdx.x * kTrainBlock];  // this CTA's first sample
+    const uint32_t num = n < N ? (uint32_t)rays[3 * n + 2] : 0u;
+    uint32_t total;
+    const uint32_t off = base + block_scan_inclusive(num, warp_tot, &total) - num;  // the barrier inside orders the read of `base`
     if (n >= N) return;
-    const uint32_t off = (uint32_t)rays[3 * n + 1], num = (uint32_t)rays[3 * n + 2];
+    float t_first = __int_as_float(rays[3 * n + 1]);
+    rays[3 * n] = (int)n;                   // the row is final from here: (ray, offset, num_steps)
+    rays[3 * n + 1] = (int)off;
     if (num == 0 || off + num > M) return;  // a ray that does not fit is dropped whole (raymarching.cu:418-419)
     const TrainRay r = load_train_ray(m, rays_o, rays_d, nears, fars, noises, n);
-    walk_ray<true>(m, r, num, xyzs + (size_t)off * 3, dirs + (size_t)off * 3, deltas + (size_t)off * 2);
+    walk_ray<true, SINGLE>(m, r, num, t_first, xyzs + (size_t)off * 3, dirs + (size_t)off * 3, deltas + (size_t)off * 2);
 }
 
-// One thread per ray: front-to-back accumulation; the early exit keeps the sample that crossed T_thresh.
+// Compositing: kRayLanes lanes per ray.  The lanes of a group load kRayLanes consecutive samples at a time (the packing is
+// ray-ordered, so a warp reads one contiguous stretch of sigmas / rgbs / deltas), then every lane replays the reference's
+// front-to-back recurrence over the group's samples through width-kRayLanes shuffles, in sample order: the arithmetic is the
+// reference's, operation for operation (T *= 1 - alpha, r += w * c, ... and the T_thresh exit after the sample that crossed
+// it), only the loads are cooperative.  A thread-per-ray loop reads 24 B per sample at a ~400 B stride between lanes.
+constexpr int kRayLanes = 8;
+constexpr int kRaysPerBlock = kTrainBlock / kRayLanes;
+
+struct RayRow { uint32_t index, offset, num; bool ok; };
+__device__ __forceinline__ RayRow load_ray_row(const int *__restrict__ rays, uint32_t n, uint32_t N, uint32_t M) {
+    RayRow r{0, 0, 0, false};
+    if (n < N) {
+        r.index = (uint32_t)rays[3 * n]; r.offset = (uint32_t)rays[3 * n + 1]; r.num = (uint32_t)rays[3 * n + 2];
+        r.ok = r.num != 0 && r.offset + r.num <= M;  // empty ray, or one that did not fit (raymarching.cu:524-531)
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(kTrainBlock) train_composite_fwd_kernel(const float *__restrict__ sigmas,
                                                                           const float *__restrict__ rgbs,
                                                                           const float *__restrict__ deltas,
@@ -148,57 +267,93 @@ __global__ void __launch_bounds__(kTrainBlock) train_composite_fwd_kernel(const 
                                                                           float *__restrict__ weights_sum,
                                                                           float *__restrict__ depth,
                                                                           float *__restrict__ image) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const uint32_t index = (uint32_t)rays[3 * n], offset = (uint32_t)rays[3 * n + 1], num = (uint32_t)rays[3 * n + 2];
-    float r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
-    if (num != 0 && offset + num <= M) {
-        const float *sg = sigmas + offset, *col = rgbs + (size_t)offset * 3, *del = deltas + (size_t)offset * 2;
-        float T = 1.0f;
-        for (uint32_t s = 0; s < num; s++) {
-            const float alpha = 1.0f - __expf(-sg[s] * del[2 * s]);
-            const float w = alpha * T;
-            r += w * col[3 * s]; g += w * col[3 * s + 1]; b += w * col[3 * s + 2];
-            t += del[2 * s + 1];
+    const uint32_t n = blockIdx.x * kRaysPerBlock + threadIdx.x / kRayLanes;
+    const uint32_t gl = threadIdx.x % kRayLanes;
+    const uint32_t gmask = ((1u << kRayLanes) - 1u) << ((threadIdx.x & 31) / kRayLanes * kRayLanes);
+    const RayRow row = load_ray_row(rays, n, N, M);
+    if (n >= N) return;  // whole groups leave together
+    float r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0, T = 1.0f;
+    bool done = !row.ok;
+    for (uint32_t c = 0; c < row.num && !done; c += kRayLanes) {
+        const uint32_t i = c + gl;
+        float alpha = 0, c0 = 0, c1 = 0, c2 = 0, d1 = 0;
+        if (i < row.num) {
+            const size_t s = (size_t)row.offset + i;
+            alpha = 1.0f - __expf(-sigmas[s] * deltas[2 * s]);
+            d1 = deltas[2 * s + 1];
+            c0 = rgbs[3 * s]; c1 = rgbs[3 * s + 1]; c2 = rgbs[3 * s + 2];
+        }
+        const uint32_t cnt = min((uint32_t)kRayLanes, row.num - c);
+        for (uint32_t k = 0; k < cnt; k++) {
+            const float a = __shfl_sync(gmask, alpha, k, kRayLanes);
+            const float w = a * T;
+            r += w * __shfl_sync(gmask, c0, k, kRayLanes);
+            g += w * __shfl_sync(gmask, c1, k, kRayLanes);
+            b += w * __shfl_sync(gmask, c2, k, kRayLanes);
+            t += __shfl_sync(gmask, d1, k, kRayLanes);
             d += w * t;
             ws += w;
-            T *= 1.0f - alpha;
-            if (T < T_thresh) break;
+            T *= 1.0f - a;
+            if (T < T_thresh) { done = true; break; }
         }
     }
-    weights_sum[index] = ws;
-    depth[index] = d;
-    image[3 * index] = r; image[3 * index + 1] = g; image[3 * index + 2] = b;
+    if (gl == 0) {
+        weights_sum[row.index] = ws;
+        depth[row.index] = d;
+        image[3 * row.index] = r; image[3 * row.index + 1] = g; image[3 * row.index + 2] = b;
+    }
 }
 
 // d(image, weights_sum)/d(sigma, rgb) with the forward recurrences replayed (no depth gradient, as in the reference).
+// Lane k of a group keeps the gradients of the group's k-th sample and stores them with its neighbours' (coalesced);
+// samples behind the T_thresh exit are not written (the caller zero-fills, raymarching.py:285-286).
 __global__ void __launch_bounds__(kTrainBlock) train_composite_bwd_kernel(
     const float *__restrict__ grad_weights_sum, const float *__restrict__ grad_image, const float *__restrict__ sigmas,
     const float *__restrict__ rgbs, const float *__restrict__ deltas, const int *__restrict__ rays,
     const float *__restrict__ weights_sum, const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
     float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const uint32_t index = (uint32_t)rays[3 * n], offset = (uint32_t)rays[3 * n + 1], num = (uint32_t)rays[3 * n + 2];
-    if (num == 0 || offset + num > M) return;
-    const float gws = grad_weights_sum[index];
-    const float gr = grad_image[3 * index], gg = grad_image[3 * index + 1], gb = grad_image[3 * index + 2];
-    const float r_final = image[3 * index], g_final = image[3 * index + 1], b_final = image[3 * index + 2];
-    const float ws_final = weights_sum[index];
-    const float *sg = sigmas + offset, *col = rgbs + (size_t)offset * 3, *del = deltas + (size_t)offset * 2;
-    float *gs = grad_sigmas + offset, *gc = grad_rgbs + (size_t)offset * 3;
+    const uint32_t n = blockIdx.x * kRaysPerBlock + threadIdx.x / kRayLanes;
+    const uint32_t gl = threadIdx.x % kRayLanes;
+    const uint32_t gmask = ((1u << kRayLanes) - 1u) << ((threadIdx.x & 31) / kRayLanes * kRayLanes);
+    const RayRow row = load_ray_row(rays, n, N, M);
+    if (n >= N || !row.ok) return;
+    const float gws = grad_weights_sum[row.index];
+    const float gr = grad_image[3 * row.index], gg = grad_image[3 * row.index + 1], gb = grad_image[3 * row.index + 2];
+    const float r_final = image[3 * row.index], g_final = image[3 * row.index + 1], b_final = image[3 * row.index + 2];
+    const float ws_final = weights_sum[row.index];
     float T = 1.0f, r = 0, g = 0, b = 0;
-    for (uint32_t s = 0; s < num; s++) {
-        const float d0 = del[2 * s];
-        const float alpha = 1.0f - __expf(-sg[s] * d0);
-        const float w = alpha * T;
-        const float c0 = col[3 * s], c1 = col[3 * s + 1], c2 = col[3 * s + 2];
-        r += w * c0; g += w * c1; b += w * c2;
-        T *= 1.0f - alpha;
-        gc[3 * s] = gr * w; gc[3 * s + 1] = gg * w; gc[3 * s + 2] = gb * w;
-        gs[s] = d0 * (gr * (T * c0 - (r_final - r)) + gg * (T * c1 - (g_final - g)) + gb * (T * c2 - (b_final - b)) +
-                      gws * (1 - ws_final));
-        if (T < T_thresh) break;
+    bool done = false;
+    for (uint32_t c = 0; c < row.num && !done; c += kRayLanes) {
+        const uint32_t i = c + gl;
+        const size_t s = (size_t)row.offset + i;
+        float alpha = 0, c0 = 0, c1 = 0, c2 = 0, d0 = 0;
+        if (i < row.num) {
+            d0 = deltas[2 * s];
+            alpha = 1.0f - __expf(-sigmas[s] * d0);
+            c0 = rgbs[3 * s]; c1 = rgbs[3 * s + 1]; c2 = rgbs[3 * s + 2];
+        }
+        const uint32_t cnt = min((uint32_t)kRayLanes, row.num - c);
+        bool mine = false;
+        float w_mine = 0, gs_mine = 0;
+        for (uint32_t k = 0; k < cnt; k++) {
+            const float a = __shfl_sync(gmask, alpha, k, kRayLanes);
+            const float w = a * T;
+            r += w * __shfl_sync(gmask, c0, k, kRayLanes);
+            g += w * __shfl_sync(gmask, c1, k, kRayLanes);
+            b += w * __shfl_sync(gmask, c2, k, kRayLanes);
+            T *= 1.0f - a;
+            if (gl == k) {
+                mine = true;
+                w_mine = w;
+                gs_mine = d0 * (gr * (T * c0 - (r_final - r)) + gg * (T * c1 - (g_final - g)) + gb * (T * c2 - (b_final - b)) +
+                                gws * (1 - ws_final));
+            }
+            if (T < T_thresh) { done = true; break; }
+        }
+        if (mine) {
+            grad_rgbs[3 * s] = gr * w_mine; grad_rgbs[3 * s + 1] = gg * w_mine; grad_rgbs[3 * s + 2] = gb * w_mine;
+            grad_sigmas[s] = gs_mine;
+        }
     }
 }
 
@@ -219,11 +374,13 @@ extern "C" int pn_march_rays_train(const float *rays_o, const float *rays_d, con
     m.dt_max = 2 * 1.7320508075688772f * (1 << (C - 1)) / H;
     m.cascade = (int)C; m.H = (int)H; m.bits = grid;
     const uint32_t blocks = div_up(N, (uint32_t)kTrainBlock);
-    train_count_kernel<<<blocks, kTrainBlock, 0, st>>>(m, max_steps, N, rays_o, rays_d, nears, fars, noises, rays);
+    if (C == 1) train_count_kernel<true><<<blocks, kTrainBlock, 0, st>>>(m, max_steps, N, rays_o, rays_d, nears, fars, noises, rays);
+    else train_count_kernel<false><<<blocks, kTrainBlock, 0, st>>>(m, max_steps, N, rays_o, rays_d, nears, fars, noises, rays);
     PN_LAUNCH_CHECK("train_count_kernel");
     train_scan_kernel<<<1, kScanThreads, 0, st>>>(N, rays, counter);
     PN_LAUNCH_CHECK("train_scan_kernel");
-    train_write_kernel<<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas);
+    if (C == 1) train_write_kernel<true><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas);
+    else train_write_kernel<false><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas);
     PN_LAUNCH_CHECK("train_write_kernel");
     return PN_OK;
 }
@@ -234,7 +391,7 @@ extern "C" int pn_composite_rays_train_forward(const float *sigmas, const float 
     if (N == 0) return PN_OK;
     PN_REQUIRE(rays && weights_sum && depth && image, "null pointer");
     PN_REQUIRE(M == 0 || (sigmas && rgbs && deltas), "null sample pointer");
-    train_composite_fwd_kernel<<<div_up(N, (uint32_t)kTrainBlock), kTrainBlock, 0, PN_STREAM(stream)>>>(
+    train_composite_fwd_kernel<<<div_up(N, (uint32_t)kRaysPerBlock), kTrainBlock, 0, PN_STREAM(stream)>>>(
         sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
     PN_LAUNCH_CHECK("train_composite_fwd_kernel");
     return PN_OK;
@@ -248,7 +405,7 @@ extern "C" int pn_composite_rays_train_backward(const float *grad_weights_sum, c
     if (N == 0 || M == 0) return PN_OK;
     PN_REQUIRE(grad_weights_sum && grad_image && rays && weights_sum && image, "null pointer");
     PN_REQUIRE(sigmas && rgbs && deltas && grad_sigmas && grad_rgbs, "null sample pointer");
-    train_composite_bwd_kernel<<<div_up(N, (uint32_t)kTrainBlock), kTrainBlock, 0, PN_STREAM(stream)>>>(
+    train_composite_bwd_kernel<<<div_up(N, (uint32_t)kRaysPerBlock), kTrainBlock, 0, PN_STREAM(stream)>>>(
         grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
     PN_LAUNCH_CHECK("train_composite_bwd_kernel");
     return PN_OK;

