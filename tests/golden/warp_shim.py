@@ -97,6 +97,13 @@ float64 = np.float64
 float32 = np.float32
 int32 = np.int32
 vec2i = vec(2, np.int32)
+vec3i = vec(3, np.int32)
+vec3f = vec(3, np.float32)
+
+# main_sample.py indexes one past the end of its arrays for the last lattice point of every row (see
+# pienerf_b200/sampling.py): with OOB_TOLERANT set, such writes are dropped and such reads return 0, the model
+# "the memory behind the array is zero and nobody else's" that the reference silently relies on.
+OOB_TOLERANT = False
 
 
 # ----------------------------------------------------------------------------------------------- arrays
@@ -114,12 +121,16 @@ class WpArray:
         return self
 
     def __getitem__(self, idx):
+        if OOB_TOLERANT and np.ndim(idx) == 0 and not (0 <= int(idx) < self.data.shape[0]):
+            return np.zeros(self.elem, self.data.dtype).view(self.kind) if self.kind is not None else self.data.dtype.type(0)
         v = self.data[idx]
         if self.kind is not None and isinstance(v, np.ndarray) and v.shape == self.elem:
             return v.view(self.kind)
         return v
 
     def __setitem__(self, idx, val):
+        if OOB_TOLERANT and np.ndim(idx) == 0 and not (0 <= int(idx) < self.data.shape[0]):
+            return
         self.data[idx] = np.asarray(val)
 
 
@@ -157,6 +168,14 @@ def to_torch(a):
 # ----------------------------------------------------------------------------------------------- builtins
 def tid():
     return _tid
+
+
+def floor(x):
+    return np.floor(x)
+
+
+def printf(*a):
+    pass
 
 
 def dot(a, b):
@@ -228,6 +247,8 @@ def launch(kernel, dim, inputs, outputs=(), device=None, **kw):
             a = ann(_scalar(a))                                          # scalars are converted to the declared type at launch
         elif ann is np.int32:
             a = np.int32(_scalar(a))
+        elif isinstance(ann, type) and issubclass(ann, Vec) and isinstance(a, torch.Tensor):
+            a = ann(*a.tolist())                                         # a torch tensor passed for a wp.vec3f parameter
         args.append(a)
     n = int(np.prod(_shape_tuple(dim)))
     f = kernel.f
@@ -259,10 +280,59 @@ def create_meshgrid3d(depth, height, width, normalized_coordinates=True, device=
     return base.permute(0, 2, 1, 3).unsqueeze(0)                                  # 1 x D x H x W x 3
 
 
+def _is_cuda(d):
+    return d is not None and str(d).startswith("cuda")
+
+
+def _cpu_only_factories():
+    """device="cuda" / .to("cuda:0") mean "this machine's device" in the reference; here that is the CPU."""
+    if getattr(torch, "_pn_cpu_only", False):
+        return
+    torch._pn_cpu_only = True
+    for name in ("zeros", "ones", "empty", "full", "rand", "randn", "tensor", "arange", "linspace", "zeros_like", "ones_like", "eye"):
+        orig = getattr(torch, name)
+
+        def wrapped(*a, _orig=orig, **k):
+            if _is_cuda(k.get("device")):
+                k["device"] = "cpu"
+            return _orig(*a, **k)
+        setattr(torch, name, wrapped)
+    orig_to = torch.Tensor.to
+
+    def to(self, *a, **k):
+        a = tuple("cpu" if isinstance(x, (str, torch.device)) and _is_cuda(x) else x for x in a)
+        if _is_cuda(k.get("device")):
+            k["device"] = "cpu"
+        return orig_to(self, *a, **k)
+    torch.Tensor.to = to
+
+
+def stub_missing_modules(names):
+    """Permissive stand-ins for third-party modules the reference imports at module scope but the exercised code never calls
+    (imageio, cv2, trimesh, lpips, ... in nerf/utils.py): attribute access yields a dummy class."""
+    import importlib
+
+    class _Stub(types.ModuleType):
+        def __getattr__(self, item):
+            if item.startswith("__"):
+                raise AttributeError(item)
+            return type(item, (), {"__init__": lambda self, *a, **k: None})
+    for n in names:
+        try:
+            importlib.import_module(n)
+        except Exception:
+            parts = n.split(".")
+            for i in range(1, len(parts) + 1):
+                sub = ".".join(parts[:i])
+                if sub not in sys.modules:
+                    sys.modules[sub] = _Stub(sub)
+                    sys.modules[sub].__path__ = []
+
+
 def install(reference_root="/root/reference"):
     """Register the stand-in modules and make torch CPU-only.  Call BEFORE importing `simulator.*`."""
     wp = types.ModuleType("warp")
-    for name in ("vec", "mat", "float64", "float32", "int32", "vec2i", "zeros", "array", "from_torch", "to_torch", "tid", "dot",
+    for name in ("vec", "mat", "float64", "float32", "int32", "vec2i", "vec3i", "vec3f", "floor", "printf", "zeros", "array", "from_torch", "to_torch", "tid", "dot",
                  "length", "outer", "identity", "transpose", "atomic_add", "svd3", "func", "kernel", "launch", "synchronize",
                  "set_device", "init"):
         setattr(wp, name, globals()[name])
@@ -276,6 +346,7 @@ def install(reference_root="/root/reference"):
     sys.modules["plyfile"] = ply
     torch.set_default_device = lambda *a, **k: None
     torch.Tensor.cuda = lambda self, *a, **k: self
+    _cpu_only_factories()
     if reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     return wp

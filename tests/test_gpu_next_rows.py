@@ -144,3 +144,37 @@ def test_wavefront_edge_cases():
     a = model.render_deformed(ro_, rd_, mode=3, **opt3); sa = int(a["stats"][0]); ia = a["image"].clone()
     b = model.render_deformed(ro_, rd_, mode=0, **opt3)
     assert sa == int(b["stats"][0]) and torch.equal(torch.nan_to_num(ia), torch.nan_to_num(b["image"]))
+
+
+def test_point_sampling_on_the_gpu(tmp_path):
+    """SURVEY 8f.4 point sampling (pienerf_b200/sampling.py; bit-for-bit parity with the reference's main_sample.py is the CPU test
+    tests/test_sampling.py).  Here: the same torch code on cuda:0 reproduces the reference's point set up to the handful of lattice
+    points whose density sits at the threshold (CUDA vs CPU expf), and it runs on a real NeRFNetwork.density."""
+    import argparse
+    import os
+    from pienerf_b200.ply import read_ply_vertices
+    from pienerf_b200.sampling import AdaptiveUniformSampling
+    from tests.sampling_cases import CASES, BlobField
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_sampling.npz"))
+    o = dict(CASES["a"]); opt = argparse.Namespace(**o)
+    offsets = torch.rand((64, 3), dtype=torch.float32, generator=torch.Generator().manual_seed(5))
+    cpu_p, cpu_v = AdaptiveUniformSampling(opt, BlobField(), device="cpu").sample(write=False, points_tmp=offsets)
+    gpu_p, gpu_v = AdaptiveUniformSampling(opt, BlobField(), device="cuda:0").sample(write=False, points_tmp=offsets)
+    assert abs(gpu_p.shape[0] - cpu_p.shape[0]) <= 0.01 * cpu_p.shape[0] and abs(gpu_p.shape[0] - G["a_points"].shape[0]) <= 0.02 * cpu_p.shape[0]
+    a = {tuple(np.round(r, 5)) for r in cpu_p.numpy()}; b = {tuple(np.round(r, 5)) for r in gpu_p.cpu().numpy()}
+    assert len(a & b) >= 0.98 * len(a)
+    # a real field: the synthetic hash-grid + MLP of the render tests, through NeRFNetwork.density (CUDA hash-grid kernel)
+    model = _model()[0]
+    opt2 = argparse.Namespace(**dict(o, density_threshold=0.02, workspace="ws/field", exp_name="pts"))
+    s = AdaptiveUniformSampling(opt2, model, out_dir=str(tmp_path))
+    dens = s.get_density(s._lattice())
+    if float(dens.max()) <= opt2.density_threshold:
+        pytest.skip("synthetic field has no density above the threshold on this lattice")
+    try:
+        pts, vols = s.sample()
+    except AssertionError as e:                       # a random-init field may have a flat density: no boundary points
+        assert "No boundary points" in str(e) or "No points" in str(e)
+        return
+    assert float(s.get_density(pts).min()) > opt2.density_threshold and float(vols.min()) > 0
+    ply = read_ply_vertices(os.path.join(str(tmp_path), "field", "pts.ply"))
+    assert ply["x"].shape[0] == pts.shape[0] and np.allclose(ply["vp"], vols.cpu().numpy().astype(np.float64))
