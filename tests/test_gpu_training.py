@@ -325,3 +325,40 @@ def test_training_entry_points_validate_arguments():
     be.composite_rays_train_forward(torch.zeros(0, device="cuda"), torch.zeros(0, 3, device="cuda"), torch.zeros(0, 2, device="cuda"),
                                     torch.zeros(0, 3, dtype=torch.int32, device="cuda"), 0, 0, 1e-4, torch.zeros(0, device="cuda"),
                                     torch.zeros(0, device="cuda"), torch.zeros(0, 3, device="cuda"))
+
+
+@pytest.mark.parametrize("bound,dt_gamma", [(1.0, 0.0), (2.0, 1.0 / 128)])
+def test_march_rays_train_full_frame_vs_reference_kernel(bound, dt_gamma):
+    """800x800 rays through the chair-sized body against the reference's own kernel: every ray has the reference's sample count and
+    its samples are bit-identical (positions, directions, deltas), for one and for two cascades.  The comparison gathers each ray's run
+    from both packings on the GPU (the reference's offsets are in atomic order, ours in ray order)."""
+    rr = load_ref("_ref_raymarching")
+    if rr is None:
+        pytest.skip("oracle/_ref not built")
+    import pienerf_b200._raymarching as be
+    from pienerf_b200 import raymarching as rm
+    from pienerf_b200.synthetic import make_body, occupancy_bitfield, orbit_intrinsics, orbit_pose
+    body = make_body("chair2k", dx=0.05, bound=1.0, seed=0)
+    bits = _gpu(occupancy_bitfield(body["pos"], 0.03, bound=bound))
+    C = 1 if bound <= 1 else 2
+    W = H = 800
+    rays = rm.get_rays(torch.from_numpy(orbit_pose(radius=2.5).astype(np.float32))[None], orbit_intrinsics(W, H, 50.0), H, W)
+    o = rays["rays_o"][0].contiguous(); d = rays["rays_d"][0].contiguous(); N = o.shape[0]
+    nears, fars = rm.near_far_from_aabb(o, d, torch.tensor([-bound] * 3 + [bound] * 3, device="cuda"), 0.2)
+    noises = torch.rand(N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    M = N * 24
+    res = []
+    for m in (be, rr):
+        xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); deltas = torch.zeros(M, 2, device="cuda")
+        rt = torch.empty(N, 3, dtype=torch.int32, device="cuda"); counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+        m.march_rays_train(o, d, bits, bound, dt_gamma, 1024, N, C, 128, M, nears, fars, xyzs, dirs, deltas, rt, counter, noises)
+        res.append((xyzs, dirs, deltas, rt, counter))
+    (x0, d0, l0, r0, c0), (x1, d1, l1, r1, c1) = res
+    assert torch.equal(c0, c1) and int(c0[0]) <= M and int(c0[0]) > 5_000_000
+    r1s = r1[torch.argsort(r1[:, 0].long())]                      # the reference's rows, by ray
+    assert torch.equal(r0[:, 0], r1s[:, 0]) and torch.equal(r0[:, 2], r1s[:, 2])
+    num = r0[:, 2].long()
+    ray_of = torch.repeat_interleave(torch.arange(N, device="cuda"), num)
+    within = torch.arange(int(num.sum()), device="cuda") - torch.repeat_interleave(torch.cumsum(num, 0) - num, num)
+    i0 = r0[:, 1].long()[ray_of] + within; i1 = r1s[:, 1].long()[ray_of] + within
+    assert torch.equal(x0[i0], x1[i1]) and torch.equal(d0[i0], d1[i1]) and torch.equal(l0[i0], l1[i1])
