@@ -101,6 +101,9 @@ int pn_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t 
                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
                         const float *fars, float *xyzs, float *dirs, float *deltas, int *rays, int *counter,
                         const float *noises, void *stream);
+/* A/B switch for march_rays_train's empty-space skipping over 8^3 / 4^3 voxel blocks (single cascade; on by default).  The samples
+ * are the reference's either way (tests assert bit-equality both ways); returns the previous setting. */
+int pn_set_train_block_skip(int on);
 /* raymarching.h:14 + raymarching.cu:583-591: sigmas [M], rgbs [M,3], deltas [M,2], rays [N,3] -> weights_sum/depth [N],
  * image [N,3], indexed by rays[:,0]. */
 int pn_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas, const int *rays, uint32_t M,

@@ -66,6 +66,52 @@ __device__ __forceinline__ float voxel_exit(const pn::MarchCfg &m, const Voxel &
     return t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
 }
 
+// Empty-space skipping over aligned 8^3 / 4^3 blocks of voxels, with the reference's result (single cascade only).
+//
+// The reference leaves an empty voxel by advancing t along its lattice (t += dt) until t >= tt, tt = the voxel's exit
+// (voxel_exit), and repeats per voxel.  The lattice does not depend on the voxels, only the landing points do; through a
+// run of empty voxels the only landing that matters is the last one, the first lattice point past the exit E of the run.
+// In Morton order an aligned 8^3 block is 64 contiguous bytes of the bitfield (an aligned 4^3 block 8 bytes), so "the
+// whole block is empty" is one 64-byte read, and the block's exit plane is the exit plane of its last voxel — the same
+// float value the per-voxel chain would use.  What differs is rounding: the chain computes its last tt from a later
+// landing point, the float position crosses the plane within an ulp or two of where the real one does.  block_exit
+// therefore returns an interval [lo, hi] that contains every value the chain's last tt can take (and the parameters at
+// which the float position can cross any of the three planes the ray is heading for); the walk advances to the first
+// lattice point >= lo, and only accepts it when it is also >= hi.  A lattice point inside [lo, hi) — a knife edge, a few
+// 1e-4 of the skips — sends the walk back to the block's entry to take the reference's per-voxel step instead.
+// Margins: position 4e-6 (>= 10x the rounding of o + t*d and of the voxel index expression at |x| <= 8), time 4e-6*(1+t).
+struct Span { float lo, hi; };
+__device__ __forceinline__ Span block_exit(const pn::MarchCfg &m, const Voxel &v, int log2b, float x, float y, float z, float t,
+                                           const TrainRay &r) {
+    const float rH = 1 / (float)m.H;
+    const int keep = ~((1 << log2b) - 1), size = 1 << log2b;
+    const float px = (float)((v.nx & keep) + (copysignf(1.0f, r.dx) > 0 ? size : 0));
+    const float py = (float)((v.ny & keep) + (copysignf(1.0f, r.dy) > 0 ? size : 0));
+    const float pz = (float)((v.nz & keep) + (copysignf(1.0f, r.dz) > 0 ? size : 0));
+    const float tx = ((px * rH * 2 - 1) * v.mip_bound - x) * r.rdx;
+    const float ty = ((py * rH * 2 - 1) * v.mip_bound - y) * r.rdy;
+    const float tz = ((pz * rH * 2 - 1) * v.mip_bound - z) * r.rdz;
+    const float et = 4e-6f * (1.0f + t);
+    const float ex = 4e-6f * fabsf(r.rdx) + et, ey = 4e-6f * fabsf(r.rdy) + et, ez = 4e-6f * fabsf(r.rdz) + et;
+    // an axis the ray is parallel to gives inf - inf = NaN here; fminf drops it, as it drops the reference's NaN exits
+    Span s;
+    s.lo = t + fmaxf(0.0f, fminf(tx - ex, fminf(ty - ey, tz - ez)));
+    s.hi = t + fmaxf(0.0f, fminf(tx + ex, fminf(ty + ey, tz + ez))) + et;
+    return s;
+}
+// 0: no skip; 3: the 8^3 block around voxel v is empty; 2: its 4^3 sub-block is
+__device__ __forceinline__ int empty_block(const pn::MarchCfg &m, const Voxel &v) {
+    const uint32_t index = pn::morton3(v.nx, v.ny, v.nz);
+    const uint4 *blk = reinterpret_cast<const uint4 *>(m.bits + ((index & ~511u) >> 3));
+    const uint4 a = __ldg(blk), b = __ldg(blk + 1), c = __ldg(blk + 2), d = __ldg(blk + 3);
+    const uint32_t any = (a.x | a.y | a.z | a.w) | (b.x | b.y | b.z | b.w) | (c.x | c.y | c.z | c.w) | (d.x | d.y | d.z | d.w);
+    if (any == 0) return 3;
+    const uint32_t sub = (index >> 6) & 7;  // which 64-bit word pair of the 16 words
+    const uint4 q = sub < 2 ? a : sub < 4 ? b : sub < 6 ? c : d;
+    const uint32_t w = (sub & 1) ? (q.z | q.w) : (q.x | q.y);
+    return w == 0 ? 2 : 0;
+}
+
 // A thread's samples are one contiguous run of floats per output array.  Stream4 turns that run into aligned 128-bit
 // stores (scalar stores only before the first and after the last 16-byte boundary): a sample's 3+3+2 floats would
 // otherwise be 8 separate 4-byte requests, each to a sector no other lane of the warp touches.
@@ -94,18 +140,21 @@ struct Stream4 {
 // first one in t_first.  WRITE=true: starts AT t_first (the empty space in front of the object, most of the walk, was
 // crossed by the counting pass and need not be crossed again) and emits the first `limit` samples.  One loop body for
 // both passes so the two walks cannot drift apart.
-template <bool WRITE, bool SINGLE>
-__device__ __forceinline__ uint32_t walk_ray(const pn::MarchCfg &m, const TrainRay &r, uint32_t limit, float &t_first,
-                                             float *xyzs, float *dirs, float *deltas) {
+// FIXED: dt_gamma == 0, the step is the same at every t (clamp(t * 0, dt_min, dt_max)), so the lattice loops are one add and
+// one compare per point instead of recomputing the clamp.
+template <bool WRITE, bool SINGLE, bool FIXED>
+__device__ __forceinline__ uint32_t walk_ray_impl(const pn::MarchCfg &m, const TrainRay &r, uint32_t limit, float &t_first,
+                                                  float *xyzs, float *dirs, float *deltas, bool blocks) {
     float t = WRITE ? t_first : r.t0, last_t = r.t0;
     uint32_t step = 0;
     Stream4 sx(xyzs), sd(dirs);
     const bool pair = (reinterpret_cast<uintptr_t>(deltas) & 7) == 0;
+    const float dt_fixed = pn::step_size(m, 0.0f);
     while (t < r.far && step < limit) {
         const float x = pn::clampf(r.ox + t * r.dx, -m.bound, m.bound);
         const float y = pn::clampf(r.oy + t * r.dy, -m.bound, m.bound);
         const float z = pn::clampf(r.oz + t * r.dz, -m.bound, m.bound);
-        const float dt = pn::step_size(m, t);
+        const float dt = FIXED ? dt_fixed : pn::step_size(m, t);
         Voxel v;
         if (voxel_occupied<SINGLE>(m, x, y, z, dt, v)) {
             if (!WRITE && step == 0) t_first = t;
@@ -121,12 +170,30 @@ __device__ __forceinline__ uint32_t walk_ray(const pn::MarchCfg &m, const TrainR
             }
             step++;
         } else {
+            if (SINGLE && blocks) {
+                const int lb = empty_block(m, v);
+                if (lb) {
+                    const Span e = block_exit(m, v, lb, x, y, z, t, r);
+                    const float stop = fminf(e.lo, r.far);
+                    float u = t;
+                    if (FIXED) { do { u += dt_fixed; } while (u < stop); }
+                    else { do { u += pn::step_size(m, u); } while (u < stop); }
+                    if (u >= e.hi || u >= r.far) { t = u; continue; }  // the landing the per-voxel chain ends on (or the end of the ray)
+                }
+            }
             const float tt = voxel_exit(m, v, x, y, z, t, r);
-            do { t += pn::step_size(m, t); } while (t < tt);  // leave the empty voxel
+            if (FIXED) { do { t += dt_fixed; } while (t < tt); }        // leave the empty voxel
+            else { do { t += pn::step_size(m, t); } while (t < tt); }
         }
     }
     if (WRITE) { sx.flush_scalar(); sd.flush_scalar(); }
     return step;
+}
+template <bool WRITE, bool SINGLE>
+__device__ __forceinline__ uint32_t walk_ray(const pn::MarchCfg &m, const TrainRay &r, uint32_t limit, float &t_first,
+                                             float *xyzs, float *dirs, float *deltas, bool blocks) {
+    if (m.dt_gamma == 0.0f) return walk_ray_impl<WRITE, SINGLE, true>(m, r, limit, t_first, xyzs, dirs, deltas, blocks);
+    return walk_ray_impl<WRITE, SINGLE, false>(m, r, limit, t_first, xyzs, dirs, deltas, blocks);
 }
 
 // inclusive scan over the kTrainBlock threads of a CTA; returns this thread's inclusive value, *total = CTA sum
@@ -157,14 +224,14 @@ __global__ void __launch_bounds__(kTrainBlock) train_count_kernel(pn::MarchCfg m
                                                                   const float *__restrict__ nears,
                                                                   const float *__restrict__ fars,
                                                                   const float *__restrict__ noises,
-                                                                  int *__restrict__ rays) {
+                                                                  int *__restrict__ rays, bool blocks) {
     __shared__ uint32_t warp_tot[kTrainBlock / 32];
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t num = 0;
     if (n < N) {
         const TrainRay r = load_train_ray(m, rays_o, rays_d, nears, fars, noises, n);
         float t_first = r.t0;
-        num = walk_ray<false, SINGLE>(m, r, max_steps, t_first, nullptr, nullptr, nullptr);
+        num = walk_ray<false, SINGLE>(m, r, max_steps, t_first, nullptr, nullptr, nullptr, blocks);
         rays[3 * n + 1] = __float_as_int(t_first);  // parked in the offset slot until the write pass replaces it
         rays[3 * n + 2] = (int)num;
     }
@@ -225,7 +292,8 @@ __global__ void __launch_bounds__(kTrainBlock) train_write_kernel(pn::MarchCfg m
                                                                   const float *__restrict__ fars,
                                                                   const float *__restrict__ noises,
                                                                   int *__restrict__ rays, float *__restrict__ xyzs,
-                                                                  float *__restrict__ dirs, float *__restrict__ deltas) {
+                                                                  float *__restrict__ dirs, float *__restrict__ deltas,
+                                                                  bool blocks) {
     __shared__ uint32_t warp_tot[kTrainBlock / 32];
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t base = (uint32_t)rays[3 * (size_t)blockIdx.x * kTrainBlock];  // this CTA's first sample
@@ -238,7 +306,7 @@ __global__ void __launch_bounds__(kTrainBlock) train_write_kernel(pn::MarchCfg m
     rays[3 * n + 1] = (int)off;
     if (num == 0 || off + num > M) return;  // a ray that does not fit is dropped whole (raymarching.cu:418-419)
     const TrainRay r = load_train_ray(m, rays_o, rays_d, nears, fars, noises, n);
-    walk_ray<true, SINGLE>(m, r, num, t_first, xyzs + (size_t)off * 3, dirs + (size_t)off * 3, deltas + (size_t)off * 2);
+    walk_ray<true, SINGLE>(m, r, num, t_first, xyzs + (size_t)off * 3, dirs + (size_t)off * 3, deltas + (size_t)off * 2, blocks);
 }
 
 // Compositing: kRayLanes lanes per ray.  The lanes of a group load kRayLanes consecutive samples at a time (the packing is
@@ -359,6 +427,14 @@ __global__ void __launch_bounds__(kTrainBlock) train_composite_bwd_kernel(
 
 }  // namespace
 
+static int g_train_block_skip = 1;
+// A/B switch for the empty-space block skipping of march_rays_train (1 = on, the default; results are identical either way).
+extern "C" int pn_set_train_block_skip(int on) {
+    const int was = g_train_block_skip;
+    g_train_block_skip = on != 0;
+    return was;
+}
+
 extern "C" int pn_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
                                    float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                                    const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
@@ -374,13 +450,15 @@ extern "C" int pn_march_rays_train(const float *rays_o, const float *rays_d, con
     m.dt_max = 2 * 1.7320508075688772f * (1 << (C - 1)) / H;
     m.cascade = (int)C; m.H = (int)H; m.bits = grid;
     const uint32_t blocks = div_up(N, (uint32_t)kTrainBlock);
-    if (C == 1) train_count_kernel<true><<<blocks, kTrainBlock, 0, st>>>(m, max_steps, N, rays_o, rays_d, nears, fars, noises, rays);
-    else train_count_kernel<false><<<blocks, kTrainBlock, 0, st>>>(m, max_steps, N, rays_o, rays_d, nears, fars, noises, rays);
+    // block skipping needs 8^3 blocks that tile the grid and 128-bit loads of the bitfield; one cascade (see block_exit)
+    const bool skip = g_train_block_skip && C == 1 && H % 8 == 0 && (reinterpret_cast<uintptr_t>(grid) & 15) == 0;
+    if (C == 1) train_count_kernel<true><<<blocks, kTrainBlock, 0, st>>>(m, max_steps, N, rays_o, rays_d, nears, fars, noises, rays, skip);
+    else train_count_kernel<false><<<blocks, kTrainBlock, 0, st>>>(m, max_steps, N, rays_o, rays_d, nears, fars, noises, rays, false);
     PN_LAUNCH_CHECK("train_count_kernel");
     train_scan_kernel<<<1, kScanThreads, 0, st>>>(N, rays, counter);
     PN_LAUNCH_CHECK("train_scan_kernel");
-    if (C == 1) train_write_kernel<true><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas);
-    else train_write_kernel<false><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas);
+    if (C == 1) train_write_kernel<true><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas, skip);
+    else train_write_kernel<false><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas, false);
     PN_LAUNCH_CHECK("train_write_kernel");
     return PN_OK;
 }

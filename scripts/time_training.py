@@ -32,8 +32,13 @@ def main(out_path):
     rg = load_ref("_ref_gridencoder"); rr = load_ref("_ref_raymarching"); rs = load_ref("_ref_shencoder")
     res = {}
     g = torch.Generator(device="cuda").manual_seed(0)
-    if os.environ.get("PN_TIME_ONLY") == "rays":        # for an ncu launch list of the ray kernels alone
+    if "PN_TRAIN_SKIP" in os.environ:                    # A/B: empty-space block skipping of march_rays_train
+        from pienerf_b200._lib import lib
+        lib.pn_set_train_block_skip(int(os.environ["PN_TRAIN_SKIP"]))
+    only_rays = os.environ.get("PN_TIME_ONLY", "") in ("rays", "rays_timed")
+    if only_rays:
         rg = rs = None
+    if os.environ.get("PN_TIME_ONLY") == "rays":        # for an ncu launch list of the ray kernels alone: a few untimed calls
         global timed
         timed = lambda fn, iters=2, warm=1: [fn() for _ in range(iters + warm)] and 0.0  # noqa: E731
     offsets, pls = grid_offsets()
@@ -42,7 +47,7 @@ def main(out_path):
     B = 1 << 20
     x = torch.rand(B, 3, device="cuda", generator=g); grad = torch.randn(16, B, 2, device="cuda", generator=g)
     gemb = torch.zeros_like(emb)
-    for name, m in (("ours", _gridencoder if rg is not None or os.environ.get("PN_TIME_ONLY") != "rays" else None), ("reference", rg)):
+    for name, m in (("ours", None if only_rays else _gridencoder), ("reference", rg)):
         if m is None:
             continue
         for dt, tag in ((torch.float32, "f32"), (torch.float16, "f16")):
@@ -82,7 +87,7 @@ def main(out_path):
         res[f"composite_train_bwd_ms/{name}"] = timed(lambda: m.composite_rays_train_backward(one, one3, sig, rgb, deltas, rt, ws, img, M, N, 1e-4, gs, gc))
     dn = torch.nn.functional.normalize(torch.randn(B, 3, device="cuda", generator=g), dim=-1)
     y = torch.empty(B, 16, device="cuda"); j = torch.empty(B, 48, device="cuda")
-    for name, m in (("ours", _shencoder if os.environ.get("PN_TIME_ONLY") != "rays" else None), ("reference", rs)):
+    for name, m in (("ours", None if only_rays else _shencoder), ("reference", rs)):
         if m is None:
             continue
         res[f"sh_forward_with_jacobian_deg4_B2^20_ms/{name}"] = timed(lambda: m.sh_encode_forward(dn, y, B, 3, 4, j))

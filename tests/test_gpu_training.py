@@ -330,8 +330,9 @@ def test_training_entry_points_validate_arguments():
 @pytest.mark.parametrize("bound,dt_gamma", [(1.0, 0.0), (2.0, 1.0 / 128)])
 def test_march_rays_train_full_frame_vs_reference_kernel(bound, dt_gamma):
     """800x800 rays through the chair-sized body against the reference's own kernel: every ray has the reference's sample count and
-    its samples are bit-identical (positions, directions, deltas), for one and for two cascades.  The comparison gathers each ray's run
-    from both packings on the GPU (the reference's offsets are in atomic order, ours in ray order)."""
+    its samples are bit-identical (positions, directions, deltas), for one cascade (where empty space is skipped block-wise, also
+    compared with the skipping switched off) and for two.  The comparison gathers each ray's run from both packings on the GPU
+    (the reference's offsets are in atomic order, ours in ray order)."""
     rr = load_ref("_ref_raymarching")
     if rr is None:
         pytest.skip("oracle/_ref not built")
@@ -347,14 +348,19 @@ def test_march_rays_train_full_frame_vs_reference_kernel(bound, dt_gamma):
     nears, fars = rm.near_far_from_aabb(o, d, torch.tensor([-bound] * 3 + [bound] * 3, device="cuda"), 0.2)
     noises = torch.rand(N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
     M = N * 24
+    from pienerf_b200._lib import lib
     res = []
-    for m in (be, rr):
+    for m, skip in ((be, 1), (rr, 1), (be, 0)):
+        lib.pn_set_train_block_skip(skip)
         xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); deltas = torch.zeros(M, 2, device="cuda")
         rt = torch.empty(N, 3, dtype=torch.int32, device="cuda"); counter = torch.zeros(2, dtype=torch.int32, device="cuda")
         m.march_rays_train(o, d, bits, bound, dt_gamma, 1024, N, C, 128, M, nears, fars, xyzs, dirs, deltas, rt, counter, noises)
         res.append((xyzs, dirs, deltas, rt, counter))
-    (x0, d0, l0, r0, c0), (x1, d1, l1, r1, c1) = res
-    assert torch.equal(c0, c1) and int(c0[0]) <= M and int(c0[0]) > 5_000_000
+    lib.pn_set_train_block_skip(1)
+    (x0, d0, l0, r0, c0), (x1, d1, l1, r1, c1), noskip = res
+    for a, b in zip(res[0], noskip):                              # block skipping changes nothing, bit for bit
+        assert torch.equal(a, b)
+    assert torch.equal(c0, c1) and int(c0[0]) <= M and int(c0[0]) > 2_000_000, (c0, c1)
     r1s = r1[torch.argsort(r1[:, 0].long())]                      # the reference's rows, by ray
     assert torch.equal(r0[:, 0], r1s[:, 0]) and torch.equal(r0[:, 2], r1s[:, 2])
     num = r0[:, 2].long()
