@@ -3,8 +3,8 @@
 // point), :505-645 (total-variation gradient) of the reference.
 //
 //  * grid_backward_kernel<T,D,C> — one thread per (sample, level) scatters w * dL/dy into the 2^D vertices of its
-//    cell.  All C channels of a vertex leave in one vector reduction where the hardware has one (red.v2.f32 for fp32
-//    pairs, red.noftz.f16x2 for fp16 pairs) instead of the reference's one atomic per channel pair per thread with
+//    cell.  All C channels of a vertex leave in vector reductions where the hardware has them (REDG.E.ADD.F32x2 /
+//    .F32x4 for fp32 pairs and quads, red.global.add.noftz.f16x2 for fp16 pairs) instead of the reference's one atomic per channel pair per thread with
 //    C/2 threads recomputing the same vertex indices.  blockIdx.y = level, so co-resident CTAs reduce into the same
 //    level slice of the table gradient and the reductions resolve in L2.
 //  * grid_input_backward_kernel<T,D,C> — dL/dx[b,d] = sum_{l,c} dL/dy[l,b,c] * dy_dx[b,l,d,c], summed in (l,c) order.
