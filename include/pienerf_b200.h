@@ -104,6 +104,9 @@ int pn_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t 
 /* A/B switch for march_rays_train's empty-space skipping over 8^3 / 4^3 voxel blocks (single cascade; on by default).  The samples
  * are the reference's either way (tests assert bit-equality both ways); returns the previous setting. */
 int pn_set_train_block_skip(int on);
+/* Write pass of march_rays_train: 1 = warp-cooperative flush through shared memory (default), 0 = per-lane stream stores.  Same
+ * output; returns the previous setting. */
+int pn_set_train_write_mode(int mode);
 /* raymarching.h:14 + raymarching.cu:583-591: sigmas [M], rgbs [M,3], deltas [M,2], rays [N,3] -> weights_sum/depth [N],
  * image [N,3], indexed by rays[:,0]. */
 int pn_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas, const int *rays, uint32_t M,

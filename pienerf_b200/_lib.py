@@ -67,6 +67,7 @@ _PROTOS = {
                                               u32, u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pn_march_rays_train": (i32, [vp, vp, vp, f32, f32, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pn_set_train_block_skip": (i32, [i32]),
+    "pn_set_train_write_mode": (i32, [i32]),
     "pn_composite_rays_train_forward": (i32, [vp, vp, vp, vp, u32, u32, f32, vp, vp, vp, vp]),
     "pn_composite_rays_train_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, f32, vp, vp, vp]),
     "pn_get_rays": (i32, [vp, f32, f32, f32, f32, u32, u32, vp, vp, vp]),

@@ -9,9 +9,10 @@
 //                            its total in the index slot of its first ray;
 //   2. train_scan_kernel   — one 1024-thread CTA turns the per-CTA totals into per-CTA base offsets (N/128 values, in
 //                            place) and advances the (points, rays) counter the way the reference's atomics do;
-//   3. train_write_kernel  — each CTA scans its 128 counts from its base, completes rays[n] = (n, offset, num_steps), and
-//                            every thread resumes its walk AT t_first writing xyzs / dirs / deltas at its offset: the empty
-//                            space in front of the object (most of a walk) is crossed once, not twice as in the reference.
+//   3. train_write_[coop_]kernel — each CTA scans its 128 counts from its base, completes rays[n] = (n, offset, num_steps),
+//                            and every thread resumes its walk AT t_first: the empty space in front of the object (most of
+//                            a walk) is crossed once, not twice as in the reference.  Samples are staged in shared memory
+//                            eight at a time per lane and written by the whole warp as contiguous runs.
 // No scratch memory: the index and offset columns of `rays` carry the partial sums and t_first between the launches.
 // The sample stream per ray is identical to the reference's (same float arithmetic through march_device.cuh); what
 // changes is the packing: ray n is row n of `rays` and the samples of ray n precede those of ray n+1, so the output
@@ -309,6 +310,117 @@ __global__ void __launch_bounds__(kTrainBlock) train_write_kernel(pn::MarchCfg m
     walk_ray<true, SINGLE>(m, r, num, t_first, xyzs + (size_t)off * 3, dirs + (size_t)off * 3, deltas + (size_t)off * 2, blocks);
 }
 
+// Cooperative write pass (the default; pn_set_train_write_mode(0) selects train_write_kernel above).  Same thread-per-ray walk, but a lane stages up
+// to kStage samples in shared memory and the warp then writes every lane's staged run together: lane i stores float i of the run,
+// so a run of 8 samples leaves as one 96-byte (xyzs, dirs) / 64-byte (deltas) contiguous store per array instead of twenty 4..16-byte
+// pieces spread over the walk.  The walk body is walk_ray_impl's (same helpers, same expressions); only where the sample goes differs.
+constexpr int kStage = 8;
+struct WalkState { float t, last_t; uint32_t step; };
+
+template <bool SINGLE, bool FIXED>
+__device__ __forceinline__ uint32_t walk_stage(const pn::MarchCfg &m, const TrainRay &r, uint32_t limit, WalkState &w, float *sx,
+                                               float *sl, bool blocks) {
+    uint32_t cnt = 0;
+    const float dt_fixed = pn::step_size(m, 0.0f);
+    float t = w.t;
+    while (t < r.far && w.step < limit && cnt < (uint32_t)kStage) {
+        const float x = pn::clampf(r.ox + t * r.dx, -m.bound, m.bound);
+        const float y = pn::clampf(r.oy + t * r.dy, -m.bound, m.bound);
+        const float z = pn::clampf(r.oz + t * r.dz, -m.bound, m.bound);
+        const float dt = FIXED ? dt_fixed : pn::step_size(m, t);
+        Voxel v;
+        if (voxel_occupied<SINGLE>(m, x, y, z, dt, v)) {
+            t += dt;
+            sx[3 * cnt] = x; sx[3 * cnt + 1] = y; sx[3 * cnt + 2] = z;
+            sl[2 * cnt] = dt; sl[2 * cnt + 1] = t - w.last_t;
+            w.last_t = t;
+            cnt++;
+            w.step++;
+        } else {
+            if (SINGLE && blocks) {
+                const int lb = empty_block(m, v);
+                if (lb) {
+                    const Span e = block_exit(m, v, lb, x, y, z, t, r);
+                    const float stop = fminf(e.lo, r.far);
+                    float u = t;
+                    if (FIXED) { do { u += dt_fixed; } while (u < stop); }
+                    else { do { u += pn::step_size(m, u); } while (u < stop); }
+                    if (u >= e.hi || u >= r.far) { t = u; continue; }
+                }
+            }
+            const float tt = voxel_exit(m, v, x, y, z, t, r);
+            if (FIXED) { do { t += dt_fixed; } while (t < tt); }
+            else { do { t += pn::step_size(m, t); } while (t < tt); }
+        }
+    }
+    w.t = t;
+    return cnt;
+}
+
+template <bool SINGLE>
+__global__ void __launch_bounds__(kTrainBlock) train_write_coop_kernel(pn::MarchCfg m, uint32_t N, uint32_t M,
+                                                                       const float *__restrict__ rays_o,
+                                                                       const float *__restrict__ rays_d,
+                                                                       const float *__restrict__ nears,
+                                                                       const float *__restrict__ fars,
+                                                                       const float *__restrict__ noises,
+                                                                       int *__restrict__ rays, float *__restrict__ xyzs,
+                                                                       float *__restrict__ dirs, float *__restrict__ deltas,
+                                                                       bool blocks) {
+    __shared__ uint32_t warp_tot[kTrainBlock / 32];
+    __shared__ float stage_x[kTrainBlock][3 * kStage + 1];  // +1: lanes start in different banks
+    __shared__ float stage_l[kTrainBlock][2 * kStage + 1];
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t base = (uint32_t)rays[3 * (size_t)blockIdx.x * kTrainBlock];
+    const uint32_t num = n < N ? (uint32_t)rays[3 * n + 2] : 0u;
+    uint32_t total;
+    const uint32_t off = base + block_scan_inclusive(num, warp_tot, &total) - num;
+    TrainRay r{};
+    WalkState w{0.f, 0.f, 0u};
+    uint32_t todo = 0;  // samples this lane still has to produce; lanes without work stay for the warp's flushes
+    if (n < N) {
+        w.t = __int_as_float(rays[3 * n + 1]);
+        rays[3 * n] = (int)n;
+        rays[3 * n + 1] = (int)off;
+        if (num != 0 && off + num <= M) {  // a ray that does not fit is dropped whole (raymarching.cu:418-419)
+            r = load_train_ray(m, rays_o, rays_d, nears, fars, noises, n);
+            w.last_t = r.t0;
+            todo = num;
+        }
+    }
+    const bool fixed = m.dt_gamma == 0.0f;
+    uint32_t done = 0;  // samples of this lane already in global memory
+    float *sx = stage_x[threadIdx.x], *sl = stage_l[threadIdx.x];
+    const float(*wx)[3 * kStage + 1] = stage_x + (threadIdx.x & ~31u);  // this warp's rows
+    const float(*wl)[2 * kStage + 1] = stage_l + (threadIdx.x & ~31u);
+    for (;;) {
+        uint32_t cnt = 0;
+        if (todo) cnt = fixed ? walk_stage<SINGLE, true>(m, r, num, w, sx, sl, blocks) : walk_stage<SINGLE, false>(m, r, num, w, sx, sl, blocks);
+        todo -= min(todo, cnt);
+        if (cnt == 0) todo = 0;  // (a walk that ends early — it cannot, the count pass walked the same ray — must not spin)
+        __syncwarp();
+        uint32_t pending = __ballot_sync(0xffffffffu, cnt > 0);
+        if (pending == 0) break;
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
+            const size_t o = (size_t)__shfl_sync(0xffffffffu, off + done, src);
+            const float ddx = __shfl_sync(0xffffffffu, r.dx, src), ddy = __shfl_sync(0xffffffffu, r.dy, src),
+                        ddz = __shfl_sync(0xffffffffu, r.dz, src);
+            if (lane < 3 * c) {
+                xyzs[3 * o + lane] = wx[src][lane];
+                const uint32_t k = lane % 3;
+                dirs[3 * o + lane] = k == 0 ? ddx : k == 1 ? ddy : ddz;
+            }
+            if (lane < 2 * c) deltas[2 * o + lane] = wl[src][lane];
+        }
+        done += cnt;
+        __syncwarp();
+    }
+}
+
 // Compositing: kRayLanes lanes per ray.  The lanes of a group load kRayLanes consecutive samples at a time (the packing is
 // ray-ordered, so a warp reads one contiguous stretch of sigmas / rgbs / deltas), then every lane replays the reference's
 // front-to-back recurrence over the group's samples through width-kRayLanes shuffles, in sample order: the arithmetic is the
@@ -428,6 +540,14 @@ __global__ void __launch_bounds__(kTrainBlock) train_composite_bwd_kernel(
 }  // namespace
 
 static int g_train_block_skip = 1;
+static int g_train_write_mode = 1;
+// Write pass of march_rays_train: 1 = warp-cooperative flush through shared memory (train_write_coop_kernel, default; 0.74 vs
+// 0.90 ms per 800x800 frame), 0 = every lane streams its own samples (train_write_kernel).  Same output either way; returns the previous setting.
+extern "C" int pn_set_train_write_mode(int mode) {
+    const int was = g_train_write_mode;
+    g_train_write_mode = mode != 0;
+    return was;
+}
 // A/B switch for the empty-space block skipping of march_rays_train (1 = on, the default; results are identical either way).
 extern "C" int pn_set_train_block_skip(int on) {
     const int was = g_train_block_skip;
@@ -457,8 +577,13 @@ extern "C" int pn_march_rays_train(const float *rays_o, const float *rays_d, con
     PN_LAUNCH_CHECK("train_count_kernel");
     train_scan_kernel<<<1, kScanThreads, 0, st>>>(N, rays, counter);
     PN_LAUNCH_CHECK("train_scan_kernel");
-    if (C == 1) train_write_kernel<true><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas, skip);
-    else train_write_kernel<false><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas, false);
+    if (g_train_write_mode) {
+        if (C == 1) train_write_coop_kernel<true><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas, skip);
+        else train_write_coop_kernel<false><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas, false);
+    } else {
+        if (C == 1) train_write_kernel<true><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas, skip);
+        else train_write_kernel<false><<<blocks, kTrainBlock, 0, st>>>(m, N, M, rays_o, rays_d, nears, fars, noises, rays, xyzs, dirs, deltas, false);
+    }
     PN_LAUNCH_CHECK("train_write_kernel");
     return PN_OK;
 }

@@ -32,6 +32,9 @@ def main(out_path):
     rg = load_ref("_ref_gridencoder"); rr = load_ref("_ref_raymarching"); rs = load_ref("_ref_shencoder")
     res = {}
     g = torch.Generator(device="cuda").manual_seed(0)
+    if "PN_TRAIN_WRITE" in os.environ:                   # A/B: 0 = stream stores, 1 = warp-cooperative flush
+        from pienerf_b200._lib import lib
+        lib.pn_set_train_write_mode(int(os.environ["PN_TRAIN_WRITE"]))
     if "PN_TRAIN_SKIP" in os.environ:                    # A/B: empty-space block skipping of march_rays_train
         from pienerf_b200._lib import lib
         lib.pn_set_train_block_skip(int(os.environ["PN_TRAIN_SKIP"]))

@@ -45,8 +45,17 @@ def _march(be, o, d, bits, bound, dt_gamma, max_steps, C, H, M, nears, fars, noi
     return xyzs.cpu().numpy(), dirs.cpu().numpy(), deltas.cpu().numpy(), rays.cpu().numpy(), counter.cpu().numpy()
 
 
+@pytest.fixture(params=[0, 1], ids=["stream-stores", "cooperative-flush"])
+def write_mode(request):
+    """Both write passes of march_rays_train (pn_set_train_write_mode) must produce the same bytes."""
+    from pienerf_b200._lib import lib
+    was = lib.pn_set_train_write_mode(request.param)
+    yield request.param
+    lib.pn_set_train_write_mode(was)
+
+
 @pytest.mark.parametrize("tag", ["mA", "mB"])
-def test_march_rays_train_vs_golden(G, tag):
+def test_march_rays_train_vs_golden(G, tag, write_mode):
     """Same compiler, same float expressions as the reference: identical ray table and bit-identical samples."""
     import pienerf_b200._raymarching as be
     bound, dt_gamma, max_steps, C, H = G[f"{tag}_par"]
@@ -61,7 +70,7 @@ def test_march_rays_train_vs_golden(G, tag):
     assert not x[m:].any() and not dl[m:].any()                     # nothing written past the samples produced
 
 
-def test_march_rays_train_vs_oracle_other_seed_and_overflow(rng):
+def test_march_rays_train_vs_oracle_other_seed_and_overflow(rng, write_mode):
     import pienerf_b200._raymarching as be
     body, field, bits, pose, intr = small_scene(W=20, H=28, seed=5)
     o, d = ro.get_rays(pose, intr, 28, 20)
@@ -350,16 +359,17 @@ def test_march_rays_train_full_frame_vs_reference_kernel(bound, dt_gamma):
     M = N * 24
     from pienerf_b200._lib import lib
     res = []
-    for m, skip in ((be, 1), (rr, 1), (be, 0)):
-        lib.pn_set_train_block_skip(skip)
+    for m, skip, mode in ((be, 1, 0), (rr, 1, 0), (be, 0, 0), (be, 1, 1), (be, 0, 1)):
+        lib.pn_set_train_block_skip(skip); lib.pn_set_train_write_mode(mode)
         xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); deltas = torch.zeros(M, 2, device="cuda")
         rt = torch.empty(N, 3, dtype=torch.int32, device="cuda"); counter = torch.zeros(2, dtype=torch.int32, device="cuda")
         m.march_rays_train(o, d, bits, bound, dt_gamma, 1024, N, C, 128, M, nears, fars, xyzs, dirs, deltas, rt, counter, noises)
         res.append((xyzs, dirs, deltas, rt, counter))
-    lib.pn_set_train_block_skip(1)
-    (x0, d0, l0, r0, c0), (x1, d1, l1, r1, c1), noskip = res
-    for a, b in zip(res[0], noskip):                              # block skipping changes nothing, bit for bit
-        assert torch.equal(a, b)
+    lib.pn_set_train_block_skip(1); lib.pn_set_train_write_mode(0)
+    (x0, d0, l0, r0, c0), (x1, d1, l1, r1, c1) = res[0], res[1]
+    for other in res[2:]:                                         # block skipping / the cooperative write pass change nothing, bit for bit
+        for a, b in zip(res[0], other):
+            assert torch.equal(a, b)
     assert torch.equal(c0, c1) and int(c0[0]) <= M and int(c0[0]) > 2_000_000, (c0, c1)
     r1s = r1[torch.argsort(r1[:, 0].long())]                      # the reference's rows, by ray
     assert torch.equal(r0[:, 0], r1s[:, 0]) and torch.equal(r0[:, 2], r1s[:, 2])
