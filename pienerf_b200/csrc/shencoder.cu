@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) sh_forward(const float *__restrict__ in, 
 // kernel), so they are bit-identical with and without the Jacobian.
 template <uint32_t DEG>
 __global__ void __launch_bounds__(128) sh_forward_jacobian(const float *__restrict__ in, float *__restrict__ dy_dx, uint32_t B,
-                                                           uint32_t D) {
+                                                           uint32_t D, bool aligned16) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     constexpr uint32_t C2 = DEG * DEG;
@@ -44,8 +44,14 @@ __global__ void __launch_bounds__(128) sh_forward_jacobian(const float *__restri
         pn::SHDual v[C2];
         pn::sh_eval<DEG, pn::SHDual>(pn::SHDual(x, a == 0 ? 1.f : 0.f), pn::SHDual(y, a == 1 ? 1.f : 0.f),
                                      pn::SHDual(z, a == 2 ? 1.f : 0.f), v);
+        if (C2 % 4 == 0 && aligned16) {  // rows of the Jacobian are 16-byte aligned: 128-bit stores
+            float4 *j4 = reinterpret_cast<float4 *>(j + a * C2);
 #pragma unroll
-        for (uint32_t i = 0; i < C2; i++) j[a * C2 + i] = v[i].d;
+            for (uint32_t i = 0; i < C2 / 4; i++) j4[i] = make_float4(v[4 * i].d, v[4 * i + 1].d, v[4 * i + 2].d, v[4 * i + 3].d);
+        } else {
+#pragma unroll
+            for (uint32_t i = 0; i < C2; i++) j[a * C2 + i] = v[i].d;
+        }
     }
 }
 
@@ -72,15 +78,16 @@ extern "C" int pn_sh_encode_forward(const float *inputs, float *outputs, uint32_
     if (dy_dx) {
         PN_REQUIRE(D == 3, "SH input gradients expect D == 3 (dy_dx is [B, 3, C*C])");
         const uint32_t gj = div_up(B, 128u);
+        const bool al = (reinterpret_cast<uintptr_t>(dy_dx) & 15) == 0;
         switch (C) {
-            case 1: sh_forward_jacobian<1><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
-            case 2: sh_forward_jacobian<2><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
-            case 3: sh_forward_jacobian<3><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
-            case 4: sh_forward_jacobian<4><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
-            case 5: sh_forward_jacobian<5><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
-            case 6: sh_forward_jacobian<6><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
-            case 7: sh_forward_jacobian<7><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
-            case 8: sh_forward_jacobian<8><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D); break;
+            case 1: sh_forward_jacobian<1><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D, al); break;
+            case 2: sh_forward_jacobian<2><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D, al); break;
+            case 3: sh_forward_jacobian<3><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D, al); break;
+            case 4: sh_forward_jacobian<4><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D, al); break;
+            case 5: sh_forward_jacobian<5><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D, al); break;
+            case 6: sh_forward_jacobian<6><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D, al); break;
+            case 7: sh_forward_jacobian<7><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D, al); break;
+            case 8: sh_forward_jacobian<8><<<gj, 128, 0, st>>>(inputs, dy_dx, B, D, al); break;
             default:
                 pn_set_error("SH encoder: degree must be in 1..8");
                 return PN_EINVAL;
