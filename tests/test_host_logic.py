@@ -151,3 +151,42 @@ def test_screen_world_roundtrip():
     assert d == 9.0
     _, d = screen_to_world(1000, -5, depth, pose, intr, average_depth=9.0)      # clamped like gui.py:649
     assert d == 9.0
+
+
+@pytest.mark.parametrize("kw", [
+    dict(), dict(desired_resolution=2048), dict(desired_resolution=4096, log2_hashmap_size=19), dict(input_dim=2, num_levels=8, level_dim=4, base_resolution=8),
+    dict(num_levels=4, level_dim=8, per_level_scale=1.5, base_resolution=4, log2_hashmap_size=10, gridtype="tiled", align_corners=True, interpolation="smoothstep")])
+def test_encoder_modules_match_the_reference_classes(kw):
+    """Host logic of GridEncoder / SHEncoder against the reference's own classes (gridencoder/grid.py, shencoder/sphere_harmonics.py,
+    imported unmodified on top of the drop-in modules; their constructors need no GPU): level offsets, parameter counts, ids, repr."""
+    import os
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present on this box")
+    from pienerf_b200 import dropin
+    from pienerf_b200.gridencoder import GridEncoder
+    from pienerf_b200.shencoder import SHEncoder
+    dropin.install(compiled=False)
+    sys.path.insert(0, ref)
+    try:
+        for m in ("gridencoder", "shencoder"):
+            sys.modules.pop(m, None)
+        import gridencoder.grid as g
+        import shencoder.sphere_harmonics as s
+        ours, theirs = GridEncoder(**kw), g.GridEncoder(**kw)
+        assert torch.equal(ours.offsets, theirs.offsets) and ours.embeddings.shape == theirs.embeddings.shape
+        for a in ("input_dim", "num_levels", "level_dim", "per_level_scale", "log2_hashmap_size", "base_resolution", "output_dim", "gridtype",
+                  "gridtype_id", "interpolation", "interp_id", "align_corners", "n_params", "max_params"):
+            assert getattr(ours, a) == getattr(theirs, a), a
+        assert repr(ours) == repr(theirs)
+        assert float(ours.embeddings.detach().abs().max()) <= 1e-4                                # reset_parameters: U(-1e-4, 1e-4)
+        assert sorted(ours.state_dict()) == sorted(theirs.state_dict())                    # checkpoints are interchangeable
+        for deg in (1, 4, 8):
+            a, b = SHEncoder(degree=deg), s.SHEncoder(degree=deg)
+            assert (a.input_dim, a.degree, a.output_dim, repr(a)) == (b.input_dim, b.degree, b.output_dim, repr(b))
+    finally:
+        sys.path.remove(ref)
+        for m in list(sys.modules):
+            if m.split(".")[0] in ("gridencoder", "shencoder", "raymarching") and "pienerf_b200" not in m:
+                sys.modules.pop(m, None)
