@@ -5,7 +5,7 @@ import ctypes as C
 
 import torch
 
-from ._lib import QgmlsStepT, check, dptr, lib, stream_ptr
+from ._lib import check, dptr, lib, stream_ptr
 
 f64, i32 = torch.float64, torch.int32
 

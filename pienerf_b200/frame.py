@@ -125,7 +125,6 @@ class DistFrameDriver:
 
     def __init__(self, model, sim, opt, tile=16, weights=None, overlap_sim=True):
         import torch.distributed as dist
-        from .dist import FrameGather, tile_partition
         self.model, self.sim, self.opt, self.tile = model, sim, opt, tile
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
@@ -150,7 +149,7 @@ class DistFrameDriver:
         self.set_partition(weights)
 
     def set_partition(self, weights=None):
-        from .dist import FrameGather, tile_partition
+        from .dist import tile_partition
         self.parts = tile_partition(self.H, self.W, self.world, self.tile, weights)
         self.my = torch.from_numpy(self.parts[self.rank]).to(self.dev)
         from .dist import PlanarFrameGather

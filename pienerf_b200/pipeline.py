@@ -21,7 +21,6 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _qgmls
 from ._lib import FrameIoT, check, dptr, lib, stream_ptr, vp
 
 

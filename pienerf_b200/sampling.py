@@ -16,7 +16,6 @@ What the reference leaves to chance is pinned here, and said so:
 """
 import os
 
-import numpy as np
 import torch
 
 from .ply import write_ply_xyz

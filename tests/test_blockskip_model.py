@@ -10,7 +10,6 @@ import numpy as np
 import pytest
 
 from oracle import render_oracle as ro
-from oracle import train_oracle as to
 
 f32 = np.float32
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_train.npz")

@@ -4,7 +4,7 @@ SH addition theorem, undeformed inverse warp == identity, rund_cuda == run_cuda 
 import numpy as np
 
 from oracle import render_oracle as ro
-from pienerf_b200.synthetic import grid_offsets, morton3d, occupancy_bitfield
+from pienerf_b200.synthetic import grid_offsets, morton3d
 from tests.util import deformed_ip_state, small_scene
 
 f32 = np.float32
