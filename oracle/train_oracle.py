@@ -256,9 +256,88 @@ def grad_total_variation(inputs, embeddings, offsets, weight, S, H, gridtype=0, 
 
 
 # ------------------------------------------------------------------ shencoder (training)
+def sh_polynomials(dirs, degree, dtype=np.float32):
+    """shencoder/src/shencoder.cu:49-123: the 64 Cartesian polynomials, evaluated in `dtype` term for term (bands 4..7 here;
+    bands 0..3 through the same expressions as render_oracle.sh_encode).  Used in float32 for values and in float64 for the
+    central differences behind sh_jacobian at degree > 4."""
+    d = np.asarray(dirs, dtype)
+    c = dtype
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    xy = x * y; xz = x * z; yz = y * z; x2 = x * x; y2 = y * y; z2 = z * z
+    x4 = x2 * x2; y4 = y2 * y2; z4 = z2 * z2
+    x6 = x4 * x2; y6 = y4 * y2; z6 = z4 * z2
+    o = np.zeros((d.shape[0], degree * degree), dtype)
+    o[:, 0] = c(0.28209479177387814)
+    if degree > 1:
+        o[:, 1] = c(-0.48860251190291987) * y; o[:, 2] = c(0.48860251190291987) * z; o[:, 3] = c(-0.48860251190291987) * x
+    if degree > 2:
+        o[:, 4] = c(1.0925484305920792) * xy; o[:, 5] = c(-1.0925484305920792) * yz
+        o[:, 6] = c(0.94617469575755997) * z2 - c(0.31539156525251999)
+        o[:, 7] = c(-1.0925484305920792) * xz; o[:, 8] = c(0.54627421529603959) * x2 - c(0.54627421529603959) * y2
+    if degree > 3:
+        o[:, 9] = c(0.59004358992664352) * y * (c(-3) * x2 + y2); o[:, 10] = c(2.8906114426405538) * xy * z
+        o[:, 11] = c(0.45704579946446572) * y * (c(1) - c(5) * z2); o[:, 12] = c(0.3731763325901154) * z * (c(5) * z2 - c(3))
+        o[:, 13] = c(0.45704579946446572) * x * (c(1) - c(5) * z2); o[:, 14] = c(1.4453057213202769) * z * (x2 - y2)
+        o[:, 15] = c(0.59004358992664352) * x * (-x2 + c(3) * y2)
+    if degree > 4:
+        o[:, 16] = c(2.5033429417967046) * xy * (x2 - y2)
+        o[:, 17] = c(1.7701307697799304) * yz * (-c(3.0) * x2 + y2)
+        o[:, 18] = c(0.94617469575756008) * xy * (c(7.0) * z2 - c(1.0))
+        o[:, 19] = c(0.66904654355728921) * yz * (c(3.0) - c(7.0) * z2)
+        o[:, 20] = -c(3.1735664074561294) * z2 + c(3.7024941420321507) * z4 + c(0.31735664074561293)
+        o[:, 21] = c(0.66904654355728921) * xz * (c(3.0) - c(7.0) * z2)
+        o[:, 22] = c(0.47308734787878004) * (x2 - y2) * (c(7.0) * z2 - c(1.0))
+        o[:, 23] = c(1.7701307697799304) * xz * (-x2 + c(3.0) * y2)
+        o[:, 24] = -c(3.7550144126950569) * x2 * y2 + c(0.62583573544917614) * x4 + c(0.62583573544917614) * y4
+    if degree > 5:
+        o[:, 25] = c(0.65638205684017015) * y * (c(10.0) * x2 * y2 - c(5.0) * x4 - y4)
+        o[:, 26] = c(8.3026492595241645) * xy * z * (x2 - y2)
+        o[:, 27] = -c(0.48923829943525038) * y * (c(3.0) * x2 - y2) * (c(9.0) * z2 - c(1.0))
+        o[:, 28] = c(4.7935367849733241) * xy * z * (c(3.0) * z2 - c(1.0))
+        o[:, 29] = c(0.45294665119569694) * y * (c(14.0) * z2 - c(21.0) * z4 - c(1.0))
+        o[:, 30] = c(0.1169503224534236) * z * (-c(70.0) * z2 + c(63.0) * z4 + c(15.0))
+        o[:, 31] = c(0.45294665119569694) * x * (c(14.0) * z2 - c(21.0) * z4 - c(1.0))
+        o[:, 32] = c(2.3967683924866621) * z * (x2 - y2) * (c(3.0) * z2 - c(1.0))
+        o[:, 33] = -c(0.48923829943525038) * x * (x2 - c(3.0) * y2) * (c(9.0) * z2 - c(1.0))
+        o[:, 34] = c(2.0756623148810411) * z * (-c(6.0) * x2 * y2 + x4 + y4)
+        o[:, 35] = c(0.65638205684017015) * x * (c(10.0) * x2 * y2 - x4 - c(5.0) * y4)
+    if degree > 6:
+        o[:, 36] = c(1.3663682103838286) * xy * (-c(10.0) * x2 * y2 + c(3.0) * x4 + c(3.0) * y4)
+        o[:, 37] = c(2.3666191622317521) * yz * (c(10.0) * x2 * y2 - c(5.0) * x4 - y4)
+        o[:, 38] = c(2.0182596029148963) * xy * (x2 - y2) * (c(11.0) * z2 - c(1.0))
+        o[:, 39] = -c(0.92120525951492349) * yz * (c(3.0) * x2 - y2) * (c(11.0) * z2 - c(3.0))
+        o[:, 40] = c(0.92120525951492349) * xy * (-c(18.0) * z2 + c(33.0) * z4 + c(1.0))
+        o[:, 41] = c(0.58262136251873131) * yz * (c(30.0) * z2 - c(33.0) * z4 - c(5.0))
+        o[:, 42] = c(6.6747662381009842) * z2 - c(20.024298714302954) * z4 + c(14.684485723822165) * z6 - c(0.31784601133814211)
+        o[:, 43] = c(0.58262136251873131) * xz * (c(30.0) * z2 - c(33.0) * z4 - c(5.0))
+        o[:, 44] = c(0.46060262975746175) * (x2 - y2) * (c(11.0) * z2 * (c(3.0) * z2 - c(1.0)) - c(7.0) * z2 + c(1.0))
+        o[:, 45] = -c(0.92120525951492349) * xz * (x2 - c(3.0) * y2) * (c(11.0) * z2 - c(3.0))
+        o[:, 46] = c(0.50456490072872406) * (c(11.0) * z2 - c(1.0)) * (-c(6.0) * x2 * y2 + x4 + y4)
+        o[:, 47] = c(2.3666191622317521) * xz * (c(10.0) * x2 * y2 - x4 - c(5.0) * y4)
+        o[:, 48] = c(10.247761577878714) * x2 * y4 - c(10.247761577878714) * x4 * y2 + c(0.6831841051919143) * x6 - c(0.6831841051919143) * y6
+    if degree > 7:
+        o[:, 49] = c(0.70716273252459627) * y * (-c(21.0) * x2 * y4 + c(35.0) * x4 * y2 - c(7.0) * x6 + y6)
+        o[:, 50] = c(5.2919213236038001) * xy * z * (-c(10.0) * x2 * y2 + c(3.0) * x4 + c(3.0) * y4)
+        o[:, 51] = -c(0.51891557872026028) * y * (c(13.0) * z2 - c(1.0)) * (-c(10.0) * x2 * y2 + c(5.0) * x4 + y4)
+        o[:, 52] = c(4.1513246297620823) * xy * z * (x2 - y2) * (c(13.0) * z2 - c(3.0))
+        o[:, 53] = -c(0.15645893386229404) * y * (c(3.0) * x2 - y2) * (c(13.0) * z2 * (c(11.0) * z2 - c(3.0)) - c(27.0) * z2 + c(3.0))
+        o[:, 54] = c(0.44253269244498261) * xy * z * (-c(110.0) * z2 + c(143.0) * z4 + c(15.0))
+        o[:, 55] = c(0.090331607582517306) * y * (-c(135.0) * z2 + c(495.0) * z4 - c(429.0) * z6 + c(5.0))
+        o[:, 56] = c(0.068284276912004949) * z * (c(315.0) * z2 - c(693.0) * z4 + c(429.0) * z6 - c(35.0))
+        o[:, 57] = c(0.090331607582517306) * x * (-c(135.0) * z2 + c(495.0) * z4 - c(429.0) * z6 + c(5.0))
+        o[:, 58] = c(0.07375544874083044) * z * (x2 - y2) * (c(143.0) * z2 * (c(3.0) * z2 - c(1.0)) - c(187.0) * z2 + c(45.0))
+        o[:, 59] = -c(0.15645893386229404) * x * (x2 - c(3.0) * y2) * (c(13.0) * z2 * (c(11.0) * z2 - c(3.0)) - c(27.0) * z2 + c(3.0))
+        o[:, 60] = c(1.0378311574405206) * z * (c(13.0) * z2 - c(3.0)) * (-c(6.0) * x2 * y2 + x4 + y4)
+        o[:, 61] = -c(0.51891557872026028) * x * (c(13.0) * z2 - c(1.0)) * (-c(10.0) * x2 * y2 + x4 + c(5.0) * y4)
+        o[:, 62] = c(2.6459606618019) * z * (c(15.0) * x2 * y4 - c(15.0) * x4 * y2 + x6 - y6)
+        o[:, 63] = c(0.70716273252459627) * x * (-c(35.0) * x2 * y4 + c(21.0) * x4 * y2 - x6 + c(7.0) * y6)
+    return o
+
+
 def sh_jacobian(dirs, degree=4):
-    """d Y / d (x,y,z) for bands below `degree` (<= 4, like render_oracle.sh_encode): [B, 3, degree^2].  Derivatives of the
-    polynomials of shencoder.cu:49-77 taken by hand; the reference tabulates the same derivatives at shencoder.cu:128-344."""
+    """d Y / d (x,y,z) for bands below `degree`: [B, 3, degree^2].  Bands 0..3: derivatives of the polynomials of
+    shencoder.cu:49-77 taken by hand; bands 4..7: float64 central differences of sh_polynomials.  The reference tabulates
+    the same derivatives at shencoder.cu:128-344."""
     v = np.asarray(dirs, np.float32)
     x, y, z = v[:, 0], v[:, 1], v[:, 2]
     B = v.shape[0]
@@ -293,7 +372,13 @@ def sh_jacobian(dirs, degree=4):
         # 15: a*x*(3y2 - x2)
         J[:, X, 15] = a * (f32(3) * y2 - f32(3) * x2); J[:, Y, 15] = a * x * f32(6) * y
     if degree > 4:
-        raise NotImplementedError("oracle restates SH up to degree 4 (the hot path)")
+        # bands 4..7: central differences of the float64 polynomials (step 1e-6: truncation ~1e-11, rounding ~1e-9), exact for
+        # the purpose of a float32 comparison; the closed forms above pin the method on bands 0..3
+        h = 1e-6
+        base = np.asarray(dirs, np.float64)
+        for a in range(3):
+            e = np.zeros(3); e[a] = h
+            J[:, a, 16:] = ((sh_polynomials(base + e, degree, np.float64) - sh_polynomials(base - e, degree, np.float64)) / (2 * h))[:, 16:]
     return J
 
 

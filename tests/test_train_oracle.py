@@ -103,3 +103,30 @@ def test_sh_jacobian_and_backward_match_reference(G):
     assert np.abs(gin - G["sh4_gin"]).max() < 1e-5
     # the degree-8 Jacobian's first 16 columns are the degree-4 one
     assert np.array_equal(G["sh8_dy_dx"].reshape(-1, 3, 64)[:, :, :16], jr)
+    # degree 8: the polynomial table in float32 (values) and its float64 central differences (Jacobian)
+    y8 = to.sh_polynomials(dirs, 8)
+    assert np.array_equal(y8[:, :16], ro.sh_encode(dirs, 4)) and np.abs(y8 - G["sh8_y"]).max() < 2e-6
+    j8 = G["sh8_dy_dx"].reshape(-1, 3, 64)
+    assert np.abs(to.sh_jacobian(dirs, 8) - j8).max() < 2e-6 * np.abs(j8).max()
+    assert np.abs(to.sh_encode_backward(G["sh8_grad"], j8) - G["sh8_gin"]).max() < 1e-5 * np.abs(G["sh8_gin"]).max()
+
+
+def test_sh_ordering_and_signs_against_the_legendre_definition(G):
+    """Independent of any transcription: real spherical harmonics from associated Legendre functions (Condon-Shortley phase,
+    output l*l + l + m, sin for m < 0) reproduce the reference's 64 outputs on unit directions."""
+    from scipy.special import factorial, lpmv
+
+    def legendre(d):
+        phi = np.arctan2(d[:, 1], d[:, 0])
+        Y = np.zeros((d.shape[0], 64))
+        for l in range(8):
+            for m in range(-l, l + 1):
+                am = abs(m)
+                K = np.sqrt((2 * l + 1) / (4 * np.pi) * factorial(l - am) / factorial(l + am))
+                P = lpmv(am, l, d[:, 2])
+                Y[:, l * l + l + m] = K * P if m == 0 else np.sqrt(2) * K * (np.cos(m * phi) if m > 0 else np.sin(am * phi)) * P
+        return Y
+    d = G["sh_dirs"].astype(np.float64)                                   # float32 unit vectors: |d| = 1 +- 4e-8
+    assert np.abs(legendre(d) - G["sh8_y"]).max() < 5e-6
+    dn = d / np.linalg.norm(d, axis=1, keepdims=True)                     # on the sphere proper the two agree to round-off
+    assert np.abs(legendre(dn) - to.sh_polynomials(dn, 8, np.float64)).max() < 1e-13
