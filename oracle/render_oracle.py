@@ -520,7 +520,11 @@ def grid_encode(inputs, embeddings, offsets, S, H, gridtype=0, align_corners=Fal
 
 
 def sh_encode(dirs, degree=4):
-    """shencoder/src/shencoder.cu:27-125 (degree <= 4 restated; the hot path uses 4)."""
+    """shencoder/src/shencoder.cu:27-125.  Bands 0..3 (the hot path uses degree 4) are spelled out here; higher degrees go to
+    train_oracle.sh_polynomials, which carries the whole table."""
+    if degree > 4:
+        from .train_oracle import sh_polynomials
+        return sh_polynomials(dirs, degree, np.float32)
     d = np.asarray(dirs, np.float32)
     x, y, z = d[:, 0], d[:, 1], d[:, 2]
     xy = x * y; xz = x * z; yz = y * z; x2 = x * x; y2 = y * y; z2 = z * z
@@ -537,8 +541,6 @@ def sh_encode(dirs, degree=4):
         o[:, 11] = f32(0.45704579946446572) * y * (f32(1) - f32(5) * z2); o[:, 12] = f32(0.3731763325901154) * z * (f32(5) * z2 - f32(3))
         o[:, 13] = f32(0.45704579946446572) * x * (f32(1) - f32(5) * z2); o[:, 14] = f32(1.4453057213202769) * z * (x2 - y2)
         o[:, 15] = f32(0.59004358992664352) * x * (-x2 + f32(3) * y2)
-    if degree > 4:
-        raise NotImplementedError("oracle restates SH up to degree 4 (the hot path)")
     return o.astype(np.float32)
 
 
