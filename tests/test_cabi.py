@@ -163,3 +163,37 @@ def test_pass_count_and_workspace_are_host_only_queries():
     small = lib.pn_render_workspace_bytes(1000, 100, 1.0, 0.06)
     big = lib.pn_render_workspace_bytes(640000, 2028, 1.0, 0.06)
     assert 0 < small < big < (2 << 30)
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """include/pienerf_b200.h compiles as C99 (no torch, no C++), and a C program linked against the library reaches the entry
+    points: version, host-only queries, and argument refusal (PN_EINVAL + pn_last_error) of compute calls given null pointers."""
+    import shutil
+    import subprocess
+    from pienerf_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "pienerf_b200.h"
+int main(void) {
+    if (pn_version() < 100) return 1;
+    if (pn_render_pass_count(1024) != 7) return 2;
+    if (pn_grid_encode_backward(0, 0, 0, 0, 0, 4, 3, 2, 1, 1.0f, 16, 0, 0, 0, 0, 0, 0, 0) != PN_EINVAL) return 3;
+    if (!strstr(pn_last_error(), "null pointer")) return 4;
+    if (pn_march_rays_train(0, 0, 0, 1.0f, 0.0f, 16, 4, 1, 128, 64, 0, 0, 0, 0, 0, 0, 0, 0, 0) != PN_EINVAL) return 5;
+    if (pn_march_rays_train(0, 0, 0, 1.0f, 0.0f, 16, 0, 1, 128, 64, 0, 0, 0, 0, 0, 0, 0, 0, 0) != PN_OK) return 6;   /* N = 0: nothing to do */
+    if (pn_composite_rays_train_forward(0, 0, 0, 0, 0, 0, 1e-4f, 0, 0, 0, 0) != PN_OK) return 7;
+    if (pn_set_train_block_skip(1) != 1 || pn_set_train_write_mode(1) != 1) return 8;
+    printf("ok %d\n", pn_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lpienerf_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), (out.returncode, out.stdout, out.stderr)
