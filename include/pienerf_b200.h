@@ -230,7 +230,9 @@ int pn_set_prep_mode(int force_multi_kernel);
  * graph captured afterwards keeps the grid sizes it was captured with. */
 int pn_set_render_sm_reserve(int n_sm);
 /* Optional profiling hook: two cudaEvent_t (as void*) that pn_render_deformed records on its stream right
- * around the persistent render kernel (NULL, NULL disables).  Used by bench.py for the roofline line. */
+ * around the persistent render kernel (NULL, NULL disables).  Used by bench.py for the roofline line.
+ * Process-wide and unsynchronised, like the other pn_set_* switches: a measurement aid for one host thread driving one
+ * renderer; set it before the calls it should bracket and clear it before another thread renders. */
 int pn_set_profile_events(void *start_event, void *stop_event);
 /* Same for mode 3: events[2k], events[2k+1] (cudaEvent_t) bracket the k-th field-kernel launch of a frame, k < n/2;
  * the pair of pn_set_profile_events then brackets all passes.  (NULL, 0) disables.  The array must stay alive. */
