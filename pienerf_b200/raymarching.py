@@ -214,11 +214,35 @@ composite_rays_train = _composite_rays_train.apply
 
 # ---- nerf/utils.py pieces of the hot path --------------------------------------------------------------
 
+def select_ray_indices(H, W, N, B=1, error_map=None, patch_size=1, device="cuda"):
+    """Which pixels a training batch looks at (nerf/utils.py:76-114): N uniform random pixels (duplicates allowed), or N // p^2 random
+    p x p patches, or N pixels drawn from the 128 x 128 error map and jittered inside their coarse cell.  Same random draws in the
+    same order as the reference, so a seeded generator on the same device selects the same pixels.  Returns (inds [B, N] int64,
+    inds_coarse [B, N] or None)."""
+    N = min(int(N), H * W)
+    if patch_size > 1:                                   # patches: the error map is ignored
+        num_patch = N // (patch_size ** 2)
+        top = torch.randint(0, H - patch_size, size=[num_patch], device=device)
+        left = torch.randint(0, W - patch_size, size=[num_patch], device=device)
+        di, dj = torch.meshgrid(torch.arange(patch_size, device=device), torch.arange(patch_size, device=device), indexing="ij")
+        rows = (top[:, None] + di.reshape(1, -1)).reshape(-1)
+        cols = (left[:, None] + dj.reshape(1, -1)).reshape(-1)
+        flat = rows * W + cols
+        return flat.expand([B, flat.shape[0]]), None       # the reference expands to [B, N]: N must be a multiple of p^2 there
+    if error_map is None:
+        return torch.randint(0, H * W, size=[N], device=device).expand([B, N]), None
+    coarse = torch.multinomial(error_map.to(device), N, replacement=False)
+    cx, cy = coarse // 128, coarse % 128
+    sx, sy = H / 128, W / 128
+    rows = (cx * sx + torch.rand(B, N, device=device) * sx).long().clamp(max=H - 1)
+    cols = (cy * sy + torch.rand(B, N, device=device) * sy).long().clamp(max=W - 1)
+    return rows * W + cols, coarse
+
+
 @torch.no_grad()
 def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1):
-    """nerf/utils.py:55-138 for the full-frame case the GUI path uses (N=-1, B=1)."""
-    if N > 0 or error_map is not None or patch_size != 1:
-        raise NotImplementedError("ray sub-sampling is training-side; the hot path renders full frames (N=-1)")
+    """nerf/utils.py:55-138 for one camera (B = 1): the full frame the GUI path renders (N = -1) or a training batch of N pixels
+    (uniform, patch-based or error-map driven; `inds` / `inds_coarse` returned as the reference returns them)."""
     poses = torch.as_tensor(poses, dtype=torch.float32)
     if poses.dim() == 3:
         if poses.shape[0] != 1:
@@ -227,6 +251,18 @@ def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1):
     pose_host = poses.detach().cpu().contiguous()
     fx, fy, cx, cy = [float(torch.tensor(float(v), dtype=torch.float32)) for v in intrinsics]
     dev = torch.device("cuda")
+    if N > 0:
+        inds, inds_coarse = select_ray_indices(H, W, N, 1, error_map, patch_size, dev)
+        n = inds.shape[1]
+        cam = torch.cat([pose_host.reshape(-1)[:16], torch.tensor([fx, fy, cx, cy], dtype=torch.float32)]).to(dev)
+        pix = inds[0].to(torch.int32).contiguous()
+        rays_o = torch.empty(1, n, 3, dtype=torch.float32, device=dev)
+        rays_d = torch.empty(1, n, 3, dtype=torch.float32, device=dev)
+        check(lib.pn_get_rays_pix(dptr(cam), int(H), int(W), dptr(pix), int(n), dptr(rays_o), dptr(rays_d), stream_ptr()))
+        out = {"rays_o": rays_o, "rays_d": rays_d, "inds": inds}
+        if inds_coarse is not None:
+            out["inds_coarse"] = inds_coarse
+        return out
     rays_o = torch.empty(1, H * W, 3, dtype=torch.float32, device=dev)
     rays_d = torch.empty(1, H * W, 3, dtype=torch.float32, device=dev)
     import ctypes

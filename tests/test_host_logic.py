@@ -190,3 +190,31 @@ def test_encoder_modules_match_the_reference_classes(kw):
         for m in list(sys.modules):
             if m.split(".")[0] in ("gridencoder", "shencoder", "raymarching") and "pienerf_b200" not in m:
                 sys.modules.pop(m, None)
+
+
+def test_training_ray_selection_matches_the_reference():
+    """get_rays with N > 0 (nerf/utils.py:76-114): uniform, patch-based and error-map driven pixel selection draw the same random
+    numbers in the same order as the reference's function (tests/golden/ref_rays.npz, from the unmodified nerf/utils.py on the CPU),
+    and the reference's rays at those pixels are the full-frame rays of the oracle gathered there (the CUDA kernel that produces
+    them for a pixel list, pn_get_rays_pix, is covered by tests/test_gpu_pipeline.py)."""
+    import os
+    from oracle import render_oracle as ro
+    from pienerf_b200.raymarching import select_ray_indices
+    from pienerf_b200.synthetic import orbit_intrinsics
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_rays.npz"))
+    cases = {"uniform": dict(H=60, W=80, N=500, seed=1), "patch": dict(H=60, W=80, N=512, patch_size=8, seed=2),
+             "errmap": dict(H=300, W=200, N=700, seed=3, error_map=True), "clip": dict(H=12, W=10, N=1000, seed=4)}
+    for tag, c in cases.items():
+        torch.manual_seed(c["seed"])
+        em = torch.rand(1, 128 * 128) if c.get("error_map") else None
+        if em is not None:
+            assert np.array_equal(em.numpy(), G[f"{tag}_error_map"])
+        inds, coarse = select_ray_indices(c["H"], c["W"], c["N"], 1, em, c.get("patch_size", 1), device="cpu")
+        assert np.array_equal(inds.numpy(), G[f"{tag}_inds"]), tag
+        if coarse is not None:
+            assert np.array_equal(coarse.numpy(), G[f"{tag}_inds_coarse"])
+        o, d = ro.get_rays(G["pose"][0], orbit_intrinsics(c["W"], c["H"], 50.0), c["H"], c["W"])
+        sel = G[f"{tag}_inds"][0]
+        assert np.array_equal(o[sel], G[f"{tag}_rays_o"][0]) and np.abs(d[sel] - G[f"{tag}_rays_d"][0]).max() < 3e-7
+    assert G["clip_inds"].shape == (1, 120)                        # N is clipped to H * W
+    assert (np.diff(G["patch_inds"][0].reshape(-1, 8, 8), axis=2) == 1).all()      # 8 x 8 patches of adjacent pixels
