@@ -358,6 +358,7 @@ def test_march_rays_train_full_frame_vs_reference_kernel(bound, dt_gamma):
     noises = torch.rand(N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
     M = N * 24
     from pienerf_b200._lib import lib
+    was_skip, was_mode = lib.pn_set_train_block_skip(1), lib.pn_set_train_write_mode(1)
     res = []
     for m, skip, mode in ((be, 1, 0), (rr, 1, 0), (be, 0, 0), (be, 1, 1), (be, 0, 1)):
         lib.pn_set_train_block_skip(skip); lib.pn_set_train_write_mode(mode)
@@ -365,7 +366,7 @@ def test_march_rays_train_full_frame_vs_reference_kernel(bound, dt_gamma):
         rt = torch.empty(N, 3, dtype=torch.int32, device="cuda"); counter = torch.zeros(2, dtype=torch.int32, device="cuda")
         m.march_rays_train(o, d, bits, bound, dt_gamma, 1024, N, C, 128, M, nears, fars, xyzs, dirs, deltas, rt, counter, noises)
         res.append((xyzs, dirs, deltas, rt, counter))
-    lib.pn_set_train_block_skip(1); lib.pn_set_train_write_mode(0)
+    lib.pn_set_train_block_skip(was_skip); lib.pn_set_train_write_mode(was_mode)
     (x0, d0, l0, r0, c0), (x1, d1, l1, r1, c1) = res[0], res[1]
     for other in res[2:]:                                         # block skipping / the cooperative write pass change nothing, bit for bit
         for a, b in zip(res[0], other):
