@@ -36,42 +36,87 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe).  nvidia-smi takes a few hundred ms to
+    deliver its first sample and the timed region is ~0.1 s, so the sampler is started when the bench process starts and the samples
+    are selected afterwards by their timestamps: those inside [begin(), end()], else the three closest to it (and the line says so)."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
+        self.t0 = self.t1 = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        import atexit
+        atexit.register(self._kill)                                           # never leave the sampler behind if the bench dies early
+
+    def _kill(self):
+        try:
+            if self.p is not None and self.p.poll() is None:
+                self.p.kill()
+        except Exception:
+            pass
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    @classmethod
+    def parse(cls, text, t0=None, t1=None):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        rows = []
+        for line in text.splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 8:
+                continue
+            try:
+                sm, mx = float(t[1]), float(t[2])
+            except ValueError:
+                continue
+            try:
+                import datetime
+                ts = datetime.datetime.strptime(t[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()      # local time, like time.time() once converted
+            except Exception:
+                ts = None
+            rows.append((ts, sm, mx, {n for n, v in zip(cls.REASONS, t[4:8]) if v.lower().startswith("active")}))
+        if not rows:
+            return out
+        sel, window = rows, "every sample of the bench process (no usable timestamps)"
+        stamped = [r for r in rows if r[0] is not None]
+        if stamped and t0 is not None and t1 is not None:
+            inside = [r for r in stamped if t0 <= r[0] <= t1]
+            if inside:
+                sel, window = inside, "timed region"
+            else:
+                near = sorted(stamped, key=lambda r: max(t0 - r[0], r[0] - t1, 0.0))[:3]
+                sel, window = near, "the 3 samples closest to the timed region (none fell inside it)"
+        return {"sm_mhz": float(np.median([r[1] for r in sel])), "sm_max_mhz": float(max(r[2] for r in sel)),
+                "reasons": sorted(set().union(*[r[3] for r in sel])), "samples": len(sel), "window": window}
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        time.sleep(0.05)                                                      # let the sample that covers the end of the window land
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
-        self.f.flush(); self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            t = [x.strip() for x in line.split(",")]
-            if len(t) < 7:
-                continue
-            try:
-                sm.append(float(t[0])); mx.append(float(t[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.f.name)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            self.f.flush(); self.f.seek(0)
+            out = self.parse(self.f.read(), self.t0, self.t1)
+        except Exception:
+            pass
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
         return out
 
 
@@ -120,6 +165,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    sampler = ClockSampler(local) if rank == 0 else None                     # started now, samples selected by timestamp later
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from pienerf_b200 import _lib
@@ -193,12 +239,15 @@ def run_ours(args):
     for _ in range(Wm):
         pipe.frame(pose, intr, to_host=True)
     pipe.drain(); sync_all()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.begin()
     torch.cuda.profiler.start()                                               # `ncu --profile-from-start off` sees exactly the timed frames
     total_ms, wall = timed(args.steps, to_host=False)
     torch.cuda.profiler.stop()
     stats = np.mean(np.asarray([[int(v) for v in sl["stats"].tolist()] for sl in pipe.slots], dtype=np.float64), axis=0)
     e2e_ms, e2e_wall = timed(args.steps, to_host=True)
+    if sampler:
+        sampler.end()
     clocks = sampler.stop() if sampler else None
     pipe.check()
 

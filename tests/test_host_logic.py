@@ -218,3 +218,30 @@ def test_training_ray_selection_matches_the_reference():
         assert np.array_equal(o[sel], G[f"{tag}_rays_o"][0]) and np.abs(d[sel] - G[f"{tag}_rays_d"][0]).max() < 3e-7
     assert G["clip_inds"].shape == (1, 120)                        # N is clipped to H * W
     assert (np.diff(G["patch_inds"][0].reshape(-1, 8, 8), axis=2) == 1).all()      # 8 x 8 patches of adjacent pixels
+
+
+def test_bench_clock_sampler_selects_samples_by_timestamp():
+    """bench.py's nvidia-smi sampler runs for the whole process and picks the samples of the timed region afterwards: inside the
+    window when there are any, else the three closest; throttle reasons only from the selected samples; garbage lines ignored."""
+    import datetime
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    base = datetime.datetime(2026, 10, 17, 12, 0, 0).timestamp()
+
+    def line(dt, sm, mx=1965, hw="Not Active", cap="Not Active"):
+        ts = datetime.datetime.fromtimestamp(base + dt).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return f"{ts}, {sm}, {mx}, 350.12, {hw}, Not Active, Not Active, {cap}"
+    text = "\n".join([line(0.00, 345), line(0.50, 1200, hw="Active"), "garbage", line(1.00, 1965), line(1.02, 1950, cap="Active"),
+                      line(1.04, 1965), line(1.50, 600), "N/A, [N/A], x, y, a, b, c, d"])
+    c = bench.ClockSampler.parse(text, base + 0.99, base + 1.05)
+    assert c == {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3, "window": "timed region"}
+    c = bench.ClockSampler.parse(text, base + 1.10, base + 1.20)                 # nothing inside: the three closest (1.04, 1.02, 1.00)
+    assert c["samples"] == 3 and c["sm_mhz"] == 1965.0 and c["window"].startswith("the 3 samples closest")
+    c = bench.ClockSampler.parse(text)                                           # no window: everything, idle samples included
+    assert c["samples"] == 6 and c["reasons"] == ["hw_slowdown", "sw_power_cap"]
+    assert bench.ClockSampler.parse("") == {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    s = bench.ClockSampler(0)                                                    # no nvidia-smi on this box, or a child to reap: both must be quiet
+    s.begin(); s.end()
+    out = s.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
